@@ -1,0 +1,47 @@
+// Shared device/host helpers for the esn_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "esn_b200.h"
+
+#define ESN_CUDA_TRY(expr)                      \
+    do {                                        \
+        cudaError_t _e = (expr);                \
+        if (_e != cudaSuccess) return (int)_e;  \
+    } while (0)
+
+static inline int esn_launch_status() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+// counter-hash uniform in [0,1) with 24 random bits; the same integer recipe is
+// restated in esn_b200/noise.py so tests can feed the oracle the identical stream.
+__host__ __device__ __forceinline__ uint32_t esn_mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU;
+    x ^= x >> 15; x *= 0x846ca68bU;
+    x ^= x >> 16;
+    return x;
+}
+__host__ __device__ __forceinline__ uint32_t esn_noise_key(uint64_t seed, uint32_t frame, uint32_t row) {
+    uint32_t k = esn_mix32((uint32_t)seed + 0x9E3779B9U * frame);
+    return esn_mix32(k ^ (row * 0x85EBCA6BU + (uint32_t)(seed >> 32)));
+}
+__host__ __device__ __forceinline__ float esn_noise_uniform(uint32_t key, uint32_t neuron) {
+    return (float)(esn_mix32(key + neuron * 0xC2B2AE35U) >> 8) * (1.0f / 16777216.0f);
+}
+
+template <typename T> struct esn_cplx { T re, im; };
+
+template <typename T> __device__ __forceinline__ T esn_tanh(T x);
+template <> __device__ __forceinline__ float esn_tanh<float>(float x) { return tanhf(x); }
+template <> __device__ __forceinline__ double esn_tanh<double>(double x) { return tanh(x); }
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}

@@ -1,0 +1,432 @@
+// OFDM-side kernels of the detection path (north-star subsystem 3): batched
+// shared-memory FFTs fused with their neighbours, pilot LS channel estimation
+// with time-domain MMSE shrinkage, per-subcarrier ZF/MMSE equalisation, hard QAM
+// demapping and bit-error counting.  All HBM-bound: one pass over the data, one
+// CTA per (frame, antenna) FFT.  Reference sites are cited per entry point in
+// include/esn_b200.h (system_model_2/OFDM_MIMO_2-2_NBF_LDPC.py).
+#include <algorithm>
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAX_FFT = 4096;
+constexpr int MAXA = 8;   // max antennas per side in the equaliser
+
+__device__ __forceinline__ void sincospi_t(float x, float *s, float *c) { sincospif(x, s, c); }
+__device__ __forceinline__ void sincospi_t(double x, double *s, double *c) { sincospi(x, s, c); }
+__device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
+__device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
+
+__device__ __forceinline__ int bitrev(int x, int logn) { return (int)(__brev((unsigned)x) >> (32 - logn)); }
+
+// twiddle table tw[k] = exp(-2 pi i k / N), k < N/2
+template <typename T>
+__device__ void fft_make_twiddles(T *twr, T *twi, int N) {
+    for (int k = threadIdx.x; k < N / 2; k += blockDim.x) {
+        T s, c;
+        sincospi_t((T)(-2.0) * (T)k / (T)N, &s, &c);
+        twr[k] = c; twi[k] = s;
+    }
+}
+
+// In-place radix-2 DIT on data already stored in bit-reversed order.  inverse:
+// conjugate twiddles (no scaling here).  Ends with a __syncthreads().
+template <typename T>
+__device__ void fft_inplace(T *re, T *im, const T *twr, const T *twi, int N, int logn, bool inverse) {
+    __syncthreads();
+    for (int s = 1; s <= logn; ++s) {
+        const int half = 1 << (s - 1);
+        const int tstride = N >> s;
+        for (int j = threadIdx.x; j < N / 2; j += blockDim.x) {
+            const int pos = j & (half - 1);
+            const int i0 = ((j >> (s - 1)) << s) + pos, i1 = i0 + half;
+            const T wr = twr[pos * tstride];
+            const T wi = inverse ? -twi[pos * tstride] : twi[pos * tstride];
+            const T xr = re[i1], xi = im[i1];
+            const T tr = wr * xr - wi * xi, ti = wr * xi + wi * xr;
+            const T ur = re[i0], ui = im[i0];
+            re[i0] = ur + tr; im[i0] = ui + ti;
+            re[i1] = ur - tr; im[i1] = ui - ti;
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ int ilog2(int n) { return 31 - __clz(n); }
+
+template <typename T>
+struct Slicer {
+    int L, bits;
+    T s;
+    __device__ Slicer(int qam_bits) {
+        bits = qam_bits;
+        L = 1 << (qam_bits / 2);
+        s = sqrt_t((T)(2.0 * (L * L - 1) / 3.0));
+    }
+    __device__ int level(T v) const {
+        int i = (int)floor((v * s + (T)L) * (T)0.5);
+        return min(max(i, 0), L - 1);
+    }
+    __device__ int index(T re, T im) const { return L * level(re) + level(im); }
+    // distance (constellation units) to the nearest decision boundary on either axis
+    __device__ T boundary_dist(T re, T im) const {
+        T d = (T)1e30;
+        for (int k = 1; k < L; ++k) {
+            const T bnd = (T)(2 * k - L) / s;
+            d = fmin(d, fmin(fabs(re - bnd), fabs(im - bnd)));
+        }
+        return d;
+    }
+};
+
+__device__ void block_add_counts(unsigned long long errs, unsigned long long near,
+                                 unsigned long long *out) {
+    __shared__ unsigned long long s_acc[2];
+    if (threadIdx.x == 0) { s_acc[0] = 0; s_acc[1] = 0; }
+    __syncthreads();
+    for (int s = 16; s > 0; s >>= 1) {
+        errs += __shfl_xor_sync(0xffffffffu, errs, s);
+        near += __shfl_xor_sync(0xffffffffu, near, s);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (errs) atomicAdd(&s_acc[0], errs);
+        if (near) atomicAdd(&s_acc[1], near);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && out) {
+        if (s_acc[0]) atomicAdd(&out[0], s_acc[0]);
+        if (s_acc[1]) atomicAdd(&out[1], s_acc[1]);
+    }
+}
+
+// ---- ESN output -> complex -> FFT -> scale -> slicer -> errors -------------
+template <typename T>
+__global__ void unpack_fft_demap_kernel(const T *__restrict__ y, int rows, int N, int N_t,
+                                        const T *__restrict__ Pi, int pi_stride, int qam_bits,
+                                        T *__restrict__ X_hat, uint8_t *__restrict__ idx,
+                                        const uint8_t *__restrict__ tx_idx, T eps,
+                                        unsigned long long *__restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    T *re = reinterpret_cast<T *>(sm), *im = re + N, *twr = im + N, *twi = twr + N / 2;
+    const int tx = blockIdx.x, b = blockIdx.y, logn = ilog2(N);
+    fft_make_twiddles(twr, twi, N);
+    const T *yb = y + (size_t)b * rows * 2 * N_t;
+    for (int t = threadIdx.x; t < N; t += blockDim.x) {
+        const int r = bitrev(t, logn);
+        re[r] = yb[(size_t)t * 2 * N_t + 2 * tx];
+        im[r] = yb[(size_t)t * 2 * N_t + 2 * tx + 1];
+    }
+    fft_inplace(re, im, twr, twi, N, logn, false);
+    const T scale = (T)1 / ((T)N * sqrt_t(Pi[(size_t)b * pi_stride]));
+    const Slicer<T> sl(qam_bits);
+    unsigned long long errs = 0, near = 0;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        const T xr = re[k] * scale, xi = im[k] * scale;
+        const size_t o = ((size_t)b * N + k) * N_t + tx;
+        if (X_hat) { X_hat[2 * o] = xr; X_hat[2 * o + 1] = xi; }
+        const int id = sl.index(xr, xi);
+        if (idx) idx[o] = (uint8_t)id;
+        if (tx_idx) errs += __popc((unsigned)(id ^ (int)tx_idx[o]));
+        if (eps > (T)0 && sl.boundary_dist(xr, xi) < eps) near += 1;
+    }
+    block_add_counts(errs, near, counts);
+}
+
+// ---- CP removal + FFT of the received samples -------------------------------
+template <typename T>
+__global__ void rx_fft_kernel(const T *__restrict__ y_cp, int N, int cp, int N_r, T *__restrict__ Y) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    T *re = reinterpret_cast<T *>(sm), *im = re + N, *twr = im + N, *twi = twr + N / 2;
+    const int rx = blockIdx.x, b = blockIdx.y, logn = ilog2(N);
+    fft_make_twiddles(twr, twi, N);
+    const T *src = y_cp + (size_t)b * (N + cp) * N_r * 2;
+    for (int t = threadIdx.x; t < N; t += blockDim.x) {
+        const int r = bitrev(t, logn);
+        re[r] = src[((size_t)(cp + t) * N_r + rx) * 2];
+        im[r] = src[((size_t)(cp + t) * N_r + rx) * 2 + 1];
+    }
+    fft_inplace(re, im, twr, twi, N, logn, false);
+    const T scale = (T)1 / (T)N;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        const size_t o = ((size_t)b * N + k) * N_r + rx;
+        Y[2 * o] = re[k] * scale; Y[2 * o + 1] = im[k] * scale;
+    }
+}
+
+// ---- pilot LS + linear inter/extrapolation + time-domain MMSE ---------------
+template <typename T>
+__global__ void chanest_kernel(const T *__restrict__ Y_LS, const T *__restrict__ X_LS, int N, int N_r,
+                               int N_t, const T *__restrict__ Pi, const T *__restrict__ mag, int taps,
+                               T No, T *__restrict__ H_LS, T *__restrict__ H_MMSE) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    T *re = reinterpret_cast<T *>(sm), *im = re + N, *twr = im + N, *twi = twr + N / 2;
+    T *hr = twi + N / 2, *hi = hr + N;                     // comb estimates, then full-band estimate
+    const int tx = blockIdx.x, nr = blockIdx.y, b = blockIdx.z, logn = ilog2(N);
+    fft_make_twiddles(twr, twi, N);
+    const T pi_b = Pi[b], sp = sqrt_t(pi_b);
+    const int M = (N - tx + N_t - 1) / N_t;
+    const T *Yb = Y_LS + (size_t)b * N * N_r * 2;
+    const T *Xb = X_LS + (size_t)b * N * N_t * 2;
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+        const int k = tx + j * N_t;
+        const T yr = Yb[((size_t)k * N_r + nr) * 2], yi = Yb[((size_t)k * N_r + nr) * 2 + 1];
+        const T dr = Xb[((size_t)k * N_t + tx) * 2] * sp + (T)1e-12, di = Xb[((size_t)k * N_t + tx) * 2 + 1] * sp;
+        const T den = dr * dr + di * di;
+        hr[j] = (yr * dr + yi * di) / den;
+        hi[j] = (yi * dr - yr * di) / den;
+    }
+    __syncthreads();
+    // interpolate into (re, im) in natural order, emit H_LS, then bit-reverse for the IFFT
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        int j = (k >= tx) ? (k - tx) / N_t : 0;
+        j = min(max(j, 0), max(M - 2, 0));
+        T vr, vi;
+        if (M >= 2) {
+            const T t = (T)(k - (tx + j * N_t)) / (T)N_t;
+            vr = hr[j] + t * (hr[j + 1] - hr[j]);
+            vi = hi[j] + t * (hi[j + 1] - hi[j]);
+        } else { vr = hr[0]; vi = hi[0]; }
+        const size_t o = (((size_t)b * N + k) * N_r + nr) * N_t + tx;
+        H_LS[2 * o] = vr; H_LS[2 * o + 1] = vi;
+        const int r = bitrev(k, logn);
+        re[r] = vr; im[r] = vi;
+    }
+    fft_inplace(re, im, twr, twi, N, logn, true);          // c_LS * N
+    // shrink the first `taps` taps, zero the rest, forward FFT
+    const T mmse_scaler = (No / pi_b) / ((T)N * (T)0.5);
+    for (int t = threadIdx.x; t < N; t += blockDim.x) {
+        T vr = (T)0, vi = (T)0;
+        if (t < taps) {
+            const T g = (T)1 / ((T)N * (mmse_scaler / mag[t] + (T)1));
+            vr = re[t] * g; vi = im[t] * g;
+        }
+        hr[t] = vr; hi[t] = vi;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < N; t += blockDim.x) {
+        const int r = bitrev(t, logn);
+        re[r] = hr[t]; im[r] = hi[t];
+    }
+    fft_inplace(re, im, twr, twi, N, logn, false);
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        const size_t o = (((size_t)b * N + k) * N_r + nr) * N_t + tx;
+        H_MMSE[2 * o] = re[k]; H_MMSE[2 * o + 1] = im[k];
+    }
+}
+
+// ---- per-subcarrier solve(H^H H + reg I, H^H Y) / power_scale ---------------
+template <typename T>
+__global__ void __launch_bounds__(128)
+equalize_kernel(const T *__restrict__ Y, const T *__restrict__ H, const int *__restrict__ h_index, int B,
+                int N, int N_r, int N_t, const T *__restrict__ reg, int reg_stride,
+                const T *__restrict__ ps, int ps_stride, T *__restrict__ X_hat) {
+    const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (gid >= (size_t)B * N) return;
+    const int b = (int)(gid / N), k = (int)(gid % N);
+    const int hb = h_index ? h_index[b] : b;
+    const T *Hk = H + (((size_t)hb * N + k) * N_r) * N_t * 2;
+    const T *Yk = Y + ((size_t)b * N + k) * N_r * 2;
+    T Gr[MAXA][MAXA], Gi[MAXA][MAXA], br[MAXA], bi[MAXA];
+    for (int i = 0; i < N_t; ++i) {
+        T sr = 0, si = 0;
+        for (int r = 0; r < N_r; ++r) {                    // (H^H Y)_i = sum_r conj(H[r][i]) Y[r]
+            const T hr = Hk[(r * N_t + i) * 2], hi = Hk[(r * N_t + i) * 2 + 1];
+            const T yr = Yk[2 * r], yi = Yk[2 * r + 1];
+            sr += hr * yr + hi * yi; si += hr * yi - hi * yr;
+        }
+        br[i] = sr; bi[i] = si;
+        for (int j = 0; j < N_t; ++j) {                    // G_ij = sum_r conj(H[r][i]) H[r][j]
+            T gr = 0, gi = 0;
+            for (int r = 0; r < N_r; ++r) {
+                const T ar = Hk[(r * N_t + i) * 2], ai = Hk[(r * N_t + i) * 2 + 1];
+                const T cr = Hk[(r * N_t + j) * 2], ci = Hk[(r * N_t + j) * 2 + 1];
+                gr += ar * cr + ai * ci; gi += ar * ci - ai * cr;
+            }
+            Gr[i][j] = gr; Gi[i][j] = gi;
+        }
+        Gr[i][i] += reg[(size_t)b * reg_stride];
+    }
+    // Gaussian elimination with partial pivoting (what LAPACK gesv does)
+    for (int c = 0; c < N_t; ++c) {
+        int piv = c; T best = Gr[c][c] * Gr[c][c] + Gi[c][c] * Gi[c][c];
+        for (int r = c + 1; r < N_t; ++r) {
+            const T v = Gr[r][c] * Gr[r][c] + Gi[r][c] * Gi[r][c];
+            if (v > best) { best = v; piv = r; }
+        }
+        if (piv != c) {
+            for (int j = 0; j < N_t; ++j) {
+                T t = Gr[c][j]; Gr[c][j] = Gr[piv][j]; Gr[piv][j] = t;
+                t = Gi[c][j]; Gi[c][j] = Gi[piv][j]; Gi[piv][j] = t;
+            }
+            T t = br[c]; br[c] = br[piv]; br[piv] = t;
+            t = bi[c]; bi[c] = bi[piv]; bi[piv] = t;
+        }
+        const T inv = (T)1 / best, pr = Gr[c][c] * inv, pi_ = -Gi[c][c] * inv;   // 1/pivot
+        for (int r = c + 1; r < N_t; ++r) {
+            const T fr = Gr[r][c] * pr - Gi[r][c] * pi_, fi = Gr[r][c] * pi_ + Gi[r][c] * pr;
+            for (int j = c; j < N_t; ++j) {
+                Gr[r][j] -= fr * Gr[c][j] - fi * Gi[c][j];
+                Gi[r][j] -= fr * Gi[c][j] + fi * Gr[c][j];
+            }
+            br[r] -= fr * br[c] - fi * bi[c];
+            bi[r] -= fr * bi[c] + fi * br[c];
+        }
+    }
+    const T inv_ps = (T)1 / ps[(size_t)b * ps_stride];
+    T xr[MAXA], xi[MAXA];
+    for (int c = N_t - 1; c >= 0; --c) {
+        T sr = br[c], si = bi[c];
+        for (int j = c + 1; j < N_t; ++j) {
+            sr -= Gr[c][j] * xr[j] - Gi[c][j] * xi[j];
+            si -= Gr[c][j] * xi[j] + Gi[c][j] * xr[j];
+        }
+        const T den = Gr[c][c] * Gr[c][c] + Gi[c][c] * Gi[c][c];
+        xr[c] = (sr * Gr[c][c] + si * Gi[c][c]) / den;
+        xi[c] = (si * Gr[c][c] - sr * Gi[c][c]) / den;
+    }
+    T *out = X_hat + ((size_t)b * N + k) * N_t * 2;
+    for (int c = 0; c < N_t; ++c) { out[2 * c] = xr[c] * inv_ps; out[2 * c + 1] = xi[c] * inv_ps; }
+}
+
+template <typename T>
+__global__ void demap_count_kernel(const T *__restrict__ X_hat, size_t total, int qam_bits,
+                                   uint8_t *__restrict__ idx, const uint8_t *__restrict__ tx_idx, T eps,
+                                   unsigned long long *__restrict__ counts) {
+    const Slicer<T> sl(qam_bits);
+    unsigned long long errs = 0, near = 0;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const T xr = X_hat[2 * e], xi = X_hat[2 * e + 1];
+        const int id = sl.index(xr, xi);
+        if (idx) idx[e] = (uint8_t)id;
+        if (tx_idx) errs += __popc((unsigned)(id ^ (int)tx_idx[e]));
+        if (eps > (T)0 && sl.boundary_dist(xr, xi) < eps) near += 1;
+    }
+    block_add_counts(errs, near, counts);
+}
+
+template <typename K>
+inline int allow_smem(K kern, size_t smem) {
+    if (smem > 48 * 1024)
+        ESN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return 0;
+}
+
+inline bool pow2_ok(int N) { return N >= 2 && N <= MAX_FFT && (N & (N - 1)) == 0; }
+inline int fft_threads(int N) { int t = N / 2; if (t < 32) t = 32; if (t > 512) t = 512; return t; }
+
+}  // namespace
+
+extern "C" int ofdm_unpack_fft_demap(int dtype, const void *y, int B, int rows, int N, int N_t, const void *Pi,
+                                     int pi_stride, int qam_bits, void *X_hat, uint8_t *idx,
+                                     const uint8_t *tx_idx, double boundary_eps, unsigned long long *counts,
+                                     void *stream) {
+    if (!y || !Pi || B <= 0 || N_t <= 0 || rows < N || !pow2_ok(N)) return ESN_E_BADARG;
+    if (qam_bits != 2 && qam_bits != 4 && qam_bits != 6) return ESN_E_BADARG;
+    dim3 grid(N_t, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = dtype == ESN_F64 ? allow_smem(unpack_fft_demap_kernel<double>, 3 * (size_t)N * sizeof(double)) : 0) return rc;
+    if (dtype == ESN_F32)
+        unpack_fft_demap_kernel<float><<<grid, fft_threads(N), 3 * N * sizeof(float), st>>>(
+            (const float *)y, rows, N, N_t, (const float *)Pi, pi_stride, qam_bits, (float *)X_hat, idx, tx_idx,
+            (float)boundary_eps, counts);
+    else if (dtype == ESN_F64)
+        unpack_fft_demap_kernel<double><<<grid, fft_threads(N), 3 * N * sizeof(double), st>>>(
+            (const double *)y, rows, N, N_t, (const double *)Pi, pi_stride, qam_bits, (double *)X_hat, idx, tx_idx,
+            boundary_eps, counts);
+    else return ESN_E_BADARG;
+    return esn_launch_status();
+}
+
+extern "C" int ofdm_rx_fft(int dtype, const void *y_cp, int B, int N, int cp, int N_r, void *Y, void *stream) {
+    if (!y_cp || !Y || B <= 0 || N_r <= 0 || cp < 0 || !pow2_ok(N)) return ESN_E_BADARG;
+    dim3 grid(N_r, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = dtype == ESN_F64 ? allow_smem(rx_fft_kernel<double>, 3 * (size_t)N * sizeof(double)) : 0) return rc;
+    if (dtype == ESN_F32)
+        rx_fft_kernel<float><<<grid, fft_threads(N), 3 * N * sizeof(float), st>>>((const float *)y_cp, N, cp, N_r, (float *)Y);
+    else if (dtype == ESN_F64)
+        rx_fft_kernel<double><<<grid, fft_threads(N), 3 * N * sizeof(double), st>>>((const double *)y_cp, N, cp, N_r, (double *)Y);
+    else return ESN_E_BADARG;
+    return esn_launch_status();
+}
+
+extern "C" int ofdm_chanest(int dtype, const void *Y_LS, const void *X_LS, int B, int N, int N_r, int N_t,
+                            const void *Pi, const void *isi_magnitude, int taps, double No, void *H_LS,
+                            void *H_MMSE, void *stream) {
+    if (!Y_LS || !X_LS || !Pi || !isi_magnitude || !H_LS || !H_MMSE) return ESN_E_BADARG;
+    if (B <= 0 || N_r <= 0 || N_t <= 0 || taps <= 0 || taps > N || !pow2_ok(N)) return ESN_E_BADARG;
+    dim3 grid(N_t, N_r, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = dtype == ESN_F32 ? allow_smem(chanest_kernel<float>, 5 * (size_t)N * sizeof(float)) : 0) return rc;
+    if (dtype == ESN_F32)
+        chanest_kernel<float><<<grid, fft_threads(N), 5 * N * sizeof(float), st>>>(
+            (const float *)Y_LS, (const float *)X_LS, N, N_r, N_t, (const float *)Pi, (const float *)isi_magnitude,
+            taps, (float)No, (float *)H_LS, (float *)H_MMSE);
+    else if (dtype == ESN_F64) {
+        auto kern = chanest_kernel<double>;
+        size_t smem = 5 * (size_t)N * sizeof(double);
+        if (smem > 48 * 1024) ESN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, fft_threads(N), smem, st>>>(
+            (const double *)Y_LS, (const double *)X_LS, N, N_r, N_t, (const double *)Pi,
+            (const double *)isi_magnitude, taps, No, (double *)H_LS, (double *)H_MMSE);
+    } else return ESN_E_BADARG;
+    return esn_launch_status();
+}
+
+extern "C" int ofdm_equalize(int dtype, const void *Y, const void *H, const int32_t *h_index, int B, int N,
+                             int N_r, int N_t, const void *reg, int reg_stride, const void *power_scale,
+                             int ps_stride, void *X_hat, void *stream) {
+    if (!Y || !H || !reg || !power_scale || !X_hat) return ESN_E_BADARG;
+    if (B <= 0 || N <= 0 || N_r <= 0 || N_t <= 0 || N_r > MAXA || N_t > MAXA) return ESN_E_BADARG;
+    const size_t total = (size_t)B * N;
+    const int blocks = (int)((total + 127) / 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == ESN_F32)
+        equalize_kernel<float><<<blocks, 128, 0, st>>>((const float *)Y, (const float *)H, h_index, B, N, N_r, N_t,
+                                                       (const float *)reg, reg_stride, (const float *)power_scale,
+                                                       ps_stride, (float *)X_hat);
+    else if (dtype == ESN_F64)
+        equalize_kernel<double><<<blocks, 128, 0, st>>>((const double *)Y, (const double *)H, h_index, B, N, N_r, N_t,
+                                                        (const double *)reg, reg_stride, (const double *)power_scale,
+                                                        ps_stride, (double *)X_hat);
+    else return ESN_E_BADARG;
+    return esn_launch_status();
+}
+
+extern "C" int ofdm_demap_count(int dtype, const void *X_hat, int B, int N, int N_t, int qam_bits, uint8_t *idx,
+                                const uint8_t *tx_idx, double boundary_eps, unsigned long long *counts,
+                                void *stream) {
+    if (!X_hat || B <= 0 || N <= 0 || N_t <= 0) return ESN_E_BADARG;
+    if (qam_bits != 2 && qam_bits != 4 && qam_bits != 6) return ESN_E_BADARG;
+    const size_t total = (size_t)B * N * N_t;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)(148 * 8));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == ESN_F32)
+        demap_count_kernel<float><<<blocks, 256, 0, st>>>((const float *)X_hat, total, qam_bits, idx, tx_idx, (float)boundary_eps, counts);
+    else if (dtype == ESN_F64)
+        demap_count_kernel<double><<<blocks, 256, 0, st>>>((const double *)X_hat, total, qam_bits, idx, tx_idx, boundary_eps, counts);
+    else return ESN_E_BADARG;
+    return esn_launch_status();
+}
+
+extern "C" int esn_version(void) { return 1; }
+
+extern "C" int esn_device_info(char *name, int n, int *major, int *minor) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return ESN_E_NODEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return ESN_E_NODEVICE;
+    if (name && n > 0) {
+        int i = 0;
+        for (; i < n - 1 && prop.name[i]; ++i) name[i] = prop.name[i];
+        name[i] = 0;
+    }
+    if (major) *major = prop.major;
+    if (minor) *minor = prop.minor;
+    return prop.multiProcessorCount;
+}
+
+// Host-callable copy of the device noise stream (tests pin the numpy restatement to it).
+extern "C" float esn_noise_uniform_host(unsigned long long seed, unsigned frame, unsigned row, unsigned neuron) {
+    return esn_noise_uniform(esn_noise_key(seed, frame, row), neuron);
+}

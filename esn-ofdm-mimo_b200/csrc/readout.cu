@@ -1,0 +1,474 @@
+// Readout training and application in fp64.
+//
+// Replaces `np.linalg.pinv(extended_states[transient:]) @ teachers` of ESN.fit
+// (reference libs/pyESN.py:189-192) by normal equations with lambda = 0 --
+// primal Gram E^T E when rows >= cols, dual Gram E E^T when rows < cols -- a
+// batched blocked Cholesky and the triangular solves, and the train-set
+// prediction E W_out^T (libs/pyESN.py:212-213).  Everything accumulates in
+// fp64: cond(E)^2 reaches 1e9..1e12.
+#include <algorithm>
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ SYRK ----
+// C[i][j] = sum_k A(k,i) A(k,j) over one or more frames, lower-triangular tiles
+// only, mirrored on store.  PRIMAL: A(k,i) = E[row k][col i]; DUAL: A(k,i) =
+// E[row i][col k].  64x64 tile per CTA, 256 threads, 4x4 doubles per thread.
+constexpr int TS = 64, TK = 16;
+
+template <typename TE, bool DUAL>
+__global__ void __launch_bounds__(256)
+syrk_f64_kernel(const TE *__restrict__ ext, int T, int p, int transient, int frames_per_cta,
+                int B, int shared, int accumulate, double *__restrict__ G) {
+    const int m = T - transient;
+    const int n = DUAL ? m : p;              // order of G
+    const int kdim = DUAL ? p : m;           // contraction length
+    // decode lower-triangular tile index
+    int tl = blockIdx.x, ti = 0;
+    while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
+    const int tj = tl - ti * (ti + 1) / 2;
+    const int i0 = ti * TS, j0 = tj * TS;
+
+    __shared__ double As[TK][TS + 2], Bs[TK][TS + 2];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    double acc[4][4] = {};
+    const int fbeg = blockIdx.y * frames_per_cta;
+    const int fend = min(B, fbeg + frames_per_cta);
+
+    for (int b = fbeg; b < fend; ++b) {
+        const TE *E = ext + ((size_t)b * T + transient) * p;   // [m][p]
+        for (int k0 = 0; k0 < kdim; k0 += TK) {
+            // load TK x TS panels of A for the i-tile and the j-tile
+            for (int e = tid; e < TK * TS; e += 256) {
+                int kk, ii;
+                if (DUAL) { kk = e % TK; ii = e / TK; } else { ii = e % TS; kk = e / TS; }
+                const int k = k0 + kk;
+                double va = 0.0, vb = 0.0;
+                if (k < kdim) {
+                    const int ia = i0 + ii, ib = j0 + ii;
+                    if (ia < n) va = (double)(DUAL ? E[(size_t)ia * p + k] : E[(size_t)k * p + ia]);
+                    if (ib < n) vb = (double)(DUAL ? E[(size_t)ib * p + k] : E[(size_t)k * p + ib]);
+                }
+                As[kk][ii] = va;
+                Bs[kk][ii] = vb;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < TK; ++kk) {
+                double a[4], bb[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { a[r] = As[kk][ty + 16 * r]; bb[r] = Bs[kk][tx + 16 * r]; }
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], bb[c], acc[r][c]);
+            }
+            __syncthreads();
+        }
+    }
+    double *Gb = G + (shared ? 0 : (size_t)fbeg * n * n);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = i0 + ty + 16 * r, j = j0 + tx + 16 * c;
+            if (i < n && j < n && j <= i) {
+                if (shared) {
+                    atomicAdd(&Gb[(size_t)i * n + j], acc[r][c]);
+                    if (i != j) atomicAdd(&Gb[(size_t)j * n + i], acc[r][c]);
+                } else if (accumulate) {
+                    Gb[(size_t)i * n + j] += acc[r][c];
+                    if (i != j) Gb[(size_t)j * n + i] += acc[r][c];
+                } else {
+                    Gb[(size_t)i * n + j] = acc[r][c];
+                    Gb[(size_t)j * n + i] = acc[r][c];
+                }
+            }
+        }
+}
+
+// ------------------------------------------------------------------- X^T Y --
+// out(i, o) = sum_r E[r][i] * Y(r, o), r over the m kept rows of each frame.
+// Y is either a scaled teacher (TY raw, scale/shift applied) or a plain fp64
+// matrix [m][n_out] (the dual solution A).  Output strides let the caller write
+// R [p][n_out] or W_out [n_out][p] directly.
+template <typename TE, typename TY>
+__global__ void __launch_bounds__(128)
+xty_f64_kernel(const TE *__restrict__ ext, const TY *__restrict__ Y, int y_is_teacher,
+               const double *__restrict__ t_scale, const double *__restrict__ t_shift,
+               int T, int p, int n_out, int transient, int frames_per_cta, int B, int shared,
+               int accumulate, double *__restrict__ out, int out_si, int out_so, size_t out_sb) {
+    const int m = T - transient;
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    __shared__ double ys[32][ESN_MAX_OUT];
+    double acc[ESN_MAX_OUT] = {};
+    const int fbeg = blockIdx.y * frames_per_cta, fend = min(B, fbeg + frames_per_cta);
+    for (int b = fbeg; b < fend; ++b) {
+        const TE *E = ext + ((size_t)b * T + transient) * p;
+        for (int r0 = 0; r0 < m; r0 += 32) {
+            for (int e = threadIdx.x; e < 32 * n_out; e += 128) {
+                int rr = e / n_out, o = e - rr * n_out, r = r0 + rr;
+                double v = 0.0;
+                if (r < m) {
+                    if (y_is_teacher)
+                        v = (double)Y[((size_t)b * T + transient + r) * n_out + o] * t_scale[o] + t_shift[o];
+                    else
+                        v = (double)Y[((size_t)b * m + r) * n_out + o];
+                }
+                ys[rr][o] = v;
+            }
+            __syncthreads();
+            if (i < p) {
+                const int rmax = min(32, m - r0);
+                for (int rr = 0; rr < rmax; ++rr) {
+                    const double e = (double)E[(size_t)(r0 + rr) * p + i];
+#pragma unroll
+                    for (int o = 0; o < ESN_MAX_OUT; ++o)
+                        if (o < n_out) acc[o] = fma(e, ys[rr][o], acc[o]);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (i < p) {
+        double *ob = out + (shared ? 0 : (size_t)fbeg * out_sb);
+#pragma unroll
+        for (int o = 0; o < ESN_MAX_OUT; ++o)
+            if (o < n_out) {
+                double *dst = &ob[(size_t)i * out_si + (size_t)o * out_so];
+                if (shared) atomicAdd(dst, acc[o]);
+                else if (accumulate) *dst += acc[o];
+                else *dst = acc[o];
+            }
+    }
+}
+
+template <typename TY>
+__global__ void scaled_teacher_rows_kernel(const TY *__restrict__ teacher, const double *__restrict__ t_scale,
+                                           const double *__restrict__ t_shift, int B, int T, int n_out,
+                                           int transient, double *__restrict__ rhs) {
+    const int m = T - transient;
+    const size_t total = (size_t)B * m * n_out;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        int o = (int)(e % n_out);
+        size_t br = e / n_out;
+        int r = (int)(br % m);
+        size_t b = br / m;
+        rhs[e] = (double)teacher[(b * T + transient + r) * n_out + o] * t_scale[o] + t_shift[o];
+    }
+}
+
+// -------------------------------------------------------------- Cholesky ----
+// One CTA per problem, matrix in global memory (L2-resident), right-looking
+// blocked factorisation with NB = 32; then forward and backward substitution
+// for n_rhs <= ESN_MAX_OUT right-hand sides.  Lower triangle is used/written.
+constexpr int NB = 32;
+constexpr int CH_THREADS = 256;
+
+__global__ void __launch_bounds__(CH_THREADS)
+cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_all, int n, int n_rhs,
+                          int *__restrict__ info_all) {
+    double *A = Gall + (size_t)blockIdx.x * n * n;
+    double *Bm = rhs_all + (size_t)blockIdx.x * n * n_rhs;
+    __shared__ double D[NB][NB + 1];          // diagonal block / its factor
+    __shared__ double Pn[64][NB + 1];         // panel rows of the i-tile
+    __shared__ double Qn[64][NB + 1];         // panel rows of the j-tile
+    __shared__ int s_info;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_info = 0;
+    __syncthreads();
+
+    for (int k0 = 0; k0 < n; k0 += NB) {
+        const int nb = min(NB, n - k0);
+        // 1. diagonal block -> shared, unblocked Cholesky
+        for (int e = tid; e < NB * NB; e += CH_THREADS) {
+            int r = e / NB, c = e % NB;
+            D[r][c] = (r < nb && c < nb && c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
+        }
+        __syncthreads();
+        for (int j = 0; j < nb; ++j) {
+            if (tid == 0) {
+                double d = D[j][j];
+                if (!(d > 0.0)) {
+                    if (s_info == 0) s_info = k0 + j + 1;
+                    d = nan("");
+                }
+                D[j][j] = sqrt(d);
+            }
+            __syncthreads();
+            const double djj = D[j][j];
+            if (tid > j && tid < nb) D[tid][j] /= djj;
+            __syncthreads();
+            // trailing update of the block: D[r][c] -= D[r][j] D[c][j], j < c <= r
+            for (int e = tid; e < nb * nb; e += CH_THREADS) {
+                int r = e / nb, c = e % nb;
+                if (c > j && r >= c) D[r][c] -= D[r][j] * D[c][j];
+            }
+            __syncthreads();
+        }
+        for (int e = tid; e < nb * nb; e += CH_THREADS) {
+            int r = e / nb, c = e % nb;
+            if (c <= r) A[(size_t)(k0 + r) * n + k0 + c] = D[r][c];
+        }
+        // 2. panel: rows below the block, A[i, k0:k0+nb] <- A[i, k0:k0+nb] L_kk^-T (one row per thread)
+        const int below = n - (k0 + nb);
+        for (int i = tid; i < below; i += CH_THREADS) {
+            double *row = A + (size_t)(k0 + nb + i) * n + k0;
+            double x[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) x[c] = c < nb ? row[c] : 0.0;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                if (c < nb) {
+                    double s = x[c];
+#pragma unroll
+                    for (int q = 0; q < NB; ++q)
+                        if (q < c) s -= x[q] * D[c][q];
+                    x[c] = s / D[c][c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NB; ++c)
+                if (c < nb) row[c] = x[c];
+        }
+        __syncthreads();
+        // 3. trailing update A[i][j] -= sum_c L[i][c] L[j][c], i >= j >= k0+nb, 64x64 tiles
+        const int t0 = k0 + nb;
+        const int ntile = (below + 63) / 64;
+        const int tx = tid & 15, ty = tid >> 4;
+        for (int ti = 0; ti < ntile; ++ti) {
+            for (int e = tid; e < 64 * NB; e += CH_THREADS) {
+                int r = e / NB, c = e % NB, gi = t0 + ti * 64 + r;
+                Pn[r][c] = (gi < n && c < nb) ? A[(size_t)gi * n + k0 + c] : 0.0;
+            }
+            for (int tj = 0; tj <= ti; ++tj) {
+                __syncthreads();
+                for (int e = tid; e < 64 * NB; e += CH_THREADS) {
+                    int r = e / NB, c = e % NB, gj = t0 + tj * 64 + r;
+                    Qn[r][c] = (gj < n && c < nb) ? A[(size_t)gj * n + k0 + c] : 0.0;
+                }
+                __syncthreads();
+                double acc[4][4] = {};
+#pragma unroll
+                for (int c = 0; c < NB; ++c) {
+                    double a[4], b[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) { a[r] = Pn[ty + 16 * r][c]; b[r] = Qn[tx + 16 * r][c]; }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[r][q] = fma(a[r], b[q], acc[r][q]);
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        int gi = t0 + ti * 64 + ty + 16 * r, gj = t0 + tj * 64 + tx + 16 * q;
+                        if (gi < n && gj <= gi) A[(size_t)gi * n + gj] -= acc[r][q];
+                    }
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+
+    // ---- forward substitution L Z = B (blocked by NB) ----
+    for (int k0 = 0; k0 < n; k0 += NB) {
+        const int nb = min(NB, n - k0);
+        for (int e = tid; e < NB * NB; e += CH_THREADS) {
+            int r = e / NB, c = e % NB;
+            D[r][c] = (r < nb && c < nb && c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
+        }
+        __syncthreads();
+        if (tid < n_rhs) {     // one thread per right-hand side solves the nb x nb block
+            double z[NB];
+            for (int r = 0; r < nb; ++r) {
+                double s = Bm[(size_t)(k0 + r) * n_rhs + tid];
+                for (int c = 0; c < r; ++c) s -= D[r][c] * z[c];
+                z[r] = s / D[r][r];
+            }
+            for (int r = 0; r < nb; ++r) Pn[r][tid] = z[r];
+            for (int r = 0; r < nb; ++r) Bm[(size_t)(k0 + r) * n_rhs + tid] = z[r];
+        }
+        __syncthreads();
+        // update the rows below: B[i] -= L[i, k0:k0+nb] z
+        const int below = n - (k0 + nb);
+        for (int e = tid; e < below * n_rhs; e += CH_THREADS) {
+            int i = e / n_rhs, o = e - i * n_rhs;
+            const double *Lrow = A + (size_t)(k0 + nb + i) * n + k0;
+            double s = 0.0;
+            for (int c = 0; c < nb; ++c) s = fma(Lrow[c], Pn[c][o], s);
+            Bm[(size_t)(k0 + nb + i) * n_rhs + o] -= s;
+        }
+        __syncthreads();
+    }
+    // ---- backward substitution L^T X = Z ----
+    const int nblk = (n + NB - 1) / NB;
+    for (int kb = nblk - 1; kb >= 0; --kb) {
+        const int k0 = kb * NB, nb = min(NB, n - k0);
+        for (int e = tid; e < NB * NB; e += CH_THREADS) {
+            int r = e / NB, c = e % NB;
+            D[r][c] = (r < nb && c < nb && c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
+        }
+        __syncthreads();
+        if (tid < n_rhs) {
+            double x[NB];
+            for (int r = nb - 1; r >= 0; --r) {
+                double s = Bm[(size_t)(k0 + r) * n_rhs + tid];
+                for (int c = r + 1; c < nb; ++c) s -= D[c][r] * x[c];
+                x[r] = s / D[r][r];
+            }
+            for (int r = 0; r < nb; ++r) Pn[r][tid] = x[r];
+            for (int r = 0; r < nb; ++r) Bm[(size_t)(k0 + r) * n_rhs + tid] = x[r];
+        }
+        __syncthreads();
+        // rows above: B[i] -= sum_c L[k0+c][i] x[c], i < k0
+        for (int e = tid; e < k0 * n_rhs; e += CH_THREADS) {
+            int i = e / n_rhs, o = e - i * n_rhs;
+            double s = 0.0;
+            for (int c = 0; c < nb; ++c) s = fma(A[(size_t)(k0 + c) * n + i], Pn[c][o], s);
+            Bm[(size_t)i * n_rhs + o] -= s;
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && info_all) info_all[blockIdx.x] = s_info;
+}
+
+// ---------------------------------------------------------- apply readout ---
+template <typename T>
+__global__ void __launch_bounds__(256)
+apply_readout_kernel(const T *__restrict__ ext, const T *__restrict__ W_out, const int *__restrict__ group_ids,
+                     const T *__restrict__ t_scale, const T *__restrict__ t_shift, size_t rows, int Trows, int p,
+                     int n_out, T *__restrict__ pred) {
+    const int lane = threadIdx.x & 31;
+    const size_t row = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int b = (int)(row / Trows);
+    const int g = group_ids ? group_ids[b] : 0;
+    const T *e = ext + row * p;
+    const T *w = W_out + (size_t)g * n_out * p;
+    T acc[ESN_MAX_OUT];
+#pragma unroll
+    for (int o = 0; o < ESN_MAX_OUT; ++o) acc[o] = (T)0;
+    for (int k = lane; k < p; k += 32) {
+        const T ev = e[k];
+#pragma unroll
+        for (int o = 0; o < ESN_MAX_OUT; ++o)
+            if (o < n_out) acc[o] = fma(w[(size_t)o * p + k], ev, acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < ESN_MAX_OUT; ++o) {
+        if (o < n_out) {
+            T v = acc[o];
+            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+            if (lane == 0) pred[row * n_out + o] = (v - t_shift[o]) / t_scale[o];
+        }
+    }
+}
+
+__global__ void transpose_rhs_kernel(const double *__restrict__ rhs, int B, int p, int n_out,
+                                     double *__restrict__ W_out) {
+    const size_t total = (size_t)B * p * n_out;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        int i = (int)(e % p);
+        size_t bo = e / p;
+        int o = (int)(bo % n_out);
+        size_t b = bo / n_out;
+        W_out[e] = rhs[(b * p + i) * n_out + o];
+    }
+}
+
+}  // namespace
+
+extern "C" int esn_gram_f64(const void *ext, int ext_dtype, const void *teacher, int teacher_dtype,
+                            const double *t_scale, const double *t_shift, int B, int T, int p,
+                            int n_out, int transient, int dual, int shared, int accumulate,
+                            double *G, double *rhs, void *stream) {
+    if (!ext || !teacher || !t_scale || !t_shift || !G || !rhs) return ESN_E_BADARG;
+    if (B <= 0 || p <= 0 || n_out <= 0 || n_out > ESN_MAX_OUT || transient < 0 || transient >= T)
+        return ESN_E_BADARG;
+    if (dual && (shared || accumulate)) return ESN_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int m = T - transient;
+    const int n = dual ? m : p;
+    const int nt = (n + TS - 1) / TS;
+    // shared readout: spread the frames over ~4 waves of CTAs, each sums its frames in registers
+    int fpc = 1;
+    if (shared) {
+        int tiles = nt * (nt + 1) / 2;
+        int want_y = max(1, (148 * 4) / tiles);
+        fpc = (B + want_y - 1) / want_y;
+    }
+    dim3 grid(nt * (nt + 1) / 2, (B + fpc - 1) / fpc);
+    const bool f32 = ext_dtype == ESN_F32;
+    if (shared && !accumulate) {
+        ESN_CUDA_TRY(cudaMemsetAsync(G, 0, sizeof(double) * (size_t)n * n, st));
+        ESN_CUDA_TRY(cudaMemsetAsync(rhs, 0, sizeof(double) * (size_t)p * n_out, st));
+    }
+#define SYRK(TE, D) syrk_f64_kernel<TE, D><<<grid, 256, 0, st>>>((const TE *)ext, T, p, transient, fpc, B, shared, accumulate, G)
+    if (dual) { if (f32) SYRK(float, true); else SYRK(double, true); }
+    else      { if (f32) SYRK(float, false); else SYRK(double, false); }
+#undef SYRK
+    int rc = esn_launch_status();
+    if (rc) return rc;
+    if (dual) {
+        const size_t total = (size_t)B * m * n_out;
+        int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)(4096));
+        if (teacher_dtype == ESN_F32)
+            scaled_teacher_rows_kernel<float><<<blocks, 256, 0, st>>>((const float *)teacher, t_scale, t_shift, B, T, n_out, transient, rhs);
+        else
+            scaled_teacher_rows_kernel<double><<<blocks, 256, 0, st>>>((const double *)teacher, t_scale, t_shift, B, T, n_out, transient, rhs);
+    } else {
+        dim3 g2((p + 127) / 128, (B + fpc - 1) / fpc);
+#define XTY(TE, TY) xty_f64_kernel<TE, TY><<<g2, 128, 0, st>>>((const TE *)ext, (const TY *)teacher, 1, t_scale, t_shift, T, p, n_out, transient, fpc, B, shared, accumulate, rhs, n_out, 1, (size_t)p * n_out)
+        if (f32) { if (teacher_dtype == ESN_F32) XTY(float, float); else XTY(float, double); }
+        else     { if (teacher_dtype == ESN_F32) XTY(double, float); else XTY(double, double); }
+#undef XTY
+    }
+    return esn_launch_status();
+}
+
+extern "C" int esn_cholesky_solve_f64(double *G, double *rhs, int batch, int n, int n_rhs, int32_t *info,
+                                      void *stream) {
+    if (!G || !rhs || batch <= 0 || n <= 0 || n_rhs <= 0 || n_rhs > ESN_MAX_OUT) return ESN_E_BADARG;
+    cholesky_solve_f64_kernel<<<batch, CH_THREADS, 0, (cudaStream_t)stream>>>(G, rhs, n, n_rhs, info);
+    return esn_launch_status();
+}
+
+extern "C" int esn_readout_from_dual_f64(const void *ext, int ext_dtype, const double *A, int B, int T,
+                                         int p, int n_out, int transient, double *W_out, void *stream) {
+    if (!ext || !A || !W_out || B <= 0 || n_out <= 0 || n_out > ESN_MAX_OUT) return ESN_E_BADARG;
+    dim3 g2((p + 127) / 128, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ext_dtype == ESN_F32)
+        xty_f64_kernel<float, double><<<g2, 128, 0, st>>>((const float *)ext, A, 0, nullptr, nullptr, T, p, n_out, transient, 1, B, 0, 0, W_out, 1, p, (size_t)p * n_out);
+    else
+        xty_f64_kernel<double, double><<<g2, 128, 0, st>>>((const double *)ext, A, 0, nullptr, nullptr, T, p, n_out, transient, 1, B, 0, 0, W_out, 1, p, (size_t)p * n_out);
+    return esn_launch_status();
+}
+
+extern "C" int esn_transpose_rhs_f64(const double *rhs, int B, int p, int n_out, double *W_out, void *stream) {
+    if (!rhs || !W_out || B <= 0) return ESN_E_BADARG;
+    const size_t total = (size_t)B * p * n_out;
+    int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)(4096));
+    transpose_rhs_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rhs, B, p, n_out, W_out);
+    return esn_launch_status();
+}
+
+extern "C" int esn_apply_readout(int dtype, const void *ext, const void *W_out, const int32_t *group_ids,
+                                 const void *t_scale, const void *t_shift, int B, int T, int p, int n_out,
+                                 void *pred, void *stream) {
+    if (!ext || !W_out || !t_scale || !t_shift || !pred || B <= 0 || T <= 0 || n_out > ESN_MAX_OUT)
+        return ESN_E_BADARG;
+    const size_t rows = (size_t)B * T;
+    const int blocks = (int)((rows + 7) / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == ESN_F32)
+        apply_readout_kernel<float><<<blocks, 256, 0, st>>>((const float *)ext, (const float *)W_out, group_ids, (const float *)t_scale, (const float *)t_shift, rows, T, p, n_out, (float *)pred);
+    else if (dtype == ESN_F64)
+        apply_readout_kernel<double><<<blocks, 256, 0, st>>>((const double *)ext, (const double *)W_out, group_ids, (const double *)t_scale, (const double *)t_shift, rows, T, p, n_out, (double *)pred);
+    else
+        return ESN_E_BADARG;
+    return esn_launch_status();
+}

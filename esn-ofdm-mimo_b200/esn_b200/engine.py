@@ -1,0 +1,250 @@
+"""Batched ESN engine on one B200: the host-side mirror of the reference's
+`pyESN.ESN` numerics, operating on torch CUDA tensors and calling the C-ABI
+kernels (include/esn_b200.h) through ctypes.  torch is used for device memory
+and streams only.
+
+Frames are independent: `predict()` never writes the ESN's state back
+(reference libs/pyESN.py:218-255), so B frames (and G trained readouts, one per
+channel realisation) are stepped in one launch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ESN_F32, ESN_F64, MODE_HARVEST, MODE_PREDICT, EsnB200Error, check, ptr
+
+_TORCH = {ESN_F32: torch.float32, ESN_F64: torch.float64}
+_CODE = {torch.float32: ESN_F32, torch.float64: ESN_F64, "fp32": ESN_F32, "fp64": ESN_F64,
+         "f32": ESN_F32, "f64": ESN_F64}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise EsnB200Error("no CUDA device: the esn_b200 engine has no CPU fallback")
+
+
+def dtype_code(precision):
+    try:
+        return _CODE[precision]
+    except KeyError:
+        raise ValueError(f"precision must be 'fp32' or 'fp64', got {precision!r}")
+
+
+def _vec(v, n, default, device):
+    """None / scalar / length-n vector -> fp64 device vector of length n."""
+    if v is None:
+        a = np.full(n, default, dtype=np.float64)
+    else:
+        a = np.asarray(v, dtype=np.float64)
+        if a.ndim == 0:
+            a = np.full(n, float(a), dtype=np.float64)
+        a = np.ascontiguousarray(a.reshape(n))
+    return torch.from_numpy(a).to(device)
+
+
+class Reservoir:
+    """Device-resident reservoir weights and the affine I/O maps of one ESN
+    (reference libs/pyESN.py:93-152).  Weights are uploaded once, in the
+    augmented transposed layout the kernels stream:
+    Wt_aug[K_aug_pad][N_pad] = [W^T; W_in^T; W_fb^T; 0]."""
+
+    def __init__(self, W, W_in, W_fb, input_scaling=None, input_shift=None,
+                 teacher_scaling=None, teacher_shift=None, noise=0.0,
+                 teacher_forcing=True, device="cuda"):
+        _require_cuda()
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        W = np.asarray(W, dtype=np.float64)
+        W_in = np.asarray(W_in, dtype=np.float64)
+        W_fb = np.asarray(W_fb, dtype=np.float64)
+        self.N, self.n_in, self.n_out = W.shape[0], W_in.shape[1], W_fb.shape[1]
+        if self.n_out > _lib.ESN_MAX_OUT or self.n_in > _lib.ESN_MAX_IN:
+            raise EsnB200Error(f"n_inputs <= {_lib.ESN_MAX_IN} and n_outputs <= {_lib.ESN_MAX_OUT} required")
+        self.P = self.N + self.n_in
+        npad, kpad = C.c_int(), C.c_int()
+        check(self.lib.esn_pad_sizes(self.N, self.n_in, self.n_out, C.byref(npad), C.byref(kpad)), "esn_pad_sizes")
+        self.N_pad, self.K_aug_pad = npad.value, kpad.value
+        self.noise = float(noise)
+        self.teacher_forcing = bool(teacher_forcing)
+        wt = np.zeros((self.K_aug_pad, self.N_pad), dtype=np.float64)
+        wt[:self.N, :self.N] = W.T
+        wt[self.N:self.P, :self.N] = W_in.T
+        if self.teacher_forcing:
+            wt[self.P:self.P + self.n_out, :self.N] = W_fb.T
+        self._wt = {ESN_F64: torch.from_numpy(wt).to(self.device)}
+        self._wt[ESN_F32] = self._wt[ESN_F64].to(torch.float32)
+        self._aff = {ESN_F64: dict(
+            in_scale=_vec(input_scaling, self.n_in, 1.0, self.device),
+            in_shift=_vec(input_shift, self.n_in, 0.0, self.device),
+            t_scale=_vec(teacher_scaling, self.n_out, 1.0, self.device),
+            t_shift=_vec(teacher_shift, self.n_out, 0.0, self.device))}
+        self._aff[ESN_F32] = {k: v.to(torch.float32) for k, v in self._aff[ESN_F64].items()}
+
+    # ------------------------------------------------------------------ run --
+    def _run(self, mode, code, inputs, teachers=None, W_out=None, group_ids=None, x0=None,
+             y0=None, noise_uniforms=None, seed=0, transient=0, want_ext=False):
+        td = _TORCH[code]
+        inputs = self._as(inputs, td, 3)
+        B, T, n_in = inputs.shape
+        if n_in != self.n_in:
+            raise ValueError(f"inputs have {n_in} columns, ESN has n_inputs={self.n_in}")
+        a = _lib.RecurrenceArgs()
+        a.dtype, a.mode, a.B, a.T = code, mode, B, T
+        a.N, a.n_in, a.n_out = self.N, self.n_in, self.n_out
+        a.N_pad, a.K_aug_pad = self.N_pad, self.K_aug_pad
+        a.transient, a.feedback = int(transient), int(self.teacher_forcing)
+        a.noise_amp, a.seed = self.noise, int(seed) & 0xFFFFFFFFFFFFFFFF
+        aff = self._aff[code]
+        keep = [inputs]
+        a.Wt_aug, a.inp = ptr(self._wt[code]), ptr(inputs)
+        a.in_scale, a.in_shift = ptr(aff["in_scale"]), ptr(aff["in_shift"])
+        a.t_scale, a.t_shift = ptr(aff["t_scale"]), ptr(aff["t_shift"])
+        steps = T if mode == MODE_PREDICT else T - 1
+        if noise_uniforms is not None:
+            noise_uniforms = self._as(noise_uniforms, td, 3)
+            if tuple(noise_uniforms.shape) != (B, steps, self.N):
+                raise ValueError(f"noise_uniforms must be [{B},{steps},{self.N}]")
+            a.noise_uniforms = ptr(noise_uniforms)
+            keep.append(noise_uniforms)
+        ext = None
+        if mode == MODE_HARVEST or want_ext:
+            ext = torch.empty((B, T, self.P), dtype=td, device=self.device)
+            a.ext_out = ptr(ext)
+        ws = torch.empty((B, self.N), dtype=td, device=self.device)
+        a.workspace = ptr(ws)
+        y = None
+        if mode == MODE_HARVEST:
+            teachers = self._as(teachers, td, 3)
+            if tuple(teachers.shape) != (B, T, self.n_out):
+                raise ValueError(f"teachers must be [{B},{T},{self.n_out}]")
+            a.teacher = ptr(teachers)
+            keep.append(teachers)
+        else:
+            W_out = self._as(W_out, td, 3)
+            if W_out.shape[1:] != (self.n_out, self.P):
+                raise ValueError(f"W_out must be [G,{self.n_out},{self.P}]")
+            a.W_out, a.n_groups = ptr(W_out), W_out.shape[0]
+            keep.append(W_out)
+            if group_ids is not None:
+                group_ids = group_ids.to(device=self.device, dtype=torch.int32).contiguous()
+                a.group_ids = ptr(group_ids)
+                keep.append(group_ids)
+            elif W_out.shape[0] != 1:
+                raise ValueError("group_ids required when W_out holds more than one readout")
+            if x0 is not None:
+                x0 = self._as(x0, td, 2)
+                a.x0 = ptr(x0)
+                keep.append(x0)
+            if y0 is not None:
+                y0 = self._as(y0, td, 2)
+                a.y0 = ptr(y0)
+                keep.append(y0)
+            y = torch.empty((B, T - int(transient), self.n_out), dtype=td, device=self.device)
+            a.y_out = ptr(y)
+        check(self.lib.esn_recurrence_run(C.byref(a), _stream()), "esn_recurrence_run")
+        return ext, y
+
+    def _as(self, t, td, ndim):
+        if isinstance(t, np.ndarray):
+            t = torch.from_numpy(np.ascontiguousarray(t))
+        t = t.to(device=self.device, dtype=td)
+        while t.dim() < ndim:
+            t = t.unsqueeze(0)
+        return t.contiguous()
+
+    def harvest(self, inputs, teachers, precision="fp64", noise_uniforms=None, seed=0):
+        """Teacher-forced harvesting (libs/pyESN.py:179-182).  Returns the
+        extended states E [B, T, N+n_in] = [x_n, u_n] (libs/pyESN.py:189)."""
+        ext, _ = self._run(MODE_HARVEST, dtype_code(precision), inputs, teachers=teachers,
+                           noise_uniforms=noise_uniforms, seed=seed)
+        return ext
+
+    def predict(self, inputs, W_out, transient=0, group_ids=None, x0=None, y0=None,
+                precision="fp32", noise_uniforms=None, seed=0, return_ext=False):
+        """Free-running prediction (libs/pyESN.py:243-255) of B frames, frame b
+        using readout W_out[group_ids[b]].  Returns y [B, T-transient, n_out]
+        in teacher units (and E if return_ext)."""
+        ext, y = self._run(MODE_PREDICT, dtype_code(precision), inputs, W_out=W_out,
+                           group_ids=group_ids, x0=x0, y0=y0, noise_uniforms=noise_uniforms,
+                           seed=seed, transient=transient, want_ext=return_ext)
+        return (y, ext) if return_ext else y
+
+    # -------------------------------------------------------------- readout --
+    def train_readout(self, ext, teachers, transient=0, shared=False):
+        """fp64 normal equations with lambda = 0 + Cholesky, reproducing the
+        reference's pinv solution (libs/pyESN.py:191-192).  One
+        readout per frame, or ONE readout over all frames when `shared`.
+        Returns (W_out [G, n_out, P] fp64, info [G] int32)."""
+        B, T, P = ext.shape
+        m = T - int(transient)
+        dual = (m < P) and not shared
+        G_n = m if dual else P
+        nprob = 1 if shared else B
+        teachers = teachers.to(self.device).contiguous()
+        if teachers.dim() == 2:
+            teachers = teachers.unsqueeze(0)
+        aff = self._aff[ESN_F64]
+        G = torch.empty((nprob, G_n, G_n), dtype=torch.float64, device=self.device)
+        rhs = torch.empty((nprob, G_n, self.n_out), dtype=torch.float64, device=self.device)
+        check(self.lib.esn_gram_f64(ptr(ext), _CODE[ext.dtype], ptr(teachers), _CODE[teachers.dtype],
+                                    ptr(aff["t_scale"]), ptr(aff["t_shift"]), B, T, P, self.n_out,
+                                    int(transient), int(dual), int(shared), 0, ptr(G), ptr(rhs), _stream()),
+              "esn_gram_f64")
+        return self.solve_readout(G, rhs, ext if dual else None, transient)
+
+    def gram(self, ext, teachers, transient=0):
+        """Shared-readout partial sums (G [P,P], R [P,n_out]) of this rank's
+        frames; allreduce them over ranks, then `solve_readout`."""
+        B, T, P = ext.shape
+        teachers = teachers.to(self.device).contiguous()
+        aff = self._aff[ESN_F64]
+        G = torch.empty((1, P, P), dtype=torch.float64, device=self.device)
+        rhs = torch.empty((1, P, self.n_out), dtype=torch.float64, device=self.device)
+        check(self.lib.esn_gram_f64(ptr(ext), _CODE[ext.dtype], ptr(teachers), _CODE[teachers.dtype],
+                                    ptr(aff["t_scale"]), ptr(aff["t_shift"]), B, T, P, self.n_out,
+                                    int(transient), 0, 1, 0, ptr(G), ptr(rhs), _stream()), "esn_gram_f64")
+        return G, rhs
+
+    def solve_readout(self, G, rhs, ext_for_dual=None, transient=0):
+        nprob, n, _ = G.shape
+        info = torch.zeros((nprob,), dtype=torch.int32, device=self.device)
+        G = G.contiguous()
+        rhs = rhs.contiguous()
+        check(self.lib.esn_cholesky_solve_f64(ptr(G), ptr(rhs), nprob, n, self.n_out, ptr(info), _stream()),
+              "esn_cholesky_solve_f64")
+        W_out = torch.empty((nprob, self.n_out, self.P), dtype=torch.float64, device=self.device)
+        if ext_for_dual is not None:
+            B, T, P = ext_for_dual.shape
+            check(self.lib.esn_readout_from_dual_f64(ptr(ext_for_dual), _CODE[ext_for_dual.dtype], ptr(rhs),
+                                                     B, T, P, self.n_out, int(transient), ptr(W_out), _stream()),
+                  "esn_readout_from_dual_f64")
+        else:
+            check(self.lib.esn_transpose_rhs_f64(ptr(rhs), nprob, self.P, self.n_out, ptr(W_out), _stream()),
+                  "esn_transpose_rhs_f64")
+        return W_out, info
+
+    def apply_readout(self, ext, W_out, group_ids=None):
+        """Train-set prediction (libs/pyESN.py:212-213) on all T rows."""
+        B, T, P = ext.shape
+        code = _CODE[ext.dtype]
+        W_out = W_out.to(device=self.device, dtype=ext.dtype).contiguous()
+        if W_out.dim() == 2:
+            W_out = W_out.unsqueeze(0)
+        if group_ids is None and W_out.shape[0] == B and B > 1:
+            group_ids = torch.arange(B, dtype=torch.int32, device=self.device)
+        if group_ids is not None:
+            group_ids = group_ids.to(device=self.device, dtype=torch.int32).contiguous()
+        aff = self._aff[code]
+        pred = torch.empty((B, T, self.n_out), dtype=ext.dtype, device=self.device)
+        check(self.lib.esn_apply_readout(code, ptr(ext), ptr(W_out), ptr(group_ids), ptr(aff["t_scale"]),
+                                         ptr(aff["t_shift"]), B, T, P, self.n_out, ptr(pred), _stream()),
+              "esn_apply_readout")
+        return pred

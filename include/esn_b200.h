@@ -1,0 +1,184 @@
+/*
+ * esn_b200.h -- C ABI of the B200 (sm_100a) ESN symbol-detection engine.
+ *
+ * This is the drop-in boundary for the hot path of aoschu/esn-ofdm-mimo.  The
+ * reference has no FFI of its own (pure Python); these entry
+ * points are what a binding for its hot path would call, one per numerical
+ * stage, each citing the reference lines it replaces (paths relative to the
+ * reference root).  The Python drop-in modules (esn-ofdm-mimo_b200/libs/pyESN.py,
+ * helper_mimo_esn_generic.py, HelpFunc.py) bind them through ctypes; see
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a DEVICE pointer unless the name
+ *    ends in `_host`; the caller owns all memory; nothing here allocates
+ *    (except esn_ws_* helpers) or synchronises.
+ *  - every launch function takes a `void *stream` (a cudaStream_t) and returns
+ *    0 on success, a negative ESN_E_* for argument errors, or a positive
+ *    cudaError_t.
+ *  - matrices are row-major, frames are the slowest dimension.
+ *  - `dtype`: ESN_F32 (fp32 SIMT FFMA path) or ESN_F64 (fp64 path).
+ */
+#ifndef ESN_B200_H
+#define ESN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESN_F32 0
+#define ESN_F64 1
+
+#define ESN_E_BADARG   (-1)   /* null pointer / non-positive size / unsupported value */
+#define ESN_E_TOOLARGE (-2)   /* shape exceeds what the kernel can stage on one SM */
+#define ESN_E_NODEVICE (-3)   /* no sm_100 device */
+
+#define ESN_MAX_OUT 16        /* n_outputs <= 16 (2*N_t; the reference uses <= 8) */
+#define ESN_MAX_IN  64        /* n_inputs  <= 64 (2*N_r; the reference uses <= 16) */
+
+/* mode of esn_recurrence_run */
+#define ESN_MODE_HARVEST 0    /* teacher-forced state harvesting of ESN.fit      */
+#define ESN_MODE_PREDICT 1    /* free-running prediction of ESN.predict          */
+
+int esn_version(void);
+/* Fills name[0..n) with the device name and returns the SM count, or <0. */
+int esn_device_info(char *name_host, int n, int *sm_major_host, int *sm_minor_host);
+/* Host copy of the device state-noise stream: the uniform in [0,1) that the
+ * recurrence kernels draw for (seed, frame, noise row, neuron). */
+float esn_noise_uniform_host(unsigned long long seed, unsigned frame, unsigned row, unsigned neuron);
+
+/* ---------------------------------------------------------------------------
+ * Reservoir recurrence.  Replaces the Python time loops and ESN._update:
+ *   libs/pyESN.py:111-125 (_update), :179-182 (harvest loop of fit),
+ *   :243-253 (free-running loop of predict), :127-152 (I/O scaling, folded in).
+ *
+ * Weights: Wt_aug[K_aug_pad][N_pad] (dtype), row k < N is column k of W,
+ * rows N..N+n_in-1 are W_in^T, rows N+n_in..N+n_in+n_out-1 are W_feedb^T,
+ * all other rows/columns zero.  N_pad is a multiple of 128, K_aug_pad a
+ * multiple of 16 (esn_pad_sizes gives both).
+ *
+ * HARVEST: x_0 = 0; for n = 1..T-1: x_n = tanh(W x_{n-1} + W_in u_n + W_fb d_{n-1}) + noise_n,
+ *   u_n = in[b,n,:]*in_scale+in_shift, d_n = teacher[b,n,:]*t_scale+t_shift.
+ *   Writes the extended state E[b,n,:] = [x_n, u_n] for n = 0..T-1 into
+ *   ext_out[B][T][N+n_in].   noise row consumed at step n is row n-1.
+ * PREDICT: x_{-1} = x0[b] (or 0), y_{-1} = y0[b] (or 0); for n = 0..T-1:
+ *   x_n = tanh(W x_{n-1} + W_in u_n + W_fb y_{n-1}) + noise_n,
+ *   y_n = W_out[g(b)] [x_n; u_n];  y_out[b, n-transient, :] = (y_n - t_shift)/t_scale
+ *   for n >= transient.  ext_out may be null (or receives E as above).
+ * noise_n = noise_amp * (U - 0.5): U read from noise_uniforms[b][step][N]
+ *   (dtype) when non-null, else drawn from a counter hash of (seed,b,n,neuron)
+ *   when noise_amp != 0.  feedback = 0 drops the W_fb term (teacher_forcing=False).
+ * ------------------------------------------------------------------------- */
+typedef struct esn_recurrence_args {
+    int32_t dtype;            /* ESN_F32 | ESN_F64 */
+    int32_t mode;             /* ESN_MODE_* */
+    int32_t B, T;             /* frames, time steps per frame */
+    int32_t N, n_in, n_out;   /* reservoir size, inputs, outputs */
+    int32_t N_pad, K_aug_pad; /* padded sizes of Wt_aug */
+    int32_t transient;        /* PREDICT: first output row kept */
+    int32_t feedback;         /* 1 = W_fb term on (teacher_forcing) */
+    int32_t n_groups;         /* PREDICT: number of readouts in W_out */
+    double  noise_amp;        /* ESN.noise */
+    uint64_t seed;            /* device noise stream when noise_uniforms == null */
+    const void *Wt_aug;       /* [K_aug_pad][N_pad] */
+    const void *in;           /* [B][T][n_in] raw inputs */
+    const void *in_scale;     /* [n_in] */
+    const void *in_shift;     /* [n_in] */
+    const void *teacher;      /* HARVEST: [B][T][n_out] raw teacher */
+    const void *t_scale;      /* [n_out] */
+    const void *t_shift;      /* [n_out] */
+    const void *W_out;        /* PREDICT: [n_groups][n_out][N+n_in] */
+    const int32_t *group_ids; /* PREDICT: [B] or null (all 0) */
+    const void *x0;           /* PREDICT: [B][N] or null */
+    const void *y0;           /* PREDICT: [B][n_out] (scaled domain) or null */
+    const void *noise_uniforms; /* [B][T-1 | T][N] or null */
+    void *ext_out;            /* [B][T][N+n_in] or null (required for HARVEST) */
+    void *y_out;              /* PREDICT: [B][T-transient][n_out] */
+    void *workspace;          /* [B][N] (dtype) scratch: the new state is parked here between steps */
+} esn_recurrence_args;
+
+int esn_pad_sizes(int N, int n_in, int n_out, int *N_pad_host, int *K_aug_pad_host);
+int esn_recurrence_run(const esn_recurrence_args *args_host, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Readout training.  Replaces np.linalg.pinv + dot of ESN.fit
+ * (libs/pyESN.py:189-192) by fp64 normal equations with lambda = 0:
+ *   rows m = T - transient, cols p = N + n_in, E = ext[b, transient:, :]
+ *   m >= p (primal): G = E^T E [p x p], R = E^T D [p x n_out], W_out^T = G^-1 R
+ *   m <  p (dual)  : G = E E^T [m x m], A = G^-1 D,            W_out^T = E^T A
+ * which equals the pinv (min-norm / least-squares) solution when E has full
+ * rank.  All accumulation in fp64; `ext` (the extended states written by
+ * esn_recurrence_run) and `teacher` may be fp32 or fp64 (ext_dtype/teacher_dtype).  D = teacher[b, transient:, :]*t_scale + t_shift.
+ *
+ * esn_gram_f64: builds G (lower triangle + mirrored) and the right-hand side
+ *   rhs[b] = R (primal, [p][n_out]) or D (dual, [m][n_out]).
+ *   If `accumulate` != 0, G and rhs are ADDED into (shared-readout training over
+ *   many frames, primal only); `shared` != 0 sums all B frames into problem 0.
+ * esn_cholesky_solve_f64: in-place batched Cholesky G = L L^T and solve for
+ *   n_rhs right-hand sides; info[b] = 0 or the 1-based index of the first
+ *   non-positive pivot (as LAPACK potrf).
+ * esn_readout_from_dual_f64: W_out[b] = (E^T A)^T, [n_out][p].
+ * esn_transpose_rhs_f64: primal: W_out[b] = rhs^T.
+ * ------------------------------------------------------------------------- */
+int esn_gram_f64(const void *ext, int ext_dtype, const void *teacher, int teacher_dtype,
+                 const double *t_scale, const double *t_shift,
+                 int B, int T, int p, int n_out, int transient,
+                 int dual, int shared, int accumulate,
+                 double *G, double *rhs, void *stream);
+int esn_cholesky_solve_f64(double *G, double *rhs, int batch, int n, int n_rhs,
+                           int32_t *info, void *stream);
+int esn_readout_from_dual_f64(const void *ext, int ext_dtype, const double *A, int B, int T,
+                              int p, int n_out, int transient, double *W_out, void *stream);
+int esn_transpose_rhs_f64(const double *rhs, int B, int p, int n_out, double *W_out,
+                          void *stream);
+
+/* Train-set prediction of ESN.fit (libs/pyESN.py:212-213):
+ * pred[b,n,:] = (W_out[g(b)] E[b,n,:] - t_shift)/t_scale for all T rows. */
+int esn_apply_readout(int dtype, const void *ext, const void *W_out, const int32_t *group_ids,
+                      const void *t_scale, const void *t_shift,
+                      int B, int T, int p, int n_out, void *pred, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * OFDM side (north-star subsystem 3).
+ * ofdm_unpack_fft_demap: ESN time-domain output -> per-Tx complex sequence ->
+ *   (1/N) FFT_N / sqrt(Pi) -> hard QAM decision -> bit errors.  Replaces
+ *   system_model_2/OFDM_MIMO_2-2_NBF_LDPC.py:56-64 (reconstruct), :435-438
+ *   (FFT), :103-111 + :36-38 (hard_bits_from_syms / bits_to_grayvec),
+ *   :469-474 (error count).
+ *   y [B][rows][2*N_t] (dtype; first N rows used), Pi[B] or Pi[1] (pi_stride 0/1),
+ *   X_hat [B][N][N_t] complex (2 x dtype) or null, idx [B][N][N_t] u8 or null,
+ *   tx_idx [B][N][N_t] u8 or null (transmitted symbol indices) -> bit errors
+ *   added to err_count[0] (u64) and near-boundary symbols (|distance to a
+ *   slicer boundary| < boundary_eps) to err_count[1].
+ * ofdm_rx_fft: Y = (1/N) FFT(y_CP[CP:]) (:428).  y_cp [B][N+CP][N_r] complex.
+ * ofdm_equalize: per-subcarrier solve(H^H H + reg I, H^H Y)/power_scale
+ *   (:41-53, :453-460).  H [Bh][N][N_r][N_t] complex with h_index[b] (or null
+ *   = b) selecting the estimate of the frame's coherence block.
+ * ofdm_chanest: pilot LS on the comb tx::N_t, linear inter/extrapolation,
+ *   IFFT, truncate to `taps`, (mmse_scaler*R_h^-1 + I)^-1, FFT (:316-334).
+ * ofdm_demap_count: slicer + error count on an arbitrary X_hat (for ZF/MMSE).
+ * N must be a power of two <= 4096; qam_bits in {2,4,6}.
+ * ------------------------------------------------------------------------- */
+int ofdm_unpack_fft_demap(int dtype, const void *y, int B, int rows, int N, int N_t,
+                          const void *Pi, int pi_stride, int qam_bits,
+                          void *X_hat, uint8_t *idx, const uint8_t *tx_idx,
+                          double boundary_eps, unsigned long long *err_count,
+                          void *stream);
+int ofdm_rx_fft(int dtype, const void *y_cp, int B, int N, int cp, int N_r,
+                void *Y, void *stream);
+int ofdm_equalize(int dtype, const void *Y, const void *H, const int32_t *h_index,
+                  int B, int N, int N_r, int N_t, const void *reg, int reg_stride,
+                  const void *power_scale, int ps_stride, void *X_hat, void *stream);
+int ofdm_chanest(int dtype, const void *Y_LS, const void *X_LS, int B, int N, int N_r,
+                 int N_t, const void *Pi, const void *isi_magnitude, int taps,
+                 double No, void *H_LS, void *H_MMSE, void *stream);
+int ofdm_demap_count(int dtype, const void *X_hat, int B, int N, int N_t, int qam_bits,
+                     uint8_t *idx, const uint8_t *tx_idx, double boundary_eps,
+                     unsigned long long *err_count, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESN_B200_H */
