@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Headline benchmark: ESN-detected OFDM symbols/s on the 4x8 16-QAM, N_sub=512,
+N_res=512 workload (BASELINE.json metric; configs[2]).
+
+  python bench.py --gpus N --steps K --warmup W            # this engine
+  python bench.py --impl reference --gpus N --steps K ...   # CPU arm (oracle port of pyESN)
+
+A "step" is one pass of the detection hot path over one batch of synthetic
+frames: free-running ESN predict with fused readout (T = 522 time steps per
+frame) -> unpack -> FFT-512 -> /sqrt(Pi) -> 16-QAM hard decisions -> bit-error
+count.  One OFDM symbol = one frame = N_t x N_sub QAM symbols.  Frames carry a
+per-coherence-block readout W_out (trained on the device before timing, on
+synthetic pilots) and the default state noise 0.001 from the device counter
+stream.  Multi-GPU: frames are sharded over ranks (weak scaling, no data-path
+collective); the error counters are summed with one NCCL allreduce per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "esn-ofdm-mimo_b200")
+for p in (ROOT, PKG, os.path.join(PKG, "libs")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "ESN-detected OFDM symbols/sec (4x8, N=512)"
+UNIT = "OFDM symbols/s"
+CFG = dict(N_t=4, N_r=8, n_in=16, n_out=8, n_res=512, N_sub=512, cp=7, delay=3, qam_bits=4,
+           rho=0.9, sparsity=0.1, noise=0.001, in_scale=0.005, t_scale=5e-7, seed=42)
+T_STEPS = CFG["N_sub"] + CFG["cp"] + CFG["delay"]          # 522
+TRANSIENT = CFG["cp"] + CFG["delay"]                       # 10
+
+
+def algorithmic_flops_per_symbol():
+    """T * [2 N (N + n_in + n_out) + 2 n_out (N + n_in)] (tanh excluded)."""
+    N, ni, no = CFG["n_res"], CFG["n_in"], CFG["n_out"]
+    return T_STEPS * (2 * N * (N + ni + no) + 2 * no * (N + ni))
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(bf16=float(p["bf16_tflops_sustained"]), hbm=float(p["hbm_gbs"]), src="measured")
+    return dict(bf16=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------- CPU arm ----
+def _cpu_worker(args):
+    """Detect `n` frames with the oracle port of pyESN.predict + FFT + demap."""
+    seed, n = args
+    from threadpoolctl import threadpool_limits
+    from oracle import esn_oracle as orc
+    with threadpool_limits(limits=1):
+        st = _cpu_state()
+        rng = np.random.RandomState(seed)
+        errs = 0
+        for _ in range(n):
+            u = rng.randn(T_STEPS, CFG["n_in"])
+            uni = rng.rand(T_STEPS, CFG["n_res"])
+            y = orc.predict(st["W"], st["W_in"], st["W_fb"], st["W_out"], u, TRANSIENT, CFG["noise"], uni,
+                            input_scaling=st["in_scale"], input_shift=None,
+                            teacher_scaling=CFG["t_scale"], teacher_shift=None)
+            X = orc.esn_output_to_freq(y, CFG["N_sub"], CFG["N_t"], 1e-4)
+            idx = orc.slicer_indices(X, CFG["qam_bits"])
+            errs += int(idx.sum() & 1)
+    return errs
+
+
+_CPU_STATE = None
+
+
+def _cpu_state():
+    global _CPU_STATE
+    if _CPU_STATE is None:
+        from oracle import esn_oracle as orc
+        rng = np.random.RandomState(CFG["seed"])
+        W, W_in, W_fb = orc.init_weights(rng, CFG["n_in"], CFG["n_out"], CFG["n_res"], CFG["rho"], CFG["sparsity"])
+        W_out = np.random.RandomState(1).randn(CFG["n_out"], CFG["n_res"] + CFG["n_in"]) * 1e-6
+        _CPU_STATE = dict(W=W, W_in=W_in, W_fb=W_fb, W_out=W_out,
+                          in_scale=CFG["in_scale"] * np.ones(CFG["n_in"]))
+    return _CPU_STATE
+
+
+def cpu_throughput(frames_per_worker, workers):
+    """OFDM symbols/s of the oracle port on `workers` host processes (1 BLAS
+    thread each; frames are independent, so this is the whole-host figure)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        pool.map(_cpu_worker, [(i, 1) for i in range(workers)])            # warm-up (weights, BLAS)
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(100 + i, frames_per_worker) for i in range(workers)])
+        dt = time.perf_counter() - t0
+    return frames_per_worker * workers / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workers = os.cpu_count() or 1
+    fpw = max(1, args.ref_frames_per_worker)
+    vals = []
+    for _ in range(args.warmup):
+        cpu_throughput(1, workers)
+    t_all = 0.0
+    for _ in range(args.steps):
+        v, dt = cpu_throughput(fpw, workers)
+        vals.append(v); t_all += dt
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "cfg3_4x8_16qam_nsub512_nres512_T522", "frames_per_step": fpw * workers,
+                   "what": "numpy float64 port of pyESN.predict + FFT + demap (oracle/esn_oracle.py), "
+                           "one process per host core, 1 BLAS thread each"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                         "sample": f"{fpw * workers} frames per step x {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------- GPU arm ----
+def run_gpu(args):
+    import torch
+    import esn_b200
+    from esn_b200 import dist as D
+    from esn_b200.engine import Reservoir
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    rank, world, local = D.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    esn_b200.load()
+
+    # reservoir: numpy init on the host (bit-identical to pyESN for seed 42), uploaded once
+    rng = np.random.RandomState(CFG["seed"])
+    N, ni, no = CFG["n_res"], CFG["n_in"], CFG["n_out"]
+    W = rng.rand(N, N) - 0.5
+    W[rng.rand(N, N) < CFG["sparsity"]] = 0
+    W *= CFG["rho"] / np.max(np.abs(np.linalg.eigvals(W)))
+    W_in = rng.rand(N, ni) * 2 - 1
+    W_fb = rng.rand(N, no) * 2 - 1
+    res = Reservoir(W, W_in, W_fb, input_scaling=CFG["in_scale"] * np.ones(ni), input_shift=np.zeros(ni),
+                    teacher_scaling=CFG["t_scale"] * np.ones(no), teacher_shift=np.zeros(no),
+                    noise=CFG["noise"], teacher_forcing=True, device=dev)
+
+    B, per_group = args.frames, args.frames_per_block
+    G = (B + per_group - 1) // per_group
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    # synthetic pilots -> one trained readout per coherence block (untimed setup, on the device)
+    pil_u = torch.randn((G, T_STEPS, ni), generator=gen, device=dev, dtype=torch.float64)
+    mix = torch.randn((ni, no), generator=gen, device=dev, dtype=torch.float64) / ni ** 0.5
+    pil_y = pil_u @ mix * 1e-2
+    W_out = []
+    for g0 in range(0, G, 64):
+        ext = res.harvest(pil_u[g0:g0 + 64], pil_y[g0:g0 + 64], precision="fp64", seed=7 + g0)
+        w, info = res.train_readout(ext, pil_y[g0:g0 + 64], TRANSIENT)
+        assert int(info.abs().max()) == 0, "readout training failed"
+        W_out.append(w)
+        del ext
+    W_out = torch.cat(W_out).to(torch.float32).contiguous()
+    group_ids = (torch.arange(B, device=dev) // per_group).to(torch.int32)
+    frames = torch.randn((B, T_STEPS, ni), generator=gen, device=dev, dtype=torch.float32)
+    tx_idx = torch.randint(0, 16, (B, CFG["N_sub"], CFG["N_t"]), generator=gen, device=dev, dtype=torch.uint8)
+    Pi = 10 ** (15 / 10) * 1e-5
+    counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    kern_ms = []
+
+    def step(x, time_kernel=False):
+        if time_kernel:
+            k0, k1 = ev(), ev()
+            k0.record(stream)
+        y = res.predict(x, W_out, transient=TRANSIENT, group_ids=group_ids, precision=args.precision,
+                        seed=99)
+        if time_kernel:
+            k1.record(stream)
+            kern_ms.append((k0, k1))
+        _, idx, _ = esn_b200.ofdm.unpack_fft_demap(y, CFG["N_sub"], CFG["N_t"], Pi, CFG["qam_bits"],
+                                                   tx_idx=tx_idx, want_xhat=False, counts=counts)
+        if world > 1:
+            D.allreduce_sum_(counts)
+        return idx
+
+    for _ in range(args.warmup):
+        step(frames)
+    torch.cuda.synchronize()
+    D.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = ev(), ev()
+    with ClockSampler(local) as clk:
+        t0.record(stream)
+        for _ in range(args.steps):
+            step(frames, time_kernel=True)
+        t1.record(stream)
+        torch.cuda.synchronize()
+    D.barrier()
+    ms = t0.elapsed_time(t1)
+    ms = D.max_over_ranks(ms, dev)
+    kms = float(np.mean([a.elapsed_time(b) for a, b in kern_ms]))
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end to end: pinned host frames -> H2D -> detect -> D2H symbol indices ----
+    h_in = torch.empty((B, T_STEPS, ni), dtype=torch.float32).pin_memory()
+    h_in.copy_(frames.cpu())
+    h_out = torch.empty((B, CFG["N_sub"], CFG["N_t"]), dtype=torch.uint8).pin_memory()
+    d_in = torch.empty_like(frames)
+    for _ in range(2):
+        d_in.copy_(h_in, non_blocking=True)
+        h_out.copy_(step(d_in), non_blocking=True)
+    torch.cuda.synchronize()
+    D.barrier()
+    e0, e1 = ev(), ev()
+    e0.record(stream)
+    for _ in range(args.steps):
+        d_in.copy_(h_in, non_blocking=True)
+        h_out.copy_(step(d_in), non_blocking=True)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    D.barrier()
+    e2e_ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        return
+    pk = peaks()
+    flops = algorithmic_flops_per_symbol() * B
+    achieved = flops / (kms * 1e-3) / 1e12
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        workers = os.cpu_count() or 1
+        v, dt = cpu_throughput(args.cpu_frames_per_worker, workers)
+        cpu = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
+               "sample": f"{args.cpu_frames_per_worker * workers} frames of the same workload "
+                         f"({dt:.1f} s; numpy float64 oracle port, one process per core, 1 BLAS thread each)"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
+        "config": {"workload": "cfg3_4x8_16qam_nsub512_nres512_T522", "frames_per_gpu_per_step": B,
+                   "frames_per_coherence_block": per_group, "readouts_per_gpu": G, "state_noise": "0.001 device counter stream",
+                   "recurrence_path": "simt_" + args.precision, "parallelism": f"frames sharded x{world}",
+                   "l2": f"inputs {frames.numel() * 4 / 2**20:.0f} MiB + outputs per step exceed the 126 MB L2"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_in.numel() * 4),
+                "d2h_bytes_per_step": int(h_out.numel()), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": 2 * args.steps,
+        "roofline": {"bound": "tensor", "kernel": "esn_recurrence (predict)", "achieved": achieved,
+                     "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"], "traffic": None,
+                     "peak_source": pk["src"] + " bf16 sustained", "kernel_ms": kms,
+                     "algorithmic_flop_per_symbol": algorithmic_flops_per_symbol(),
+                     "kernel_share_of_step": kms / (ms / args.steps)},
+        "cpu_baseline": cpu,
+        "clocks": clk.summary(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=148 * 64, help="frames per GPU per step")
+    ap.add_argument("--frames-per-block", type=int, default=64, help="frames sharing one trained readout")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--cpu-frames-per-worker", type=int, default=12)
+    ap.add_argument("--ref-frames-per-worker", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

@@ -314,7 +314,7 @@ int launch_cfg(RecParams p, cudaStream_t st, bool dry) {
 }
 
 // Pick the largest frame tile that fits shared memory and still gives every SM
-// a CTA; small batches get the smallest tile.
+// at least one CTA; small batches get the smallest tile.
 template <typename T>
 int launch_any(const RecParams &p, cudaStream_t st) {
     const int slabs128 = p.N_pad / 128;
@@ -322,7 +322,7 @@ int launch_any(const RecParams &p, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 #define TRY(BT_, WN_, KC_)                                                              \
-    if (p.B >= (BT_ / 2) * sms && launch_cfg<T, BT_, WN_, KC_>(p, st, true) == 0)        \
+    if ((p.B + BT_ - 1) / BT_ >= sms && launch_cfg<T, BT_, WN_, KC_>(p, st, true) == 0)  \
         return launch_cfg<T, BT_, WN_, KC_>(p, st, false);
 #define LAST(BT_, WN_, KC_)                                                             \
     if (launch_cfg<T, BT_, WN_, KC_>(p, st, true) == 0)                                  \
