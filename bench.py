@@ -216,20 +216,31 @@ def run_gpu(args):
     pil_u = torch.randn((G, T_STEPS, ni), generator=gen, device=dev, dtype=torch.float64)
     mix = torch.randn((ni, no), generator=gen, device=dev, dtype=torch.float64) / ni ** 0.5
     pil_y = pil_u @ mix * 1e-2
-    W_out = []
+    W_out_parts = []
     for g0 in range(0, G, 64):
         ext = res.harvest(pil_u[g0:g0 + 64], pil_y[g0:g0 + 64], precision="fp64", seed=7 + g0)
         w, info = res.train_readout(ext, pil_y[g0:g0 + 64], TRANSIENT)
         assert int(info.abs().max()) == 0, "readout training failed"
-        W_out.append(w)
+        W_out_parts.append(w)
         del ext
-    W_out = torch.cat(W_out).to(torch.float32).contiguous()
     group_ids = (torch.arange(B, device=dev) // per_group).to(torch.int32)
+    W_out64 = torch.cat(W_out_parts)
+    del W_out_parts
     frames = torch.randn((B, T_STEPS, ni), generator=gen, device=dev, dtype=torch.float32)
     tx_idx = torch.randint(0, 16, (B, CFG["N_sub"], CFG["N_t"]), generator=gen, device=dev, dtype=torch.uint8)
     Pi = 10 ** (15 / 10) * 1e-5
     counts = torch.zeros(2, dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream()
+    path = args.path
+    if path == "tc":
+        if per_group % 64:
+            raise SystemExit("--path tc needs --frames-per-block to be a multiple of 64")
+        # fold the feedback into the weights per readout (part of training, untimed)
+        readout = res.tc_prepare(W_out64, res.input_scale_exponent(frames))
+        precision = "tc"
+    else:
+        readout = W_out64.to(torch.float32).contiguous()
+        precision = args.precision
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     kern_ms = []
@@ -238,8 +249,10 @@ def run_gpu(args):
         if time_kernel:
             k0, k1 = ev(), ev()
             k0.record(stream)
-        y = res.predict(x, W_out, transient=TRANSIENT, group_ids=group_ids, precision=args.precision,
-                        seed=99)
+        if path == "tc":
+            y = res.predict_tc(x, readout, transient=TRANSIENT, group_ids=group_ids, seed=99)
+        else:
+            y = res.predict(x, readout, transient=TRANSIENT, group_ids=group_ids, precision=precision, seed=99)
         if time_kernel:
             k1.record(stream)
             kern_ms.append((k0, k1))
@@ -303,15 +316,15 @@ def run_gpu(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
+        "vs_baseline": None, "dtype": ("f16x2-split/f32-accum" if path == "tc" else ("f32" if args.precision == "fp32" else "f64")), "data": "synthetic",
         "config": {"workload": "cfg3_4x8_16qam_nsub512_nres512_T522", "frames_per_gpu_per_step": B,
                    "frames_per_coherence_block": per_group, "readouts_per_gpu": G, "state_noise": "0.001 device counter stream",
-                   "recurrence_path": "simt_" + args.precision, "parallelism": f"frames sharded x{world}",
+                   "recurrence_path": ("tcgen05 fp16 hi/lo split x3, fp32 accumulate in TMEM" if path == "tc" else "simt_" + args.precision), "parallelism": f"frames sharded x{world}",
                    "l2": f"inputs {frames.numel() * 4 / 2**20:.0f} MiB + outputs per step exceed the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_in.numel() * 4),
                 "d2h_bytes_per_step": int(h_out.numel()), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": 2 * args.steps,
-        "roofline": {"bound": "tensor", "kernel": "esn_recurrence (predict)", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": ("esn_predict_tc" if path == "tc" else "esn_recurrence_simt"), "achieved": achieved,
                      "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"], "traffic": None,
                      "peak_source": pk["src"] + " bf16 sustained", "kernel_ms": kms,
                      "algorithmic_flop_per_symbol": algorithmic_flops_per_symbol(),
@@ -330,7 +343,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=148 * 64, help="frames per GPU per step")
     ap.add_argument("--frames-per-block", type=int, default=64, help="frames sharing one trained readout")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--path", default="tc", choices=["tc", "simt"], help="recurrence kernel: tensor cores or SIMT")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"], help="SIMT path precision")
     ap.add_argument("--cpu-frames-per-worker", type=int, default=12)
     ap.add_argument("--ref-frames-per-worker", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -50,6 +50,13 @@ def _vec(v, n, default, device):
     return torch.from_numpy(a).to(device)
 
 
+class TcReadout:
+    """Handle of the tensor-core weight image built by Reservoir.tc_prepare."""
+
+    def __init__(self, image, yscale, su_exp, n_groups):
+        self.image, self.yscale, self.su_exp, self.n_groups = image, yscale, su_exp, n_groups
+
+
 class Reservoir:
     """Device-resident reservoir weights and the affine I/O maps of one ESN
     (reference libs/pyESN.py:93-152).  Weights are uploaded once, in the
@@ -79,6 +86,10 @@ class Reservoir:
         wt[self.N:self.P, :self.N] = W_in.T
         if self.teacher_forcing:
             wt[self.P:self.P + self.n_out, :self.N] = W_fb.T
+        # plain fp64 copies for the tensor-core path's weight folding (esn_tc_prepare)
+        self._W64 = torch.from_numpy(np.ascontiguousarray(W)).to(self.device)
+        self._Win64 = torch.from_numpy(np.ascontiguousarray(W_in)).to(self.device)
+        self._Wfb64 = torch.from_numpy(np.ascontiguousarray(W_fb)).to(self.device)
         self._wt = {ESN_F64: torch.from_numpy(wt).to(self.device)}
         self._wt[ESN_F32] = self._wt[ESN_F64].to(torch.float32)
         self._aff = {ESN_F64: dict(
@@ -160,6 +171,78 @@ class Reservoir:
             t = t.unsqueeze(0)
         return t.contiguous()
 
+    # ---------------------------------------------------- tensor-core path --
+    def tc_supported(self):
+        return bool(self.lib.esn_tc_supported(self.N, self.n_in, self.n_out))
+
+    def input_scale_exponent(self, inputs):
+        """su_exp for the tensor-core path: the power of two that brings the
+        largest scaled input to about 2^9 (one device reduction + sync)."""
+        aff = self._aff[ESN_F32]
+        u = inputs.to(self.device, torch.float32) * aff["in_scale"] + aff["in_shift"]
+        umax = float(u.abs().max().item())
+        if not np.isfinite(umax):
+            raise EsnB200Error("non-finite inputs")
+        e = int(np.ceil(np.log2(umax))) if umax > 0 else 0
+        su = 9 - e
+        if su < 1:
+            raise EsnB200Error("inputs too large for the tensor-core path (max |u| > 256); use precision='fp32'")
+        return min(su, 24)
+
+    def tc_prepare(self, W_out, su_exp):
+        """Fold the output feedback into the weights for every readout in
+        W_out [G, n_out, P] and build the UMMA-ready fp16 hi/lo image."""
+        if not self.tc_supported():
+            raise EsnB200Error("tensor-core path needs N <= 512, n_inputs <= 32, n_outputs <= 16")
+        W_out = self._as(W_out, torch.float64, 3)
+        G = W_out.shape[0]
+        nbytes = int(self.lib.esn_tc_image_bytes(self.N, self.n_in))
+        image = torch.empty((G, nbytes), dtype=torch.uint8, device=self.device)
+        yscale = torch.empty((G,), dtype=torch.float32, device=self.device)
+        so = torch.empty((G,), dtype=torch.int32, device=self.device)
+        check(self.lib.esn_tc_prepare(ptr(self._W64), ptr(self._Win64), ptr(self._Wfb64), ptr(W_out), self.N,
+                                      self.n_in, self.n_out, G, int(su_exp), int(self.teacher_forcing),
+                                      ptr(image), ptr(yscale), ptr(so), _stream()), "esn_tc_prepare")
+        return TcReadout(image, yscale, int(su_exp), G)
+
+    def predict_tc(self, inputs, readout, transient=0, group_ids=None, noise_uniforms=None, seed=0,
+                   return_ext=False):
+        """Free-running prediction on the tensor cores (continuation=False
+        semantics: zero initial state and output).  `readout` comes from
+        tc_prepare; each 64-frame tile must use a single readout."""
+        inputs = self._as(inputs, torch.float32, 3)
+        B, T, n_in = inputs.shape
+        if n_in != self.n_in:
+            raise ValueError(f"inputs have {n_in} columns, ESN has n_inputs={self.n_in}")
+        a = _lib.TcPredictArgs()
+        a.B, a.T, a.N, a.n_in, a.n_out = B, T, self.N, self.n_in, self.n_out
+        a.transient, a.su_exp, a.n_groups = int(transient), readout.su_exp, readout.n_groups
+        a.noise_amp, a.seed = self.noise, int(seed) & 0xFFFFFFFFFFFFFFFF
+        aff = self._aff[ESN_F32]
+        a.image, a.yscale, a.inp = ptr(readout.image), ptr(readout.yscale), ptr(inputs)
+        a.in_scale, a.in_shift = ptr(aff["in_scale"]), ptr(aff["in_shift"])
+        a.t_scale, a.t_shift = ptr(aff["t_scale"]), ptr(aff["t_shift"])
+        keep = [inputs]
+        if group_ids is not None:
+            group_ids = group_ids.to(device=self.device, dtype=torch.int32).contiguous()
+            a.group_ids = ptr(group_ids)
+            keep.append(group_ids)
+        elif readout.n_groups != 1:
+            raise ValueError("group_ids required when the readout handle holds more than one readout")
+        if noise_uniforms is not None:
+            noise_uniforms = self._as(noise_uniforms, torch.float32, 3)
+            if tuple(noise_uniforms.shape) != (B, T, self.N):
+                raise ValueError(f"noise_uniforms must be [{B},{T},{self.N}]")
+            a.noise_uniforms = ptr(noise_uniforms)
+        ext = None
+        if return_ext:
+            ext = torch.empty((B, T, self.P), dtype=torch.float32, device=self.device)
+            a.ext_out = ptr(ext)
+        y = torch.empty((B, T - int(transient), self.n_out), dtype=torch.float32, device=self.device)
+        a.y_out = ptr(y)
+        check(self.lib.esn_tc_predict(C.byref(a), _stream()), "esn_tc_predict")
+        return (y, ext) if return_ext else y
+
     def harvest(self, inputs, teachers, precision="fp64", noise_uniforms=None, seed=0):
         """Teacher-forced harvesting (libs/pyESN.py:179-182).  Returns the
         extended states E [B, T, N+n_in] = [x_n, u_n] (libs/pyESN.py:189)."""
@@ -172,6 +255,21 @@ class Reservoir:
         """Free-running prediction (libs/pyESN.py:243-255) of B frames, frame b
         using readout W_out[group_ids[b]].  Returns y [B, T-transient, n_out]
         in teacher units (and E if return_ext)."""
+        if precision == "tc":
+            if x0 is not None or y0 is not None:
+                raise EsnB200Error("the tensor-core path starts from the zero state (continuation=False)")
+            if not isinstance(W_out, TcReadout):
+                W_out = self.tc_prepare(W_out, self.input_scale_exponent(inputs))
+            if group_ids is not None:
+                tiles = group_ids.to(self.device).reshape(-1)
+                pad = (-tiles.numel()) % 64
+                if pad:
+                    tiles = torch.cat([tiles, tiles[-1:].expand(pad)])
+                tiles = tiles.view(-1, 64)
+                if not bool((tiles == tiles[:, :1]).all()):
+                    raise EsnB200Error("tensor-core path: each 64-frame tile must share one readout")
+            return self.predict_tc(inputs, W_out, transient=transient, group_ids=group_ids,
+                                   noise_uniforms=noise_uniforms, seed=seed, return_ext=return_ext)
         ext, y = self._run(MODE_PREDICT, dtype_code(precision), inputs, W_out=W_out,
                            group_ids=group_ids, x0=x0, y0=y0, noise_uniforms=noise_uniforms,
                            seed=seed, transient=transient, want_ext=return_ext)

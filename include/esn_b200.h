@@ -34,6 +34,7 @@ extern "C" {
 #define ESN_E_BADARG   (-1)   /* null pointer / non-positive size / unsupported value */
 #define ESN_E_TOOLARGE (-2)   /* shape exceeds what the kernel can stage on one SM */
 #define ESN_E_NODEVICE (-3)   /* no sm_100 device */
+#define ESN_E_UNSUPPORTED (-4) /* shape outside what this path supports (use the SIMT path) */
 
 #define ESN_MAX_OUT 16        /* n_outputs <= 16 (2*N_t; the reference uses <= 8) */
 #define ESN_MAX_IN  64        /* n_inputs  <= 64 (2*N_r; the reference uses <= 16) */
@@ -101,6 +102,45 @@ typedef struct esn_recurrence_args {
 
 int esn_pad_sizes(int N, int n_in, int n_out, int *N_pad_host, int *K_aug_pad_host);
 int esn_recurrence_run(const esn_recurrence_args *args_host, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Tensor-core recurrence (tcgen05 + TMEM), free-running predict only.  Same
+ * reference lines as esn_recurrence_run in PREDICT mode (libs/pyESN.py:243-255)
+ * with zero initial state/output (continuation=False).  fp16 hi/lo operand
+ * split (three MMAs per product, fp32 accumulation in TMEM), 64 frames per CTA;
+ * frames of one 64-frame tile share one readout (group_ids uniform per tile).
+ *
+ * esn_tc_prepare folds the output feedback into the weights per readout g
+ * (W_eff = W + W_fb W_out_x, extra input block W_fb W_out_u for u_{t-1}) in fp64
+ * and writes the pre-swizzled UMMA-ready fp16 image [n_groups][esn_tc_image_bytes].
+ * su_exp: inputs (after in_scale/in_shift) are multiplied by 2^su_exp before the
+ * fp16 split; choose it so that max|u| 2^su_exp is about 2^9 (1 <= su_exp).
+ * ------------------------------------------------------------------------- */
+typedef struct esn_tc_predict_args {
+    int32_t B, T;
+    int32_t N, n_in, n_out;
+    int32_t transient;
+    int32_t su_exp;
+    int32_t n_groups;
+    double  noise_amp;
+    uint64_t seed;
+    const void *image;          /* from esn_tc_prepare */
+    const float *yscale;        /* [n_groups], from esn_tc_prepare */
+    const float *in;            /* [B][T][n_in] raw inputs (fp32) */
+    const float *in_scale, *in_shift;   /* [n_in] */
+    const float *t_scale, *t_shift;     /* [n_out] */
+    const int32_t *group_ids;   /* [B] or null */
+    const float *noise_uniforms;/* [B][T][N] or null (device counter stream) */
+    float *ext_out;             /* [B][T][N+n_in] or null */
+    float *y_out;               /* [B][T-transient][n_out] */
+} esn_tc_predict_args;
+
+int esn_tc_supported(int N, int n_in, int n_out);
+long long esn_tc_image_bytes(int N, int n_in);
+int esn_tc_prepare(const double *W, const double *W_in, const double *W_fb, const double *W_out,
+                   int N, int n_in, int n_out, int n_groups, int su_exp, int feedback,
+                   void *image, float *yscale, int32_t *so_workspace, void *stream);
+int esn_tc_predict(const esn_tc_predict_args *args_host, void *stream);
 
 /* ---------------------------------------------------------------------------
  * Readout training.  Replaces np.linalg.pinv + dot of ESN.fit

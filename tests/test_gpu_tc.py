@@ -1,0 +1,130 @@
+"""GPU parity tests of the tensor-core (tcgen05) recurrence path against the
+CPU oracle: a ladder from one time step (input block + one UMMA pass + epilogue)
+to full-length grouped prediction at the cfg3 shape.  Tolerances as in
+BASELINE.json: states 1e-5 relative, outputs 1e-4 relative."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from conftest import rel_err
+from oracle import esn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import __graft_entry__ as g
+    g.build()
+
+
+def _cuda(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def _setup(n_res, n_in, n_out, seed, noise=0.001, feedback=True, in_scale=0.01, t_scale=5e-7):
+    from esn_b200 import Reservoir
+    rng = np.random.RandomState(seed)
+    W, W_in, W_fb = orc.init_weights(rng, n_in, n_out, n_res, 0.9, 0.1)
+    aff = dict(input_scaling=in_scale * np.ones(n_in), input_shift=np.zeros(n_in),
+               teacher_scaling=t_scale * np.ones(n_out), teacher_shift=np.zeros(n_out),
+               teacher_forcing=feedback)
+    eng = Reservoir(W, W_in, W_fb, aff["input_scaling"], aff["input_shift"], aff["teacher_scaling"],
+                    aff["teacher_shift"], noise, feedback)
+    return rng, (W, W_in, W_fb), aff, eng
+
+
+def _check(eng, Ws, aff, us, W_outs, gid, T, transient, noise, uni, state_tol=1e-5, out_tol=1e-4):
+    W, W_in, W_fb = Ws
+    y, ext = eng.predict(_cuda(us), _cuda(W_outs), transient=transient,
+                         group_ids=None if gid is None else _cuda(gid.astype(np.int32)),
+                         precision="tc", noise_uniforms=None if uni is None else _cuda(uni), return_ext=True)
+    torch.cuda.synchronize()
+    y, ext = y.double().cpu().numpy(), ext.double().cpu().numpy()
+    N = W.shape[0]
+    ws = wy = 0.0
+    for b in range(us.shape[0]):
+        g = 0 if gid is None else gid[b]
+        ref, st = orc.predict(W, W_in, W_fb, W_outs[g], us[b], transient, noise,
+                              uni[b] if uni is not None else np.zeros((T, N)), return_states=True, **aff)
+        ws = max(ws, rel_err(ext[b, :, :N], st))
+        wy = max(wy, rel_err(y[b], ref))
+        assert rel_err(ext[b, :, N:], orc.scale_inputs(us[b], aff["input_scaling"], aff["input_shift"])) < 1e-6
+    assert ws < state_tol, ("states", ws)
+    assert wy < out_tol, ("outputs", wy)
+    return ws, wy
+
+
+@pytest.mark.parametrize("T", [1, 2, 5])
+def test_tc_ladder_small_steps(T):
+    """N=128 (one slab), no noise: step 1 exercises the input block and the UMMA
+    descriptors, step 2 the swizzled state write/read, 5 steps the feedback fold."""
+    rng, Ws, aff, eng = _setup(128, 4, 4, seed=3, noise=0.0)
+    B = 70                                               # ragged second tile
+    us = rng.randn(B, T, 4)
+    W_outs = rng.randn(1, 4, 132) * 1e-6
+    _check(eng, Ws, aff, us, W_outs, None, T, 0, 0.0, None)
+
+
+def test_tc_cfg3_shape_grouped_with_noise():
+    """4x8 / 512 neurons / T=522 / transient 10, two readouts on separate tiles,
+    host-supplied state noise."""
+    c = cases.ESN_CASES["cfg3_4x8_n512"]
+    rng, Ws, aff, eng = _setup(512, 16, 8, seed=42, noise=0.001, in_scale=0.005)
+    B, T = 64 + 9, c["T"]
+    us = rng.randn(B, T, 16)
+    # realistic readouts: train with the oracle on a pilot so W_out carries the ill-conditioning
+    W_outs = []
+    for g in range(2):
+        u, y = cases.esn_io(c, 20 + g)
+        r = orc.fit(Ws[0], Ws[1], Ws[2], u, y, 10, 0.001, rng.rand(T - 1, 512), **aff)
+        W_outs.append(r["W_out"])
+    W_outs = np.stack(W_outs)
+    gid = np.array([0] * 64 + [1] * 9)
+    uni = rng.rand(B, T, 512)
+    ws, wy = _check(eng, Ws, aff, us[:, :, :], W_outs, gid, T, 10, 0.001, uni)
+    print("tc cfg3 worst state err %.2e, output err %.2e" % (ws, wy))
+
+
+def test_tc_device_noise_and_no_feedback():
+    from esn_b200.noise import device_noise_uniforms
+    rng, Ws, aff, eng = _setup(256, 16, 8, seed=5, noise=0.001, feedback=False)
+    B, T = 64, 40
+    us = rng.randn(B, T, 16)
+    W_outs = rng.randn(1, 8, 272) * 1e-5
+    seed = 77
+    y = eng.predict(_cuda(us), _cuda(W_outs), transient=3, precision="tc", seed=seed).double().cpu().numpy()
+    uni = device_noise_uniforms(seed, B, T, 256)
+    for b in (0, 31, 63):
+        ref = orc.predict(Ws[0], Ws[1], Ws[2], W_outs[0], us[b], 3, 0.001, uni[b], **aff)
+        assert rel_err(y[b], ref) < 1e-4
+
+
+def test_tc_padded_reservoir_and_small_io():
+    """N=100 (padded to one 128 slab), 2x2 (n_in=4, n_out=4) and SISO-sized I/O."""
+    for n_res, n_in, n_out in ((100, 4, 4), (200, 2, 2), (300, 4, 4)):
+        rng, Ws, aff, eng = _setup(n_res, n_in, n_out, seed=n_res, noise=0.001)
+        B, T = 20, 30
+        us = rng.randn(B, T, n_in)
+        W_outs = rng.randn(1, n_out, n_res + n_in) * 1e-6
+        uni = rng.rand(B, T, n_res)
+        _check(eng, Ws, aff, us, W_outs, None, T, 2, 0.001, uni)
+
+
+def test_tc_rejects_what_it_cannot_do():
+    from esn_b200 import EsnB200Error
+    rng, Ws, aff, eng = _setup(128, 4, 4, seed=1)
+    us = _cuda(rng.randn(130, 6, 4))
+    W_outs = _cuda(rng.randn(2, 4, 132) * 1e-6)
+    gid = torch.arange(130, device="cuda") % 2                  # mixed readouts inside a tile
+    with pytest.raises(EsnB200Error):
+        eng.predict(us, W_outs, group_ids=gid, precision="tc")
+    with pytest.raises(EsnB200Error):
+        eng.predict(us, W_outs[:1], x0=torch.zeros(130, 128), precision="tc")
+    rng, Ws, aff, big = _setup(640, 4, 4, seed=2)
+    with pytest.raises(EsnB200Error):
+        big.predict(_cuda(rng.randn(4, 6, 4)), _cuda(rng.randn(1, 4, 644)), precision="tc")
