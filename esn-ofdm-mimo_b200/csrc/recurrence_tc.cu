@@ -1,27 +1,34 @@
 // Reservoir recurrence on the 5th-generation tensor cores (tcgen05 + TMEM).
 //
 // Free-running ESN.predict (reference libs/pyESN.py:243-255) for reservoirs of
-// N = 128*S neurons (S <= 4), batched over frames: one CTA owns 64 frames and
-// steps them through all T time steps.
+// up to 512 neurons (S = ceil(N/128) slabs), batched over frames: one CTA owns 64
+// frames and steps them through all T time steps.
 //
 // Per step the pre-activation of all neurons is D[neuron, frame] =
-// W_eff[neuron, :] . s[frame, :], an M=128 x N=64 x K UMMA per 128-neuron slab:
-//   A (M side) = weight tiles, streamed from L2 every step through a 4-slot ring
-//                of 16 KB slots with cp.async.bulk (UBLKCP) + mbarrier tx counts;
-//                the image in global memory is pre-swizzled (SWIZZLE_128B,
-//                K-major), so a plain bulk copy lands a UMMA-ready tile.
-//   B (N side) = the state tile [64 frames x K] kept in shared memory for the whole
-//                kernel, rewritten in place by the epilogue warps every step.
+// [W | W_in | 0 | W_fb][neuron, :] . [x_{t-1} | u_t | u_{t-1} | y_{t-1}][frame, :],
+// an M=128 x N=64 x K UMMA chain per 128-neuron slab:
+//   A (M side) = weight tiles, ONE image shared by every CTA and every readout (it
+//                stays L2-resident), streamed each step through a ring of 16 KB
+//                slots with cp.async.bulk (UBLKCP) + mbarrier tx counts; the image
+//                is pre-swizzled (SWIZZLE_128B, K-major) so a plain bulk copy lands
+//                a UMMA-ready tile.
+//   B (N side) = the state tile [64 frames x K] that lives in shared memory for the
+//                whole kernel and is rewritten in place every step.
 //   D          = fp32 accumulators in TMEM (S x 64 columns), read with tcgen05.ld.
+// The readout y_{t-1} = W_out[g] [x_{t-1}; u_{t-1}] is one more small UMMA chain
+// over the same state tile (M = frames, N = 16) issued FIRST in the step; two
+// "frame" warps pull it out of TMEM while the big chain runs, emit it, and write
+// it back into the y columns of the state tile, where the last K chunk of the
+// big chain (W_in, W_fb) picks it up -- the output feedback of the reference
+// without serialising the tensor pipe.
 // fp32-grade accuracy from fp16 operands: every operand v is split v = hi + lo
 // (two fp16, ~22 mantissa bits, power-of-two pre-scaling keeps lo out of the
 // subnormals) and each product is issued as hi*hi + lo*hi + hi*lo with fp32
 // accumulation -- three kind::f16 MMAs, half the tensor time of 3xTF32.
-// Output feedback (teacher_forcing) is folded into the weights per readout:
-// W_eff = W + W_fb W_out[:, :N] and the extra input block W_fb W_out[:, N:] u_{t-1},
-// which is algebraically identical to feeding y_{t-1} = W_out [x_{t-1}; u_{t-1}]
-// back through W_fb.  The readout itself, y_t = W_out [x_t; u_t], rides along as
-// one more small UMMA (M = frames, N = 16) over the same state tile.
+//
+// Warp roles (640 threads): 0-1 frame warps (inputs, readout, noise keys),
+// 2 weight-ring producer, 3 MMA issuer + TMEM owner, 4-19 epilogue
+// (TMEM -> tanh -> noise -> fp16 hi/lo -> swizzled state tile).
 #include <algorithm>
 #include "common.cuh"
 #include <cuda_fp16.h>
@@ -34,25 +41,25 @@ constexpr int SLOT = 16384;            // bytes per ring slot: [128 rows x 64 k]
 constexpr int STILE = 8192;            // bytes per state tile: [64 rows x 64 k] fp16
 constexpr int YTILE = 2048;            // bytes per readout tile: [16 rows x 64 k] fp16
 constexpr int SX = 8, SW = 8;          // power-of-two pre-scales of state and weights
-constexpr int TC_THREADS = 640;        // warp 0 producer, 1 MMA, 2-3 inputs, 4-19 epilogue
+constexpr int TC_THREADS = 640;
 constexpr int TMEM_COLS = 512;
 constexpr int YCOL = 256;              // TMEM column of the readout accumulator
 
 struct TcGeom {
-    int S, C, UW, ca, klast;           // slabs, 64-wide K chunks, input block width, aug chunk, k-steps in last chunk
-    size_t image_bytes;
+    int S, C, UW, YO, ca, kaug;        // slabs, 64-wide K chunks, input block width, y column offset, aug chunk, k-steps in aug chunk
+    size_t weight_bytes, readout_bytes;
 };
 
 __host__ __device__ inline TcGeom tc_geom(int N, int n_in) {
     TcGeom g;
     g.S = (N + 127) / 128;
     g.UW = (n_in + 7) / 8 * 8;
-    int kaug = g.S * 128 + 2 * g.UW;
-    kaug = (kaug + 15) / 16 * 16;
-    g.C = (kaug + 63) / 64;
-    g.ca = g.S * 2;
-    g.klast = (kaug - (g.C - 1) * 64) / 16;
-    g.image_bytes = (size_t)g.S * g.C * 2 * SLOT + (size_t)g.C * 2 * YTILE;
+    g.YO = (2 * g.UW + 15) / 16 * 16;
+    g.C = 2 * g.S + 1;
+    g.ca = 2 * g.S;
+    g.kaug = g.YO / 16 + 1;
+    g.weight_bytes = (size_t)g.S * g.C * 2 * SLOT;
+    g.readout_bytes = (size_t)g.C * 2 * YTILE;
     return g;
 }
 
@@ -61,26 +68,48 @@ __host__ __device__ inline int sw128_off(int r, int k) {
     return (r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 3) & 7) ^ (r & 7)) << 4) + (k & 7) * 2;
 }
 
-// ------------------------------------------------------------- prepare ------
-// Build, per readout g, the UMMA-ready fp16 hi/lo image of
-//   [ W + W_fb W_out_x | W_in 2^(SX+SW-SU) | W_fb W_out_u 2^(SX+SW-SU) ] * 2^SW   (main tiles)
-//   [ W_out_x 2^SO     | 0                 | W_out_u 2^(SX+SO-SU)      ]          (readout tiles)
-// computed in fp64.  yscale[g] = 2^-(SX+SO_g).
-struct PrepParams {
-    const double *W, *W_in, *W_fb, *W_out;   // W_out [G][n_out][N+n_in]
-    int N, n_in, n_out, G, su, feedback;
-    unsigned char *image;
-    float *yscale;
-    int *so;                                  // [G] readout scale exponents (workspace)
-};
+__device__ inline void store_split(unsigned char *tile_hi, unsigned char *tile_lo, int off, double v) {
+    const __half hi = __double2half(v);
+    const __half lo = __double2half(v - (double)__half2float(hi));
+    *reinterpret_cast<__half *>(tile_hi + off) = hi;
+    *reinterpret_cast<__half *>(tile_lo + off) = lo;
+}
 
-__global__ void tc_wout_scale_kernel(PrepParams p) {
-    const int g = blockIdx.x;
-    const int P = p.N + p.n_in;
-    const double *w = p.W_out + (size_t)g * p.n_out * P;
-    double m = 0.0;
-    for (int i = threadIdx.x; i < p.n_out * P; i += blockDim.x) m = fmax(m, fabs(w[i]));
+// ------------------------------------------------------------- prepare ------
+// Shared weight image: rows = neurons (padded to 128 S), columns =
+// [ W 2^SW | W_in 2^(SX+SW-su) | 0 (u_{t-1}) | W_fb 2^(SX+SW-sy) ], fp16 hi/lo tiles.
+__global__ void tc_prepare_weights_kernel(const double *__restrict__ W, const double *__restrict__ W_in,
+                                          const double *__restrict__ W_fb, int N, int n_in, int n_out, int su,
+                                          int sy, int feedback, unsigned char *__restrict__ img) {
+    const TcGeom gm = tc_geom(N, n_in);
+    const int rows = gm.S * 128, cols = gm.C * 64, xcols = gm.S * 128;
+    const size_t total = (size_t)rows * cols;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(e / cols), k = (int)(e % cols);
+        double v = 0.0;
+        if (r < N) {
+            if (k < N) v = ldexp(W[(size_t)r * N + k], SW);
+            else if (k >= xcols && k < xcols + n_in) v = ldexp(W_in[r * n_in + (k - xcols)], SX + SW - su);
+            else if (feedback && k >= xcols + gm.YO && k < xcols + gm.YO + n_out)
+                v = ldexp(W_fb[r * n_out + (k - xcols - gm.YO)], SX + SW - sy);
+        }
+        const int s = r >> 7, c = k >> 6;
+        unsigned char *tile = img + ((size_t)(s * gm.C + c) * 2) * SLOT;
+        store_split(tile, tile + SLOT, sw128_off(r & 127, k & 63), v);
+    }
+}
+
+// Per-readout image: rows = outputs (padded to 16), columns =
+// [ W_out_x 2^so | 0 (u_t) | W_out_u 2^(SX+so-su) | 0 (y) ];  yscale[g] = 2^-(SX+so).
+__global__ void tc_prepare_readout_kernel(const double *__restrict__ W_out, int N, int n_in, int n_out, int su,
+                                          unsigned char *__restrict__ img, float *__restrict__ yscale) {
+    const TcGeom gm = tc_geom(N, n_in);
+    const int g = blockIdx.x, P = N + n_in;
+    const double *w = W_out + (size_t)g * n_out * P;
     __shared__ double sm[256];
+    __shared__ int s_so;
+    double m = 0.0;
+    for (int i = threadIdx.x; i < n_out * P; i += blockDim.x) m = fmax(m, fabs(w[i]));
     sm[threadIdx.x] = m;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) {
@@ -89,61 +118,26 @@ __global__ void tc_wout_scale_kernel(PrepParams p) {
     }
     if (threadIdx.x == 0) {
         int e = 0;
-        double mx = sm[0];
-        if (mx > 0.0) frexp(mx, &e);          // mx = f * 2^e, f in [0.5, 1)
-        int so = 10 - e;                      // max |W_out| 2^so in [2^9, 2^10)
-        // input-block entries carry an extra 2^(SX - su); keep them finite in fp16
-        if (SX - p.su > 0) so -= (SX - p.su);
-        p.so[g] = so;
-        p.yscale[g] = (float)ldexp(1.0, -(SX + so));
+        if (sm[0] > 0.0) frexp(sm[0], &e);          // max = f 2^e, f in [0.5, 1)
+        int so = 10 - e;                            // max |W_out| 2^so in [2^9, 2^10)
+        if (SX - su > 0) so -= (SX - su);           // input-block entries carry an extra 2^(SX-su)
+        s_so = so;
+        yscale[g] = (float)ldexp(1.0, -(SX + so));
     }
-}
-
-__global__ void tc_prepare_kernel(PrepParams p) {
-    const TcGeom gm = tc_geom(p.N, p.n_in);
-    const int g = blockIdx.y;
-    const int P = p.N + p.n_in;
-    const double *Wo = p.W_out + (size_t)g * p.n_out * P;
-    unsigned char *img = p.image + (size_t)g * gm.image_bytes;
-    const int rows_main = gm.S * 128, cols = gm.C * 64;
-    const size_t total = (size_t)(rows_main + 16) * cols;
-    const int so = p.so[g];
-    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-        const int r = (int)(e / cols), k = (int)(e % cols);
+    __syncthreads();
+    const int so = s_so;
+    unsigned char *out = img + (size_t)g * gm.readout_bytes;
+    const int cols = gm.C * 64, xcols = gm.S * 128;
+    for (int e = threadIdx.x; e < 16 * cols; e += blockDim.x) {
+        const int o = e / cols, k = e % cols;
         double v = 0.0;
-        size_t off;
-        if (r < rows_main) {
-            if (r < p.N) {
-                if (k < p.N) {
-                    v = p.W[(size_t)r * p.N + k];
-                    if (p.feedback)
-                        for (int o = 0; o < p.n_out; ++o) v += p.W_fb[r * p.n_out + o] * Wo[(size_t)o * P + k];
-                    v = ldexp(v, SW);
-                } else if (k >= rows_main && k < rows_main + p.n_in) {
-                    v = ldexp(p.W_in[r * p.n_in + (k - rows_main)], SX + SW - p.su);
-                } else if (k >= rows_main + gm.UW && k < rows_main + gm.UW + p.n_in && p.feedback) {
-                    const int j = k - rows_main - gm.UW;
-                    for (int o = 0; o < p.n_out; ++o) v += p.W_fb[r * p.n_out + o] * Wo[(size_t)o * P + p.N + j];
-                    v = ldexp(v, SX + SW - p.su);
-                }
-            }
-            const int s = r >> 7, c = k >> 6;
-            off = ((size_t)(s * gm.C + c) * 2) * SLOT + sw128_off(r & 127, k & 63);
-        } else {
-            const int o = r - rows_main;
-            if (o < p.n_out) {
-                if (k < p.N) v = ldexp(Wo[(size_t)o * P + k], so);
-                else if (k >= rows_main + gm.UW && k < rows_main + gm.UW + p.n_in)
-                    v = ldexp(Wo[(size_t)o * P + p.N + (k - rows_main - gm.UW)], SX + so - p.su);
-            }
-            const int c = k >> 6;
-            off = (size_t)gm.S * gm.C * 2 * SLOT + ((size_t)c * 2) * YTILE + sw128_off(o, k & 63);
+        if (o < n_out) {
+            if (k < N) v = ldexp(w[(size_t)o * P + k], so);
+            else if (k >= xcols + gm.UW && k < xcols + gm.UW + n_in)
+                v = ldexp(w[(size_t)o * P + N + (k - xcols - gm.UW)], SX + so - su);
         }
-        const __half hi = __double2half(v);
-        const __half lo = __double2half(v - (double)__half2float(hi));
-        const size_t lo_off = off + (r < rows_main ? SLOT : YTILE);
-        *reinterpret_cast<__half *>(img + off) = hi;
-        *reinterpret_cast<__half *>(img + lo_off) = lo;
+        unsigned char *tile = out + ((size_t)(k >> 6) * 2) * YTILE;
+        store_split(tile, tile + YTILE, sw128_off(o, k & 63), v);
     }
 }
 
@@ -159,7 +153,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Spin with a watchdog: a protocol bug traps instead of hanging the GPU.
+// Spin with a watchdog: a protocol bug traps instead of hanging the GPU.  SLEEP backs
+// off between polls so that the many waiting warps do not steal issue slots from the
+// single MMA-issuing thread and the producer.
+template <bool SLEEP>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
@@ -169,7 +166,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.b32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (spin > (1u << 24)) __trap();
+        if (!done) {
+            if (SLEEP) __nanosleep(64);
+            if (spin > (1u << 24)) __trap();
+        }
     }
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -180,21 +180,23 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    // K-major, SWIZZLE_128B, 8-row groups 1024 B apart, descriptor version 1 (sm_100)
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-           (2ull << 61);
-}
+// Shared-memory matrix descriptor (K-major, SWIZZLE_128B, 8-row groups 1024 B apart,
+// descriptor version 1 of sm_100).  Only the low word depends on the address, so the
+// issuing thread keeps low words in registers and advances them by adds.
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFF) | (1u << 16); }
 __device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
     // D = F32, A = B = F16, both K-major
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(DESC_HI) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
@@ -221,32 +223,41 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+// x (already pre-scaled) -> fp16 hi at `addr`, fp16 lo at `addr + lo_delta`
+__device__ __forceinline__ void split_sts(uint32_t addr, uint32_t lo_delta, float xs) {
+    const __half h = __float2half_rn(xs);
+    const __half l = __float2half_rn(xs - __half2float(h));
+    sts_u16(addr, __half_as_ushort(h));
+    sts_u16(addr + lo_delta, __half_as_ushort(l));
+}
+
 // ------------------------------------------------------------- predict ------
 struct TcParams {
-    int B, T, N, n_in, n_out, transient;
-    int su;                                  // inputs are multiplied by 2^su before the fp16 split
+    int B, T, N, n_in, n_out, transient, feedback;
+    int su, sy;                              // inputs x 2^su, fed-back outputs x 2^sy before the fp16 split
     float noise_amp;
     unsigned long long seed;
-    const unsigned char *image;              // [G][image_bytes]
+    const unsigned char *weights;            // shared image
+    const unsigned char *readouts;           // [G][readout_bytes]
     const float *yscale;                     // [G]
     const float *in, *in_scale, *in_shift, *t_scale, *t_shift;
     const int *group_ids;                    // [B] or null; uniform within each 64-frame tile
+    const float *x0, *y0;                    // [B][N], [B][n_out] (scaled domain) or null
     const float *noise;                      // [B][T][N] uniforms or null
     float *ext_out;                          // [B][T][N+n_in] or null
     float *y_out;                            // [B][T-transient][n_out]
 };
 
-__device__ __forceinline__ void split_store(unsigned char *hi_base, unsigned char *lo_base, int off, float xs) {
-    const __half h = __float2half_rn(xs);
-    const __half l = __float2half_rn(xs - __half2float(h));
-    *reinterpret_cast<__half *>(hi_base + off) = h;
-    *reinterpret_cast<__half *>(lo_base + off) = l;
-}
-
+// DBG = host noise tensor and/or extended-state output requested (parity runs)
+template <bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p) {
     extern __shared__ unsigned char smem_dyn[];
-    __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_d, bar_state;
+    __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_d, bar_state, bar_y, bar_yready;
     __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_key[2][FT];        // noise keys of (frame, step), double-buffered by step parity
 
     const TcGeom gm = tc_geom(p.N, p.n_in);
     const int S = gm.S, C = gm.C;
@@ -254,157 +265,215 @@ __global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p
     unsigned char *st_hi = base;                            // C state tiles, hi halves
     unsigned char *st_lo = base + (size_t)C * STILE;        // C state tiles, lo halves
     unsigned char *ring = base + (size_t)2 * C * STILE;     // NST slots
+    const uint32_t lo_delta = (uint32_t)C * STILE;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile0 = blockIdx.x * FT;
     const int g = p.group_ids ? p.group_ids[tile0] : 0;
-    const unsigned char *img = p.image + (size_t)g * gm.image_bytes;
     const int P = p.N + p.n_in;
+    const bool full_tile = tile0 + FT <= p.B;
     const int items_per_step = 2 * C + 2 * S * C;
 
     if (tid == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
         mbar_init(&bar_d, 1);
+        mbar_init(&bar_y, 1);
+        mbar_init(&bar_yready, 2);
         mbar_init(&bar_state, 4 * S + 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == 3) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(&s_tmem)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = tid; i < 2 * C * STILE / 16; i += TC_THREADS)
         reinterpret_cast<uint4 *>(base)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (p.x0) {                                             // continuation: x_{-1} = x0
+        const float xscale = ldexpf(1.0f, SX);
+        for (int i = tid; i < FT * p.N; i += TC_THREADS) {
+            const int f = i / p.N, n = i - f * p.N, b = tile0 + f;
+            if (b < p.B)
+                split_sts(smem_u32(st_hi) + (n >> 6) * STILE + sw128_off(f, n & 63), lo_delta,
+                          p.x0[(size_t)b * p.N + n] * xscale);
+        }
+    }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
 
-    if (warp == 0) {
-        // ================= producer: stream the weight image, every step =================
-        if (lane == 0) {
-            uint32_t item = 0;
-            for (int it = 0; it <= p.T; ++it) {
-                for (int i = 0; i < items_per_step; ++i, ++item) {
-                    const int slot = item % NST;
-                    mbar_wait(&bar_empty[slot], ((item / NST) & 1) ^ 1);
-                    const unsigned char *src;
-                    uint32_t bytes;
-                    if (i < 2 * C) { src = img + (size_t)S * C * 2 * SLOT + (size_t)i * YTILE; bytes = YTILE; }
-                    else { src = img + (size_t)(i - 2 * C) * SLOT; bytes = SLOT; }
-                    mbar_expect_tx(&bar_full[slot], bytes);
-                    bulk_g2s(ring + (size_t)slot * SLOT, src, bytes, &bar_full[slot]);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t id_main = umma_idesc(128, FT), id_y = umma_idesc(128, 16);
-            const uint32_t hi0 = smem_u32(st_hi), lo0 = smem_u32(st_lo), ring0 = smem_u32(ring);
-            uint32_t item = 0;
-            for (int it = 0; it <= p.T; ++it) {
-                mbar_wait(&bar_state, it & 1);
-                tc_fence_after();
-                // readout y_{it-1} = W_out [x_{it-1}; u_{it-1}]: D_y[frame, out] += state . Wout^T
-                for (int c = 0; c < C; ++c) {
-                    const int ks = (c == C - 1) ? gm.klast : 4;
-                    for (int h = 0; h < 2; ++h, ++item) {
-                        const int slot = item % NST;
-                        mbar_wait(&bar_full[slot], (item / NST) & 1);
-                        tc_fence_after();
-                        const uint32_t wt = ring0 + slot * SLOT;
-                        for (int kk = 0; kk < ks; ++kk) {
-                            const uint64_t bd = umma_desc(wt + kk * 32);
-                            const uint64_t ah = umma_desc(hi0 + c * STILE + kk * 32);
-                            if (h == 0) {
-                                umma_f16(tmem + YCOL, ah, bd, id_y, (c | kk) ? 1u : 0u);
-                                umma_f16(tmem + YCOL, umma_desc(lo0 + c * STILE + kk * 32), bd, id_y, 1u);
-                            } else {
-                                umma_f16(tmem + YCOL, ah, bd, id_y, 1u);
-                            }
-                        }
-                        umma_commit(&bar_empty[slot]);
-                    }
-                }
-                // pre-activations of step it: D_s[neuron, frame] += W_eff tile . state^T
-                for (int s = 0; s < S; ++s) {
-                    for (int c = 0; c < C; ++c) {
-                        const int ks = (c == C - 1) ? gm.klast : 4;
-                        for (int h = 0; h < 2; ++h, ++item) {
-                            const int slot = item % NST;
-                            mbar_wait(&bar_full[slot], (item / NST) & 1);
-                            tc_fence_after();
-                            const uint32_t wt = ring0 + slot * SLOT;
-                            for (int kk = 0; kk < ks; ++kk) {
-                                const uint64_t ad = umma_desc(wt + kk * 32);
-                                const uint64_t bh = umma_desc(hi0 + c * STILE + kk * 32);
-                                if (h == 0) {
-                                    umma_f16(tmem + s * FT, ad, bh, id_main, (c | kk) ? 1u : 0u);
-                                    umma_f16(tmem + s * FT, ad, umma_desc(lo0 + c * STILE + kk * 32), id_main, 1u);
-                                } else {
-                                    umma_f16(tmem + s * FT, ad, bh, id_main, 1u);
-                                }
-                            }
-                            umma_commit(&bar_empty[slot]);
-                        }
-                    }
-                }
-                umma_commit(&bar_d);
-            }
-        }
-    } else if (warp < 4) {
-        // ================= input warps: u_{it+1} into the aug chunk, frame = lane =================
-        const int f = (warp - 2) * 32 + lane, b = tile0 + f;
-        const int row_off = gm.ca * STILE + (f >> 3) * 1024 + (f & 7) * 128;
-        const int ng = gm.UW >> 3;                         // 16-byte granules per input block
-        const float su = ldexpf(1.0f, p.su);
-        float cur[32], nxt[32];
+    if (warp < 2) {
+        // ============ frame warps: thread = frame; inputs, readout, noise keys ============
+        const int f = warp * 32 + lane, b = tile0 + f;
+        const bool live = b < p.B;
+        const uint32_t row = smem_u32(st_hi) + gm.ca * STILE + (f >> 3) * 1024 + (f & 7) * 128;
+        const int fx = f & 7;
+        const int ng = gm.UW >> 3, yg = gm.YO >> 3;
+        const float su = ldexpf(1.0f, p.su), sy = ldexpf(1.0f, p.sy), ys = p.yscale[g];
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        float cur[24], nxt[24];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { cur[j] = 0.f; nxt[j] = 0.f; }
-        auto load_row = [&](int row) {
+        for (int j = 0; j < 24; ++j) { cur[j] = 0.f; nxt[j] = 0.f; }
+        auto load_row = [&](int r) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 24; ++j) {
                 float v = 0.f;
-                if (j < p.n_in && b < p.B && row < p.T) {
-                    v = p.in[((size_t)b * p.T + row) * p.n_in + j] * p.in_scale[j] + p.in_shift[j];
-                    if (p.ext_out) p.ext_out[((size_t)b * p.T + row) * P + p.N + j] = v;
+                if (j < p.n_in && live && r < p.T) {
+                    v = p.in[((size_t)b * p.T + r) * p.n_in + j] * p.in_scale[j] + p.in_shift[j];
+                    if (DBG && p.ext_out) p.ext_out[((size_t)b * p.T + r) * P + p.N + j] = v;
                     v *= su;
                 }
                 nxt[j] = v;
             }
         };
-        auto write_blocks = [&]() {       // block 0 <- nxt (u_it), block 1 <- cur (u_{it-1})
+        auto write_inputs = [&]() {       // block 0 <- nxt (u_it), block 1 <- cur (u_{it-1})
 #pragma unroll
-            for (int gi = 0; gi < 4; ++gi) {
+            for (int gi = 0; gi < 3; ++gi) {
                 if (gi < ng) {
 #pragma unroll
                     for (int blk = 0; blk < 2; ++blk) {
-                        const int gran = ((gi + blk * ng) ^ (f & 7)) << 4;
+                        const uint32_t a = row + (((gi + blk * ng) ^ fx) << 4);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float v = blk == 0 ? nxt[gi * 8 + e] : cur[gi * 8 + e];
-                            split_store(st_hi, st_lo, row_off + gran + e * 2, v);
-                        }
+                        for (int e = 0; e < 8; ++e)
+                            split_sts(a + e * 2, lo_delta, blk == 0 ? nxt[gi * 8 + e] : cur[gi * 8 + e]);
                     }
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) cur[j] = nxt[j];
+            for (int j = 0; j < 24; ++j) cur[j] = nxt[j];
         };
         load_row(0);
-        write_blocks();
+        s_key[0][f] = esn_noise_key(p.seed, (uint32_t)b, 0u);
+        write_inputs();
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_state);
-        for (int it = 0; it < p.T; ++it) {
-            load_row(it + 1);
-            mbar_wait(&bar_d, it & 1);
-            write_blocks();
+        for (int it = 0; it <= p.T; ++it) {
+            if (it < p.T) load_row(it + 1);
+            // ---- readout y_{it-1}: out of TMEM, emit, feed back into the y columns ----
+            mbar_wait<true>(&bar_y, it & 1);
+            tc_fence_after();
+            // every epilogue warp has finished step it-1 by now, so its key row can be replaced
+            s_key[(it + 1) & 1][f] = esn_noise_key(p.seed, (uint32_t)b, (uint32_t)(it + 1));
+            uint32_t yv[16];
+            tmem_ld16(lane_base + YCOL, yv);
+            tmem_ld_wait();
+            float y[16];
+#pragma unroll
+            for (int o = 0; o < 16; ++o) {
+                y[o] = __uint_as_float(yv[o]) * ys;
+                if (it == 0) y[o] = (p.y0 && live && o < p.n_out) ? p.y0[(size_t)b * p.n_out + o] : 0.f;
+                if (o >= p.n_out) y[o] = 0.f;
+            }
+            if (it >= 1 && it - 1 >= p.transient && live) {
+                float *dst = p.y_out + ((size_t)b * (p.T - p.transient) + (it - 1 - p.transient)) * p.n_out;
+#pragma unroll
+                for (int o = 0; o < 16; ++o)
+                    if (o < p.n_out) dst[o] = (y[o] - p.t_shift[o]) / p.t_scale[o];
+            }
+            if (it == p.T) break;
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+                const uint32_t a = row + (((yg + gi) ^ fx) << 4);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split_sts(a + e * 2, lo_delta, p.feedback ? y[gi * 8 + e] * sy : 0.f);
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_yready);
+            // ---- inputs for step it+1 once the big chain of step it is done ----
+            mbar_wait<true>(&bar_d, it & 1);
+            write_inputs();
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_state);
+        }
+    } else if (warp == 2) {
+        // ================= producer: stream the weight image, every step =================
+        if (lane == 0) {
+            const unsigned char *wimg = p.weights;
+            const unsigned char *yimg = p.readouts + (size_t)g * gm.readout_bytes;
+            uint32_t item = 0;
+            for (int it = 0; it <= p.T; ++it) {
+                const int n_items = it == p.T ? 2 * C : items_per_step;
+                for (int i = 0; i < n_items; ++i, ++item) {
+                    const int slot = item % NST;
+                    mbar_wait<false>(&bar_empty[slot], ((item / NST) & 1) ^ 1);
+                    const unsigned char *src;
+                    uint32_t bytes;
+                    if (i < 2 * C) { src = yimg + (size_t)i * YTILE; bytes = YTILE; }
+                    else {
+                        // consumption order: all state chunks of every slab, then the aug chunk of every slab
+                        int m = i - 2 * C, s, c, h;
+                        const int main_items = 2 * S * (C - 1);
+                        if (m < main_items) { s = m / (2 * (C - 1)); m -= s * 2 * (C - 1); c = m >> 1; h = m & 1; }
+                        else { m -= main_items; s = m >> 1; h = m & 1; c = C - 1; }
+                        src = wimg + ((size_t)(s * C + c) * 2 + h) * SLOT;
+                        bytes = SLOT;
+                    }
+                    mbar_expect_tx(&bar_full[slot], bytes);
+                    bulk_g2s(ring + (size_t)slot * SLOT, src, bytes, &bar_full[slot]);
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t id_main = umma_idesc(128, FT), id_y = umma_idesc(128, 16);
+            const uint32_t hi0 = desc_lo(smem_u32(st_hi)), ring0 = smem_u32(ring);
+            const uint32_t lod = lo_delta >> 4;            // hi -> lo state tile, in descriptor units
+            uint32_t item = 0;
+            // one ring item: streamed tile in the slot, state chunk c, hi (h=0) or lo (h=1) half of
+            // the streamed operand; 2 (h=0) or 1 (h=1) MMAs per 16-wide k-step
+            auto chain = [&](bool readout, uint32_t d, int c, int h, int ks, bool first) {
+                const int slot = item % NST;
+                mbar_wait<false>(&bar_full[slot], (item / NST) & 1);
+                tc_fence_after();
+                const uint32_t w = desc_lo(ring0 + slot * SLOT);
+                const uint32_t x = hi0 + c * (STILE >> 4);
+                const uint32_t idesc = readout ? id_y : id_main;
+#pragma unroll 4
+                for (int kk = 0; kk < ks; ++kk) {
+                    const uint32_t wk = w + kk * 2, xk = x + kk * 2;
+                    const uint32_t acc = (first && kk == 0) ? 0u : 1u;
+                    // readout: D_y[frame, out] += state . W_out^T ; else D_s[neuron, frame] += W . state^T
+                    if (h == 0) {
+                        umma_f16(d, readout ? xk : wk, readout ? wk : xk, idesc, acc);
+                        umma_f16(d, readout ? xk + lod : wk, readout ? wk : xk + lod, idesc, 1u);
+                    } else {
+                        umma_f16(d, readout ? xk : wk, readout ? wk : xk, idesc, 1u);
+                    }
+                }
+                umma_commit(&bar_empty[slot]);
+                ++item;
+            };
+            for (int it = 0; it <= p.T; ++it) {
+                mbar_wait<false>(&bar_state, it & 1);
+                tc_fence_after();
+                for (int c = 0; c < C; ++c) {
+                    const int ks = (c == C - 1) ? gm.YO / 16 : 4;
+                    chain(true, tmem + YCOL, c, 0, ks, c == 0);
+                    chain(true, tmem + YCOL, c, 1, ks, false);
+                }
+                umma_commit(&bar_y);
+                if (it == p.T) break;                    // only the last readout is left
+                for (int s = 0; s < S; ++s)
+                    for (int c = 0; c < C - 1; ++c) {
+                        chain(false, tmem + s * FT, c, 0, 4, c == 0);
+                        chain(false, tmem + s * FT, c, 1, 4, false);
+                    }
+                mbar_wait<false>(&bar_yready, it & 1);   // y_{it-1} is in the state tile
+                tc_fence_after();
+                for (int s = 0; s < S; ++s) {
+                    chain(false, tmem + s * FT, C - 1, 0, gm.kaug, false);
+                    chain(false, tmem + s * FT, C - 1, 1, gm.kaug, false);
+                }
+                umma_commit(&bar_d);
+            }
         }
     } else {
         // ================= epilogue warps: TMEM -> tanh -> fp16 hi/lo state =================
@@ -412,49 +481,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p
         if (s < S) {
             const int n = s * 128 + q * 32 + lane;         // neuron of this thread (TMEM lane)
             const bool n_ok = n < p.N;
-            const int c = n >> 6, k = n & 63;
+            const int k = n & 63;
             const float dscale = ldexpf(1.0f, -(SX + SW)), xscale = ldexpf(1.0f, SX);
-            const float ys = p.yscale[g];
-            const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+            const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + s * FT;
             const bool use_noise = p.noise_amp != 0.f;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_state);        // initial (all-zero) state is in place
-            for (int it = 0; it <= p.T; ++it) {
-                mbar_wait(&bar_d, it & 1);
-                tc_fence_after();
-                if (e < 2) {                               // readout of step it-1, frame = 32 e + lane
-                    uint32_t yv[16];
-                    tmem_ld16(lane_base + YCOL, yv);
-                    tmem_ld_wait();
-                    const int b = tile0 + e * 32 + lane, row = it - 1;
-                    if (row >= p.transient && b < p.B) {
-                        float *dst = p.y_out + ((size_t)b * (p.T - p.transient) + (row - p.transient)) * p.n_out;
+            const uint32_t nmul = (uint32_t)n * 0xC2B2AE35U;
+            const uint32_t tile = smem_u32(st_hi) + (n >> 6) * STILE + (k & 7) * 2;
+            uint32_t goff[8];                              // row-in-group + swizzled granule offsets
 #pragma unroll
-                        for (int o = 0; o < 16; ++o)
-                            if (o < p.n_out) dst[o] = (__uint_as_float(yv[o]) * ys - p.t_shift[o]) / p.t_scale[o];
-                    }
-                }
-                if (it == p.T) break;
+            for (int i = 0; i < 8; ++i) goff[i] = i * 128 + ((((k >> 3) & 7) ^ i) << 4);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_state);        // initial state is in place
+            for (int it = 0; it < p.T; ++it) {
+                mbar_wait<true>(&bar_d, it & 1);
+                tc_fence_after();
+                const uint32_t *keys = s_key[it & 1];
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     uint32_t v[32];
-                    tmem_ld32(lane_base + s * FT + half * 32, v);
+                    tmem_ld32(lane_base + half * 32, v);
                     tmem_ld_wait();
+                    const uint32_t hbase = tile + half * 4096;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const int f = half * 32 + j, b = tile0 + f;
-                        float x = 0.f;
-                        if (n_ok && b < p.B) {
-                            x = tanhf(__uint_as_float(v[j]) * dscale);
-                            if (use_noise) {
-                                float u;
-                                if (p.noise) u = p.noise[((size_t)b * p.T + it) * p.N + n];
-                                else u = esn_noise_uniform(esn_noise_key(p.seed, (uint32_t)b, (uint32_t)it), (uint32_t)n);
-                                x += p.noise_amp * (u - 0.5f);
+                        const int f = half * 32 + j;
+                        float x = tanhf(__uint_as_float(v[j]) * dscale);
+                        if (use_noise) {
+                            float u;
+                            if (DBG && p.noise) {
+                                const int b = tile0 + f;
+                                u = (b < p.B && n_ok) ? p.noise[((size_t)b * p.T + it) * p.N + n] : 0.5f;
+                            } else {
+                                u = (float)(esn_mix32(keys[f] + nmul) >> 8) * (1.0f / 16777216.0f);
                             }
-                            if (p.ext_out) p.ext_out[((size_t)b * p.T + it) * P + n] = x;
+                            x = fmaf(p.noise_amp, u - 0.5f, x);
                         }
-                        split_store(st_hi, st_lo, c * STILE + sw128_off(f, k), x * xscale);
+                        if (!n_ok || (!full_tile && tile0 + f >= p.B)) x = 0.f;
+                        if (DBG && p.ext_out && n_ok && tile0 + f < p.B)
+                            p.ext_out[((size_t)(tile0 + f) * p.T + it) * P + n] = x;
+                        split_sts(hbase + (j >> 3) * 1024 + goff[j & 7], lo_delta, x * xscale);
                     }
                 }
                 fence_async_smem();
@@ -466,7 +531,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 3) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
     }
 }
@@ -474,30 +539,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p
 }  // namespace
 
 extern "C" int esn_tc_supported(int N, int n_in, int n_out) {
-    return (N > 0 && N <= 512 && n_in > 0 && n_in <= 32 && n_out > 0 && n_out <= 16) ? 1 : 0;
+    return (N > 0 && N <= 512 && n_in > 0 && n_in <= 24 && n_out > 0 && n_out <= 16) ? 1 : 0;
 }
 
-extern "C" long long esn_tc_image_bytes(int N, int n_in) {
-    return (long long)tc_geom(N, n_in).image_bytes;
-}
+extern "C" long long esn_tc_weight_bytes(int N, int n_in) { return (long long)tc_geom(N, n_in).weight_bytes; }
+extern "C" long long esn_tc_readout_bytes(int N, int n_in) { return (long long)tc_geom(N, n_in).readout_bytes; }
 
-extern "C" int esn_tc_prepare(const double *W, const double *W_in, const double *W_fb, const double *W_out,
-                              int N, int n_in, int n_out, int n_groups, int su_exp, int feedback,
-                              void *image, float *yscale, int32_t *so_workspace, void *stream) {
-    if (!W || !W_in || !W_fb || !W_out || !image || !yscale || !so_workspace) return ESN_E_BADARG;
-    if (!esn_tc_supported(N, n_in, n_out) || n_groups <= 0) return ESN_E_UNSUPPORTED;
-    PrepParams p;
-    p.W = W; p.W_in = W_in; p.W_fb = W_fb; p.W_out = W_out;
-    p.N = N; p.n_in = n_in; p.n_out = n_out; p.G = n_groups; p.su = su_exp; p.feedback = feedback;
-    p.image = (unsigned char *)image; p.yscale = yscale; p.so = so_workspace;
-    cudaStream_t st = (cudaStream_t)stream;
-    tc_wout_scale_kernel<<<n_groups, 256, 0, st>>>(p);
-    int rc = esn_launch_status();
-    if (rc) return rc;
+extern "C" int esn_tc_prepare_weights(const double *W, const double *W_in, const double *W_fb, int N, int n_in,
+                                      int n_out, int su_exp, int sy_exp, int feedback, void *image, void *stream) {
+    if (!W || !W_in || !W_fb || !image) return ESN_E_BADARG;
+    if (!esn_tc_supported(N, n_in, n_out)) return ESN_E_UNSUPPORTED;
     const TcGeom gm = tc_geom(N, n_in);
-    const size_t total = (size_t)(gm.S * 128 + 16) * gm.C * 64;
-    dim3 grid((unsigned)std::min<size_t>((total + 255) / 256, 1024), n_groups);
-    tc_prepare_kernel<<<grid, 256, 0, st>>>(p);
+    const size_t total = (size_t)gm.S * 128 * gm.C * 64;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 2048);
+    tc_prepare_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, W_in, W_fb, N, n_in, n_out, su_exp, sy_exp,
+                                                                       feedback, (unsigned char *)image);
+    return esn_launch_status();
+}
+
+extern "C" int esn_tc_prepare_readout(const double *W_out, int N, int n_in, int n_out, int n_groups, int su_exp,
+                                      void *image, float *yscale, void *stream) {
+    if (!W_out || !image || !yscale || n_groups <= 0) return ESN_E_BADARG;
+    if (!esn_tc_supported(N, n_in, n_out)) return ESN_E_UNSUPPORTED;
+    tc_prepare_readout_kernel<<<n_groups, 256, 0, (cudaStream_t)stream>>>(W_out, N, n_in, n_out, su_exp,
+                                                                          (unsigned char *)image, yscale);
     return esn_launch_status();
 }
 
@@ -505,20 +570,29 @@ extern "C" int esn_tc_predict(const esn_tc_predict_args *a, void *stream) {
     if (!a) return ESN_E_BADARG;
     if (a->B <= 0 || a->T <= 0 || a->transient < 0 || a->transient >= a->T) return ESN_E_BADARG;
     if (!esn_tc_supported(a->N, a->n_in, a->n_out)) return ESN_E_UNSUPPORTED;
-    if (!a->image || !a->yscale || !a->in || !a->in_scale || !a->in_shift || !a->t_scale || !a->t_shift ||
-        !a->y_out)
+    if (!a->weights || !a->readouts || !a->yscale || !a->in || !a->in_scale || !a->in_shift || !a->t_scale ||
+        !a->t_shift || !a->y_out)
         return ESN_E_BADARG;
     TcParams p;
     p.B = a->B; p.T = a->T; p.N = a->N; p.n_in = a->n_in; p.n_out = a->n_out; p.transient = a->transient;
-    p.su = a->su_exp; p.noise_amp = (float)a->noise_amp; p.seed = a->seed;
-    p.image = (const unsigned char *)a->image; p.yscale = a->yscale;
+    p.feedback = a->feedback; p.su = a->su_exp; p.sy = a->sy_exp;
+    p.noise_amp = (float)a->noise_amp; p.seed = a->seed;
+    p.weights = (const unsigned char *)a->weights; p.readouts = (const unsigned char *)a->readouts;
+    p.yscale = a->yscale;
     p.in = a->in; p.in_scale = a->in_scale; p.in_shift = a->in_shift; p.t_scale = a->t_scale; p.t_shift = a->t_shift;
-    p.group_ids = a->group_ids; p.noise = a->noise_uniforms; p.ext_out = a->ext_out; p.y_out = a->y_out;
+    p.group_ids = a->group_ids; p.x0 = a->x0; p.y0 = a->y0; p.noise = a->noise_uniforms;
+    p.ext_out = a->ext_out; p.y_out = a->y_out;
     const TcGeom gm = tc_geom(a->N, a->n_in);
     const size_t smem = (size_t)2 * gm.C * STILE + (size_t)NST * SLOT + 1024;
-    if (smem > 227 * 1024 - 512) return ESN_E_TOOLARGE;
-    ESN_CUDA_TRY(cudaFuncSetAttribute(esn_predict_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 227 * 1024 - 1024) return ESN_E_TOOLARGE;
     const int grid = (a->B + FT - 1) / FT;
-    esn_predict_tc<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
+    const bool dbg = a->noise_uniforms || a->ext_out;
+    if (dbg) {
+        ESN_CUDA_TRY(cudaFuncSetAttribute(esn_predict_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        esn_predict_tc<true><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
+    } else {
+        ESN_CUDA_TRY(cudaFuncSetAttribute(esn_predict_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        esn_predict_tc<false><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
+    }
     return esn_launch_status();
 }

@@ -42,11 +42,13 @@ class RecurrenceArgs(C.Structure):
 class TcPredictArgs(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("T", C.c_int32), ("N", C.c_int32), ("n_in", C.c_int32), ("n_out", C.c_int32),
-        ("transient", C.c_int32), ("su_exp", C.c_int32), ("n_groups", C.c_int32),
+        ("transient", C.c_int32), ("feedback", C.c_int32), ("su_exp", C.c_int32), ("sy_exp", C.c_int32),
+        ("n_groups", C.c_int32),
         ("noise_amp", C.c_double), ("seed", C.c_uint64),
-        ("image", C.c_void_p), ("yscale", C.c_void_p), ("inp", C.c_void_p),
+        ("weights", C.c_void_p), ("readouts", C.c_void_p), ("yscale", C.c_void_p), ("inp", C.c_void_p),
         ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("t_scale", C.c_void_p), ("t_shift", C.c_void_p),
-        ("group_ids", C.c_void_p), ("noise_uniforms", C.c_void_p), ("ext_out", C.c_void_p), ("y_out", C.c_void_p),
+        ("group_ids", C.c_void_p), ("x0", C.c_void_p), ("y0", C.c_void_p), ("noise_uniforms", C.c_void_p),
+        ("ext_out", C.c_void_p), ("y_out", C.c_void_p),
     ]
 
 
@@ -59,8 +61,10 @@ SIGNATURES = {
     "esn_pad_sizes": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "esn_recurrence_run": (_i, [C.POINTER(RecurrenceArgs), _vp]),
     "esn_tc_supported": (_i, [_i, _i, _i]),
-    "esn_tc_image_bytes": (C.c_longlong, [_i, _i]),
-    "esn_tc_prepare": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "esn_tc_weight_bytes": (C.c_longlong, [_i, _i]),
+    "esn_tc_readout_bytes": (C.c_longlong, [_i, _i]),
+    "esn_tc_prepare_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "esn_tc_prepare_readout": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "esn_tc_predict": (_i, [C.POINTER(TcPredictArgs), _vp]),
     "esn_gram_f64": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "esn_cholesky_solve_f64": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),

@@ -53,8 +53,9 @@ def _vec(v, n, default, device):
 class TcReadout:
     """Handle of the tensor-core weight image built by Reservoir.tc_prepare."""
 
-    def __init__(self, image, yscale, su_exp, n_groups):
-        self.image, self.yscale, self.su_exp, self.n_groups = image, yscale, su_exp, n_groups
+    def __init__(self, weights, image, yscale, su_exp, sy_exp, n_groups):
+        self.weights, self.image, self.yscale = weights, image, yscale
+        self.su_exp, self.sy_exp, self.n_groups = su_exp, sy_exp, n_groups
 
 
 class Reservoir:
@@ -90,6 +91,7 @@ class Reservoir:
         self._W64 = torch.from_numpy(np.ascontiguousarray(W)).to(self.device)
         self._Win64 = torch.from_numpy(np.ascontiguousarray(W_in)).to(self.device)
         self._Wfb64 = torch.from_numpy(np.ascontiguousarray(W_fb)).to(self.device)
+        self._tc_images = {}
         self._wt = {ESN_F64: torch.from_numpy(wt).to(self.device)}
         self._wt[ESN_F32] = self._wt[ESN_F64].to(torch.float32)
         self._aff = {ESN_F64: dict(
@@ -189,26 +191,50 @@ class Reservoir:
             raise EsnB200Error("inputs too large for the tensor-core path (max |u| > 256); use precision='fp32'")
         return min(su, 24)
 
-    def tc_prepare(self, W_out, su_exp):
-        """Fold the output feedback into the weights for every readout in
-        W_out [G, n_out, P] and build the UMMA-ready fp16 hi/lo image."""
+    def output_scale_exponent(self, y_absmax):
+        """sy_exp for the tensor-core path: brings the largest fed-back output
+        (scaled teacher domain) to about 2^6, leaving 2^10 of fp16 headroom."""
+        y_absmax = float(y_absmax)
+        if not np.isfinite(y_absmax) or y_absmax <= 0:
+            return 0
+        return int(np.clip(6 - int(np.ceil(np.log2(y_absmax))), -8, 40))
+
+    def _tc_weights(self, su_exp, sy_exp):
+        key = (int(su_exp), int(sy_exp))
+        if key not in self._tc_images:
+            nbytes = int(self.lib.esn_tc_weight_bytes(self.N, self.n_in))
+            image = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+            check(self.lib.esn_tc_prepare_weights(ptr(self._W64), ptr(self._Win64), ptr(self._Wfb64), self.N,
+                                                  self.n_in, self.n_out, key[0], key[1],
+                                                  int(self.teacher_forcing), ptr(image), _stream()),
+                  "esn_tc_prepare_weights")
+            self._tc_images[key] = image
+        return self._tc_images[key]
+
+    def tc_prepare(self, W_out, su_exp, y_absmax=None):
+        """Build the per-readout tensor-core images for W_out [G, n_out, P]
+        (and, once per (su, sy), the shared weight image).  `y_absmax`: largest
+        |scaled teacher| the readouts were trained on (sets the feedback
+        pre-scale); defaults to the t_scale magnitude."""
         if not self.tc_supported():
-            raise EsnB200Error("tensor-core path needs N <= 512, n_inputs <= 32, n_outputs <= 16")
+            raise EsnB200Error("tensor-core path needs N <= 512, n_inputs <= 24, n_outputs <= 16")
         W_out = self._as(W_out, torch.float64, 3)
         G = W_out.shape[0]
-        nbytes = int(self.lib.esn_tc_image_bytes(self.N, self.n_in))
+        if y_absmax is None:
+            aff = self._aff[ESN_F64]
+            y_absmax = float((aff["t_scale"].abs() * 4 + aff["t_shift"].abs()).max().item())
+        sy_exp = self.output_scale_exponent(y_absmax)
+        weights = self._tc_weights(su_exp, sy_exp)
+        nbytes = int(self.lib.esn_tc_readout_bytes(self.N, self.n_in))
         image = torch.empty((G, nbytes), dtype=torch.uint8, device=self.device)
         yscale = torch.empty((G,), dtype=torch.float32, device=self.device)
-        so = torch.empty((G,), dtype=torch.int32, device=self.device)
-        check(self.lib.esn_tc_prepare(ptr(self._W64), ptr(self._Win64), ptr(self._Wfb64), ptr(W_out), self.N,
-                                      self.n_in, self.n_out, G, int(su_exp), int(self.teacher_forcing),
-                                      ptr(image), ptr(yscale), ptr(so), _stream()), "esn_tc_prepare")
-        return TcReadout(image, yscale, int(su_exp), G)
+        check(self.lib.esn_tc_prepare_readout(ptr(W_out), self.N, self.n_in, self.n_out, G, int(su_exp),
+                                              ptr(image), ptr(yscale), _stream()), "esn_tc_prepare_readout")
+        return TcReadout(weights, image, yscale, int(su_exp), sy_exp, G)
 
-    def predict_tc(self, inputs, readout, transient=0, group_ids=None, noise_uniforms=None, seed=0,
-                   return_ext=False):
-        """Free-running prediction on the tensor cores (continuation=False
-        semantics: zero initial state and output).  `readout` comes from
+    def predict_tc(self, inputs, readout, transient=0, group_ids=None, x0=None, y0=None,
+                   noise_uniforms=None, seed=0, return_ext=False):
+        """Free-running prediction on the tensor cores.  `readout` comes from
         tc_prepare; each 64-frame tile must use a single readout."""
         inputs = self._as(inputs, torch.float32, 3)
         B, T, n_in = inputs.shape
@@ -216,10 +242,12 @@ class Reservoir:
             raise ValueError(f"inputs have {n_in} columns, ESN has n_inputs={self.n_in}")
         a = _lib.TcPredictArgs()
         a.B, a.T, a.N, a.n_in, a.n_out = B, T, self.N, self.n_in, self.n_out
-        a.transient, a.su_exp, a.n_groups = int(transient), readout.su_exp, readout.n_groups
+        a.transient, a.feedback = int(transient), int(self.teacher_forcing)
+        a.su_exp, a.sy_exp, a.n_groups = readout.su_exp, readout.sy_exp, readout.n_groups
         a.noise_amp, a.seed = self.noise, int(seed) & 0xFFFFFFFFFFFFFFFF
         aff = self._aff[ESN_F32]
-        a.image, a.yscale, a.inp = ptr(readout.image), ptr(readout.yscale), ptr(inputs)
+        a.weights, a.readouts, a.yscale = ptr(readout.weights), ptr(readout.image), ptr(readout.yscale)
+        a.inp = ptr(inputs)
         a.in_scale, a.in_shift = ptr(aff["in_scale"]), ptr(aff["in_shift"])
         a.t_scale, a.t_shift = ptr(aff["t_scale"]), ptr(aff["t_shift"])
         keep = [inputs]
@@ -229,6 +257,12 @@ class Reservoir:
             keep.append(group_ids)
         elif readout.n_groups != 1:
             raise ValueError("group_ids required when the readout handle holds more than one readout")
+        if x0 is not None:
+            x0 = self._as(x0, torch.float32, 2)
+            a.x0 = ptr(x0)
+        if y0 is not None:
+            y0 = self._as(y0, torch.float32, 2)
+            a.y0 = ptr(y0)
         if noise_uniforms is not None:
             noise_uniforms = self._as(noise_uniforms, torch.float32, 3)
             if tuple(noise_uniforms.shape) != (B, T, self.N):
@@ -256,8 +290,6 @@ class Reservoir:
         using readout W_out[group_ids[b]].  Returns y [B, T-transient, n_out]
         in teacher units (and E if return_ext)."""
         if precision == "tc":
-            if x0 is not None or y0 is not None:
-                raise EsnB200Error("the tensor-core path starts from the zero state (continuation=False)")
             if not isinstance(W_out, TcReadout):
                 W_out = self.tc_prepare(W_out, self.input_scale_exponent(inputs))
             if group_ids is not None:
@@ -268,7 +300,7 @@ class Reservoir:
                 tiles = tiles.view(-1, 64)
                 if not bool((tiles == tiles[:, :1]).all()):
                     raise EsnB200Error("tensor-core path: each 64-frame tile must share one readout")
-            return self.predict_tc(inputs, W_out, transient=transient, group_ids=group_ids,
+            return self.predict_tc(inputs, W_out, transient=transient, group_ids=group_ids, x0=x0, y0=y0,
                                    noise_uniforms=noise_uniforms, seed=seed, return_ext=return_ext)
         ext, y = self._run(MODE_PREDICT, dtype_code(precision), inputs, W_out=W_out,
                            group_ids=group_ids, x0=x0, y0=y0, noise_uniforms=noise_uniforms,

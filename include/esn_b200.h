@@ -104,42 +104,51 @@ int esn_pad_sizes(int N, int n_in, int n_out, int *N_pad_host, int *K_aug_pad_ho
 int esn_recurrence_run(const esn_recurrence_args *args_host, void *stream);
 
 /* ---------------------------------------------------------------------------
- * Tensor-core recurrence (tcgen05 + TMEM), free-running predict only.  Same
- * reference lines as esn_recurrence_run in PREDICT mode (libs/pyESN.py:243-255)
- * with zero initial state/output (continuation=False).  fp16 hi/lo operand
- * split (three MMAs per product, fp32 accumulation in TMEM), 64 frames per CTA;
- * frames of one 64-frame tile share one readout (group_ids uniform per tile).
+ * Tensor-core recurrence (tcgen05 + TMEM), free-running predict.  Same reference
+ * lines as esn_recurrence_run in PREDICT mode (libs/pyESN.py:243-255).  fp16
+ * hi/lo operand split (three MMAs per product, fp32 accumulation in TMEM), 64
+ * frames per CTA; the frames of one 64-frame tile share one readout (group_ids
+ * uniform per tile).  N <= 512, n_in <= 24, n_out <= 16.
  *
- * esn_tc_prepare folds the output feedback into the weights per readout g
- * (W_eff = W + W_fb W_out_x, extra input block W_fb W_out_u for u_{t-1}) in fp64
- * and writes the pre-swizzled UMMA-ready fp16 image [n_groups][esn_tc_image_bytes].
- * su_exp: inputs (after in_scale/in_shift) are multiplied by 2^su_exp before the
- * fp16 split; choose it so that max|u| 2^su_exp is about 2^9 (1 <= su_exp).
+ * esn_tc_prepare_weights builds the UMMA-ready (pre-swizzled, fp16 hi/lo) image
+ * of [W | W_in | 0 | W_feedb] once per reservoir -- it is shared by all CTAs and
+ * all readouts.  esn_tc_prepare_readout builds the small per-readout image of
+ * W_out (and yscale[g]).  Power-of-two pre-scales keep the fp16 halves in range:
+ *   su_exp: inputs (after in_scale/in_shift) are multiplied by 2^su_exp; choose
+ *           it so that max|u| 2^su_exp is about 2^9 (su_exp >= 1);
+ *   sy_exp: fed-back outputs (scaled teacher domain) are multiplied by 2^sy_exp;
+ *           choose it so that max|y| 2^sy_exp is about 2^6.
  * ------------------------------------------------------------------------- */
 typedef struct esn_tc_predict_args {
     int32_t B, T;
     int32_t N, n_in, n_out;
     int32_t transient;
-    int32_t su_exp;
+    int32_t feedback;           /* 1 = teacher_forcing (W_feedb y fed back) */
+    int32_t su_exp, sy_exp;
     int32_t n_groups;
     double  noise_amp;
     uint64_t seed;
-    const void *image;          /* from esn_tc_prepare */
-    const float *yscale;        /* [n_groups], from esn_tc_prepare */
+    const void *weights;        /* from esn_tc_prepare_weights (same su_exp, sy_exp) */
+    const void *readouts;       /* [n_groups][esn_tc_readout_bytes], from esn_tc_prepare_readout */
+    const float *yscale;        /* [n_groups], from esn_tc_prepare_readout */
     const float *in;            /* [B][T][n_in] raw inputs (fp32) */
     const float *in_scale, *in_shift;   /* [n_in] */
     const float *t_scale, *t_shift;     /* [n_out] */
     const int32_t *group_ids;   /* [B] or null */
+    const float *x0;            /* [B][N] initial state or null (zeros) */
+    const float *y0;            /* [B][n_out] initial output (scaled domain) or null */
     const float *noise_uniforms;/* [B][T][N] or null (device counter stream) */
     float *ext_out;             /* [B][T][N+n_in] or null */
     float *y_out;               /* [B][T-transient][n_out] */
 } esn_tc_predict_args;
 
 int esn_tc_supported(int N, int n_in, int n_out);
-long long esn_tc_image_bytes(int N, int n_in);
-int esn_tc_prepare(const double *W, const double *W_in, const double *W_fb, const double *W_out,
-                   int N, int n_in, int n_out, int n_groups, int su_exp, int feedback,
-                   void *image, float *yscale, int32_t *so_workspace, void *stream);
+long long esn_tc_weight_bytes(int N, int n_in);
+long long esn_tc_readout_bytes(int N, int n_in);
+int esn_tc_prepare_weights(const double *W, const double *W_in, const double *W_fb, int N, int n_in,
+                           int n_out, int su_exp, int sy_exp, int feedback, void *image, void *stream);
+int esn_tc_prepare_readout(const double *W_out, int N, int n_in, int n_out, int n_groups, int su_exp,
+                           void *image, float *yscale, void *stream);
 int esn_tc_predict(const esn_tc_predict_args *args_host, void *stream);
 
 /* ---------------------------------------------------------------------------

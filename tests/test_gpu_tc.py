@@ -115,6 +115,31 @@ def test_tc_padded_reservoir_and_small_io():
         _check(eng, Ws, aff, us, W_outs, None, T, 2, 0.001, uni)
 
 
+def test_tc_continuation_and_strong_feedback():
+    """continuation=True semantics (explicit x0 / y0) and a teacher scale large
+    enough that the W_fb y term matters (SISO demo regime)."""
+    rng, Ws, aff, eng = _setup(128, 2, 2, seed=9, noise=0.001, in_scale=0.05, t_scale=5e-2)
+    B, T, N = 40, 25, 128
+    us = rng.randn(B, T, 2)
+    W_outs = rng.randn(1, 2, N + 2) * 3e-3
+    x0 = rng.randn(B, N) * 0.1
+    y0 = rng.randn(B, 2) * 0.05
+    uni = rng.rand(B, T, N)
+    rd = eng.tc_prepare(_cuda(W_outs), eng.input_scale_exponent(_cuda(us)), y_absmax=0.2)
+    y, ext = eng.predict_tc(_cuda(us), rd, x0=_cuda(x0), y0=_cuda(y0), noise_uniforms=_cuda(uni), return_ext=True)
+    y, ext = y.double().cpu().numpy(), ext.double().cpu().numpy()
+    fb_effect = 0.0
+    for b in range(B):
+        ref, st = orc.predict(Ws[0], Ws[1], Ws[2], W_outs[0], us[b], 0, 0.001, uni[b], x0=x0[b], y0=y0[b],
+                              return_states=True, **aff)
+        assert rel_err(ext[b, :, :N], st) < 1e-5
+        assert rel_err(y[b], ref) < 1e-4
+        nofb = orc.predict(Ws[0], Ws[1], Ws[2], W_outs[0], us[b], 0, 0.001, uni[b], x0=x0[b], y0=None,
+                           **{**aff, "teacher_forcing": False})
+        fb_effect = max(fb_effect, rel_err(nofb, ref))
+    assert fb_effect > 1e-2           # the feedback path really is exercised
+
+
 def test_tc_rejects_what_it_cannot_do():
     from esn_b200 import EsnB200Error
     rng, Ws, aff, eng = _setup(128, 4, 4, seed=1)
@@ -123,8 +148,6 @@ def test_tc_rejects_what_it_cannot_do():
     gid = torch.arange(130, device="cuda") % 2                  # mixed readouts inside a tile
     with pytest.raises(EsnB200Error):
         eng.predict(us, W_outs, group_ids=gid, precision="tc")
-    with pytest.raises(EsnB200Error):
-        eng.predict(us, W_outs[:1], x0=torch.zeros(130, 128), precision="tc")
     rng, Ws, aff, big = _setup(640, 4, 4, seed=2)
     with pytest.raises(EsnB200Error):
         big.predict(_cuda(rng.randn(4, 6, 4)), _cuda(rng.randn(1, 4, 644)), precision="tc")
