@@ -234,6 +234,22 @@ __device__ __forceinline__ void split_sts(uint32_t addr, uint32_t lo_delta, floa
     sts_u16(addr + lo_delta, __half_as_ushort(l));
 }
 
+// tanh to ~1e-7: odd Taylor series below 0.35 (truncation < 5e-9), 1 - 2/(e^{2|z|}+1) above
+__device__ __forceinline__ float tanh_f32(float z) {
+    const float az = fabsf(z);
+    if (az < 0.35f) {
+        const float z2 = z * z;
+        float p = -0.008863235f;                 // -1382/155925
+        p = fmaf(p, z2, 0.021869488f);           //  62/2835
+        p = fmaf(p, z2, -0.053968254f);          // -17/315
+        p = fmaf(p, z2, 0.133333333f);           //  2/15
+        p = fmaf(p, z2, -0.333333333f);          // -1/3
+        return fmaf(z * z2, p, z);
+    }
+    const float e = __expf(2.0f * az);
+    return copysignf(1.0f - __fdividef(2.0f, e + 1.0f), z);
+}
+
 // ------------------------------------------------------------- predict ------
 struct TcParams {
     int B, T, N, n_in, n_out, transient, feedback;
@@ -249,6 +265,7 @@ struct TcParams {
     const float *noise;                      // [B][T][N] uniforms or null
     float *ext_out;                          // [B][T][N+n_in] or null
     float *y_out;                            // [B][T-transient][n_out]
+    long long *timeline;                     // [T+1][8] SM-clock stamps of CTA 0 (profiling aid) or null
 };
 
 // DBG = host noise tensor and/or extended-state output requested (parity runs)
@@ -451,9 +468,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p
                 umma_commit(&bar_empty[slot]);
                 ++item;
             };
+            const bool stamp = p.timeline && blockIdx.x == 0;
             for (int it = 0; it <= p.T; ++it) {
+                if (stamp) p.timeline[it * 8 + 0] = clock64();       // waiting for the state tile
                 mbar_wait<false>(&bar_state, it & 1);
                 tc_fence_after();
+                if (stamp) p.timeline[it * 8 + 1] = clock64();       // state ready, issue starts
                 for (int c = 0; c < C; ++c) {
                     const int ks = (c == C - 1) ? gm.YO / 16 : 4;
                     chain(true, tmem + YCOL, c, 0, ks, c == 0);
@@ -466,6 +486,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p
                         chain(false, tmem + s * FT, c, 0, 4, c == 0);
                         chain(false, tmem + s * FT, c, 1, 4, false);
                     }
+                if (stamp) p.timeline[it * 8 + 2] = clock64();       // main chain issued
                 mbar_wait<false>(&bar_yready, it & 1);   // y_{it-1} is in the state tile
                 tc_fence_after();
                 for (int s = 0; s < S; ++s) {
@@ -473,6 +494,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p
                     chain(false, tmem + s * FT, C - 1, 1, gm.kaug, false);
                 }
                 umma_commit(&bar_d);
+                if (stamp) p.timeline[it * 8 + 3] = clock64();       // everything issued
             }
         }
     } else {
@@ -495,6 +517,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p
             for (int it = 0; it < p.T; ++it) {
                 mbar_wait<true>(&bar_d, it & 1);
                 tc_fence_after();
+                if (p.timeline && blockIdx.x == 0 && warp == 4 && lane == 0) p.timeline[it * 8 + 4] = clock64();
                 const uint32_t *keys = s_key[it & 1];
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
@@ -505,7 +528,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int f = half * 32 + j;
-                        float x = tanhf(__uint_as_float(v[j]) * dscale);
+                        float x = tanh_f32(__uint_as_float(v[j]) * dscale);
                         if (use_noise) {
                             float u;
                             if (DBG && p.noise) {
@@ -514,7 +537,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p
                             } else {
                                 u = (float)(esn_mix32(keys[f] + nmul) >> 8) * (1.0f / 16777216.0f);
                             }
-                            x = fmaf(p.noise_amp, u - 0.5f, x);
+                            x = fmaf(u, p.noise_amp, x - 0.5f * p.noise_amp);
                         }
                         if (!n_ok || (!full_tile && tile0 + f >= p.B)) x = 0.f;
                         if (DBG && p.ext_out && n_ok && tile0 + f < p.B)
@@ -526,6 +549,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_state);
+                if (p.timeline && blockIdx.x == 0 && warp == 4 && lane == 0) p.timeline[it * 8 + 5] = clock64();
             }
         }
     }
@@ -533,6 +557,385 @@ __global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p
     __syncthreads();
     if (warp == 3) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+
+// =====================================================================================
+// Pair kernel: two CTAs of a cluster (one TPC) work as one 256-row tensor core
+// (tcgen05 cta_group::2).  The pair owns 128 frames; CTA r keeps the state tile of its
+// own 64 frames (the N-half of the B operand) and streams only ITS half of every weight
+// tile (neuron slabs 2j + r), so each SM moves half the bytes per step and each UMMA
+// does four times the work of the single-CTA kernel's (M = 256 x N = 128).  The
+// accumulator of CTA r holds its 128 neurons for all 128 frames, so the epilogue sends
+// half of the new state to the peer CTA through distributed shared memory
+// (st.shared::cluster, ~20 B/cycle, measured in profiles/probes/dsmem_store_probe.cu).
+// Barriers that collect arrivals from both CTAs live in CTA 0 (the MMA issuer).
+// =====================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+template <bool SLEEP>
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (!done) {
+            if (SLEEP) __nanosleep(64);
+            if (spin > (1u << 24)) __trap();
+        }
+    }
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(DESC_HI) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_pair(uint64_t *bar) {     // arrives on `bar` in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void sts_cluster_u16(uint32_t cluster_addr, unsigned short v) {
+    asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(cluster_addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ void split_sts_cluster(uint32_t addr, uint32_t lo_delta, float xs) {
+    const __half h = __float2half_rn(xs);
+    const __half l = __float2half_rn(xs - __half2float(h));
+    sts_cluster_u16(addr, __half_as_ushort(h));
+    sts_cluster_u16(addr + lo_delta, __half_as_ushort(l));
+}
+
+constexpr int PF = 2 * FT;             // frames per CTA pair
+
+template <bool DBG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_predict_tc2(const TcParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_d, bar_state, bar_y, bar_yready;
+    __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_key[2][PF];        // noise keys of (pair frame, step), double-buffered by step parity
+
+    const TcGeom gm = tc_geom(p.N, p.n_in);
+    const int S = gm.S, C = gm.C, J = S >> 1;
+    unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    unsigned char *st_hi = base, *st_lo = base + (size_t)C * STILE, *ring = base + (size_t)2 * C * STILE;
+    const uint32_t lo_delta = (uint32_t)C * STILE;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair0 = (blockIdx.x >> 1) * PF;               // first frame of the pair
+    const int tile0 = pair0 + (int)rank * FT;               // first frame owned by this CTA
+    const int g = p.group_ids ? p.group_ids[min(pair0, p.B - 1)] : 0;
+    const int P = p.N + p.n_in;
+    const int n_epi = 8 * J + 2;                            // arriving warps per CTA and step
+
+    if (tid == 0) {
+        for (int i = 0; i < NST; ++i) { mbar_init(&bar_full[i], rank == 0 ? 2 : 1); mbar_init(&bar_empty[i], 1); }
+        mbar_init(&bar_d, 1);
+        mbar_init(&bar_y, 1);
+        mbar_init(&bar_yready, 4);
+        mbar_init(&bar_state, 2 * n_epi);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 3) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&s_tmem)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < 2 * C * STILE / 16; i += TC_THREADS)
+        reinterpret_cast<uint4 *>(base)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (p.x0) {
+        const float xscale = ldexpf(1.0f, SX);
+        for (int i = tid; i < FT * p.N; i += TC_THREADS) {
+            const int f = i / p.N, n = i - f * p.N, b = tile0 + f;
+            if (b < p.B)
+                split_sts(smem_u32(st_hi) + (n >> 6) * STILE + sw128_off(f, n & 63), lo_delta,
+                          p.x0[(size_t)b * p.N + n] * xscale);
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                   // peer barriers, TMEM and state tiles exist before any remote op
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t r_state = mapa_u32(smem_u32(&bar_state), 0), r_yready = mapa_u32(smem_u32(&bar_yready), 0);
+
+    if (warp < 2) {
+        // ============ frame warps: thread = own frame; inputs, readout, noise keys ============
+        const int f = warp * 32 + lane, b = tile0 + f;
+        const bool live = b < p.B;
+        const uint32_t row = smem_u32(st_hi) + gm.ca * STILE + (f >> 3) * 1024 + (f & 7) * 128;
+        const int fx = f & 7;
+        const int ng = gm.UW >> 3, yg = gm.YO >> 3;
+        const float su = ldexpf(1.0f, p.su), sy = ldexpf(1.0f, p.sy), ys = p.yscale[g];
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        float cur[24], nxt[24];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) { cur[j] = 0.f; nxt[j] = 0.f; }
+        auto load_row = [&](int r) {
+#pragma unroll
+            for (int j = 0; j < 24; ++j) {
+                float v = 0.f;
+                if (j < p.n_in && live && r < p.T) {
+                    v = p.in[((size_t)b * p.T + r) * p.n_in + j] * p.in_scale[j] + p.in_shift[j];
+                    if (DBG && p.ext_out) p.ext_out[((size_t)b * p.T + r) * P + p.N + j] = v;
+                    v *= su;
+                }
+                nxt[j] = v;
+            }
+        };
+        auto write_keys = [&](int r) {    // keys of both CTAs' frames (the epilogue serves all 128)
+            s_key[r & 1][f] = esn_noise_key(p.seed, (uint32_t)(pair0 + f), (uint32_t)r);
+            s_key[r & 1][f + FT] = esn_noise_key(p.seed, (uint32_t)(pair0 + f + FT), (uint32_t)r);
+        };
+        auto write_inputs = [&]() {
+#pragma unroll
+            for (int gi = 0; gi < 3; ++gi) {
+                if (gi < ng) {
+#pragma unroll
+                    for (int blk = 0; blk < 2; ++blk) {
+                        const uint32_t a = row + (((gi + blk * ng) ^ fx) << 4);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            split_sts(a + e * 2, lo_delta, blk == 0 ? nxt[gi * 8 + e] : cur[gi * 8 + e]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 24; ++j) cur[j] = nxt[j];
+        };
+        load_row(0);
+        write_keys(0);
+        write_inputs();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(r_state);
+        for (int it = 0; it <= p.T; ++it) {
+            if (it < p.T) load_row(it + 1);
+            mbar_wait<true>(&bar_y, it & 1);
+            tc_fence_after();
+            write_keys(it + 1);
+            uint32_t yv[16];
+            tmem_ld16(lane_base + YCOL, yv);
+            tmem_ld_wait();
+            float y[16];
+#pragma unroll
+            for (int o = 0; o < 16; ++o) {
+                y[o] = __uint_as_float(yv[o]) * ys;
+                if (it == 0) y[o] = (p.y0 && live && o < p.n_out) ? p.y0[(size_t)b * p.n_out + o] : 0.f;
+                if (o >= p.n_out) y[o] = 0.f;
+            }
+            if (it >= 1 && it - 1 >= p.transient && live) {
+                float *dst = p.y_out + ((size_t)b * (p.T - p.transient) + (it - 1 - p.transient)) * p.n_out;
+#pragma unroll
+                for (int o = 0; o < 16; ++o)
+                    if (o < p.n_out) dst[o] = (y[o] - p.t_shift[o]) / p.t_scale[o];
+            }
+            if (it == p.T) break;
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+                const uint32_t a = row + (((yg + gi) ^ fx) << 4);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split_sts(a + e * 2, lo_delta, p.feedback ? y[gi * 8 + e] * sy : 0.f);
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(r_yready);
+            mbar_wait<true>(&bar_d, it & 1);
+            write_inputs();
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(r_state);
+        }
+    } else if (warp == 2) {
+        // ============ producer: this CTA's half of every tile, every step ============
+        const unsigned char *wimg = p.weights;
+        const unsigned char *yimg = p.readouts + (size_t)g * gm.readout_bytes + rank * 1024;
+        const bool lead = elect_one();
+        uint32_t item = 0;
+        auto fetch = [&](const unsigned char *src, uint32_t bytes) {
+            const int slot = item % NST;
+            mbar_wait<false>(&bar_empty[slot], ((item / NST) & 1) ^ 1);
+            if (lead) {
+                mbar_expect_tx(&bar_full[slot], bytes);
+                bulk_g2s(ring + (size_t)slot * SLOT, src, bytes, &bar_full[slot]);
+            }
+            ++item;
+        };
+        for (int it = 0; it <= p.T; ++it) {
+            for (int i = 0; i < 2 * C; ++i) fetch(yimg + (size_t)i * YTILE, 1024);      // 8 of the 16 output rows
+            if (it == p.T) break;
+            for (int j = 0; j < J; ++j)
+                for (int i = 0; i < 2 * (C - 1); ++i)
+                    fetch(wimg + ((size_t)(2 * j + rank) * C * 2 + i) * SLOT, SLOT);
+            for (int j = 0; j < J; ++j)
+                for (int h = 0; h < 2; ++h)
+                    fetch(wimg + (((size_t)(2 * j + rank) * C + (C - 1)) * 2 + h) * SLOT, SLOT);
+        }
+    } else if (warp == 3 && rank == 1) {
+        // ============ relay: tell the issuer in CTA 0 that this CTA's half has landed ============
+        const bool lead = elect_one();
+        const int items_per_step = 2 * C + 2 * J * C;
+        const uint32_t total = (uint32_t)p.T * items_per_step + 2 * C;
+        for (uint32_t item = 0; item < total; ++item) {
+            const int slot = item % NST;
+            mbar_wait<false>(&bar_full[slot], (item / NST) & 1);
+            if (lead) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_full[slot]), 0));
+        }
+    } else if (warp == 3) {
+        // ============ MMA issuer (CTA 0): one thread drives both tensor cores ============
+        const bool lead = elect_one();
+        const uint32_t id_main = umma_idesc(256, PF), id_y = umma_idesc(256, 16);
+        const uint32_t hi0 = desc_lo(smem_u32(st_hi)), ring0 = smem_u32(ring);
+        const uint32_t lod = lo_delta >> 4;
+        const bool stamp = p.timeline && blockIdx.x == 0 && lane == 0;
+        uint32_t item = 0;
+        auto chain = [&](bool readout, uint32_t d, int c, int h, int ks, bool first) {
+            const int slot = item % NST;
+            mbar_wait_cluster<false>(&bar_full[slot], (item / NST) & 1);
+            tc_fence_after();
+            const uint32_t w = desc_lo(ring0 + slot * SLOT);
+            const uint32_t x = hi0 + c * (STILE >> 4);
+            const uint32_t idesc = readout ? id_y : id_main;
+            if (lead) {
+#pragma unroll 4
+                for (int kk = 0; kk < ks; ++kk) {
+                    const uint32_t wk = w + kk * 2, xk = x + kk * 2;
+                    const uint32_t acc = (first && kk == 0) ? 0u : 1u;
+                    if (h == 0) {
+                        umma2_f16(d, readout ? xk : wk, readout ? wk : xk, idesc, acc);
+                        umma2_f16(d, readout ? xk + lod : wk, readout ? wk : xk + lod, idesc, 1u);
+                    } else {
+                        umma2_f16(d, readout ? xk : wk, readout ? wk : xk, idesc, 1u);
+                    }
+                }
+                umma2_commit_pair(&bar_empty[slot]);
+            }
+            __syncwarp();
+            ++item;
+        };
+        for (int it = 0; it <= p.T; ++it) {
+            if (stamp) p.timeline[it * 8 + 0] = clock64();
+            mbar_wait_cluster<false>(&bar_state, it & 1);
+            tc_fence_after();
+            if (stamp) p.timeline[it * 8 + 1] = clock64();
+            for (int c = 0; c < C; ++c) {
+                const int ks = (c == C - 1) ? gm.YO / 16 : 4;
+                chain(true, tmem + YCOL, c, 0, ks, c == 0);
+                chain(true, tmem + YCOL, c, 1, ks, false);
+            }
+            if (lead) umma2_commit_pair(&bar_y);
+            __syncwarp();
+            if (it == p.T) break;
+            for (int j = 0; j < J; ++j)
+                for (int c = 0; c < C - 1; ++c) {
+                    chain(false, tmem + j * PF, c, 0, 4, c == 0);
+                    chain(false, tmem + j * PF, c, 1, 4, false);
+                }
+            if (stamp) p.timeline[it * 8 + 2] = clock64();
+            mbar_wait_cluster<false>(&bar_yready, it & 1);
+            tc_fence_after();
+            for (int j = 0; j < J; ++j) {
+                chain(false, tmem + j * PF, C - 1, 0, gm.kaug, false);
+                chain(false, tmem + j * PF, C - 1, 1, gm.kaug, false);
+            }
+            if (lead) umma2_commit_pair(&bar_d);
+            __syncwarp();
+            if (stamp) p.timeline[it * 8 + 3] = clock64();
+        }
+    } else if (warp >= 4) {
+        // ============ epilogue: TMEM -> tanh -> noise -> fp16 hi/lo -> owner CTA's state tile ============
+        const int e = warp - 4, q = warp & 3, cg = e >> 2, j = cg >> 1, fh = cg & 1;
+        if (j < J) {
+            const int n = 256 * j + 128 * (int)rank + q * 32 + lane;   // neuron (TMEM lane of this CTA)
+            const bool n_ok = n < p.N;
+            const int k = n & 63;
+            const float dscale = ldexpf(1.0f, -(SX + SW)), xscale = ldexpf(1.0f, SX);
+            const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + j * PF + fh * FT;
+            const bool use_noise = p.noise_amp != 0.f;
+            const uint32_t nmul = (uint32_t)n * 0xC2B2AE35U;
+            // state tile of the CTA that owns frames fh*64 .. fh*64+63 (cluster address; may be this CTA)
+            const uint32_t tile = mapa_u32(smem_u32(st_hi), (uint32_t)fh) + (n >> 6) * STILE + (k & 7) * 2;
+            const int fbase = pair0 + fh * FT;
+            const bool full_tile = fbase + FT <= p.B;
+            uint32_t goff[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) goff[i] = i * 128 + ((((k >> 3) & 7) ^ i) << 4);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(r_state);
+            for (int it = 0; it < p.T; ++it) {
+                mbar_wait<true>(&bar_d, it & 1);
+                tc_fence_after();
+                if (p.timeline && blockIdx.x == 0 && warp == 4 && lane == 0) p.timeline[it * 8 + 4] = clock64();
+                const uint32_t *keys = s_key[it & 1] + fh * FT;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_base + half * 32, v);
+                    tmem_ld_wait();
+                    const uint32_t hbase = tile + half * 4096;
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) {
+                        const int f = half * 32 + jj;
+                        float x = tanh_f32(__uint_as_float(v[jj]) * dscale);
+                        if (use_noise) {
+                            float u;
+                            if (DBG && p.noise) {
+                                const int b = fbase + f;
+                                u = (b < p.B && n_ok) ? p.noise[((size_t)b * p.T + it) * p.N + n] : 0.5f;
+                            } else {
+                                u = (float)(esn_mix32(keys[f] + nmul) >> 8) * (1.0f / 16777216.0f);
+                            }
+                            x = fmaf(u, p.noise_amp, x - 0.5f * p.noise_amp);
+                        }
+                        if (!n_ok || (!full_tile && fbase + f >= p.B)) x = 0.f;
+                        if (DBG && p.ext_out && n_ok && fbase + f < p.B)
+                            p.ext_out[((size_t)(fbase + f) * p.T + it) * P + n] = x;
+                        split_sts_cluster(hbase + (jj >> 3) * 1024 + goff[jj & 7], lo_delta, x * xscale);
+                    }
+                }
+                asm volatile("fence.proxy.async;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(r_state);
+                if (p.timeline && blockIdx.x == 0 && warp == 4 && lane == 0) p.timeline[it * 8 + 5] = clock64();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                   // nobody leaves while the peer may still touch its SMEM / TMEM
+    if (warp == 3) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -581,12 +984,24 @@ extern "C" int esn_tc_predict(const esn_tc_predict_args *a, void *stream) {
     p.yscale = a->yscale;
     p.in = a->in; p.in_scale = a->in_scale; p.in_shift = a->in_shift; p.t_scale = a->t_scale; p.t_shift = a->t_shift;
     p.group_ids = a->group_ids; p.x0 = a->x0; p.y0 = a->y0; p.noise = a->noise_uniforms;
-    p.ext_out = a->ext_out; p.y_out = a->y_out;
+    p.ext_out = a->ext_out; p.y_out = a->y_out; p.timeline = (long long *)a->timeline;
     const TcGeom gm = tc_geom(a->N, a->n_in);
     const size_t smem = (size_t)2 * gm.C * STILE + (size_t)NST * SLOT + 1024;
     if (smem > 227 * 1024 - 1024) return ESN_E_TOOLARGE;
-    const int grid = (a->B + FT - 1) / FT;
     const bool dbg = a->noise_uniforms || a->ext_out;
+    if (gm.S % 2 == 0 && !a->single_cta) {
+        // CTA-pair kernel (cta_group::2): 128 frames per 2-CTA cluster
+        const int grid2 = 2 * ((a->B + PF - 1) / PF);
+        if (dbg) {
+            ESN_CUDA_TRY(cudaFuncSetAttribute(esn_predict_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            esn_predict_tc2<true><<<grid2, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
+        } else {
+            ESN_CUDA_TRY(cudaFuncSetAttribute(esn_predict_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            esn_predict_tc2<false><<<grid2, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
+        }
+        return esn_launch_status();
+    }
+    const int grid = (a->B + FT - 1) / FT;
     if (dbg) {
         ESN_CUDA_TRY(cudaFuncSetAttribute(esn_predict_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         esn_predict_tc<true><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);

@@ -177,6 +177,11 @@ class Reservoir:
     def tc_supported(self):
         return bool(self.lib.esn_tc_supported(self.N, self.n_in, self.n_out))
 
+    def tc_tile_frames(self):
+        """Frames that must share one readout on the tensor-core path: 128 for
+        the CTA-pair kernel (N padded to 256 or 512), else 64."""
+        return 128 if ((self.N + 127) // 128) % 2 == 0 else 64
+
     def input_scale_exponent(self, inputs):
         """su_exp for the tensor-core path: the power of two that brings the
         largest scaled input to about 2^9 (one device reduction + sync)."""
@@ -233,7 +238,7 @@ class Reservoir:
         return TcReadout(weights, image, yscale, int(su_exp), sy_exp, G)
 
     def predict_tc(self, inputs, readout, transient=0, group_ids=None, x0=None, y0=None,
-                   noise_uniforms=None, seed=0, return_ext=False):
+                   noise_uniforms=None, seed=0, return_ext=False, timeline=None, single_cta=False):
         """Free-running prediction on the tensor cores.  `readout` comes from
         tc_prepare; each 64-frame tile must use a single readout."""
         inputs = self._as(inputs, torch.float32, 3)
@@ -274,6 +279,9 @@ class Reservoir:
             a.ext_out = ptr(ext)
         y = torch.empty((B, T - int(transient), self.n_out), dtype=torch.float32, device=self.device)
         a.y_out = ptr(y)
+        a.single_cta = int(bool(single_cta))
+        if timeline is not None:           # [T+1, 8] int64 device tensor (profiling aid)
+            a.timeline = ptr(timeline)
         check(self.lib.esn_tc_predict(C.byref(a), _stream()), "esn_tc_predict")
         return (y, ext) if return_ext else y
 
@@ -294,12 +302,13 @@ class Reservoir:
                 W_out = self.tc_prepare(W_out, self.input_scale_exponent(inputs))
             if group_ids is not None:
                 tiles = group_ids.to(self.device).reshape(-1)
-                pad = (-tiles.numel()) % 64
+                tile = self.tc_tile_frames()
+                pad = (-tiles.numel()) % tile
                 if pad:
                     tiles = torch.cat([tiles, tiles[-1:].expand(pad)])
-                tiles = tiles.view(-1, 64)
+                tiles = tiles.view(-1, tile)
                 if not bool((tiles == tiles[:, :1]).all()):
-                    raise EsnB200Error("tensor-core path: each 64-frame tile must share one readout")
+                    raise EsnB200Error(f"tensor-core path: each {tile}-frame tile must share one readout")
             return self.predict_tc(inputs, W_out, transient=transient, group_ids=group_ids, x0=x0, y0=y0,
                                    noise_uniforms=noise_uniforms, seed=seed, return_ext=return_ext)
         ext, y = self._run(MODE_PREDICT, dtype_code(precision), inputs, W_out=W_out,

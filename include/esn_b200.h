@@ -107,8 +107,10 @@ int esn_recurrence_run(const esn_recurrence_args *args_host, void *stream);
  * Tensor-core recurrence (tcgen05 + TMEM), free-running predict.  Same reference
  * lines as esn_recurrence_run in PREDICT mode (libs/pyESN.py:243-255).  fp16
  * hi/lo operand split (three MMAs per product, fp32 accumulation in TMEM), 64
- * frames per CTA; the frames of one 64-frame tile share one readout (group_ids
- * uniform per tile).  N <= 512, n_in <= 24, n_out <= 16.
+ * frames per CTA; reservoirs padded to 256 or 512 neurons run on CTA pairs
+ * (cta_group::2, 128 frames per pair, state halves exchanged through DSMEM).
+ * The frames of one tile (64, or 128 for the pair kernel) share one readout
+ * (group_ids uniform per tile).  N <= 512, n_in <= 24, n_out <= 16.
  *
  * esn_tc_prepare_weights builds the UMMA-ready (pre-swizzled, fp16 hi/lo) image
  * of [W | W_in | 0 | W_feedb] once per reservoir -- it is shared by all CTAs and
@@ -140,6 +142,8 @@ typedef struct esn_tc_predict_args {
     const float *noise_uniforms;/* [B][T][N] or null (device counter stream) */
     float *ext_out;             /* [B][T][N+n_in] or null */
     float *y_out;               /* [B][T-transient][n_out] */
+    void *timeline;             /* profiling aid: [T+1][8] int64 SM-clock stamps of CTA 0, or null */
+    int32_t single_cta;         /* 1 = force the one-CTA kernel (default 0: CTA-pair kernel when N_pad is 256 or 512) */
 } esn_tc_predict_args;
 
 int esn_tc_supported(int N, int n_in, int n_out);

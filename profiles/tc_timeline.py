@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Per-step phase timing of the tensor-core recurrence kernel (CTA 0), from the
+kernel's own SM-clock stamps (esn_tc_predict_args.timeline).  Run on the GPU box:
+    python profiles/tc_timeline.py [frames]
+Columns (cycles): wait_state = MMA thread idle until the state tile is ready;
+issue_main = issuing readout + main chain (ring-bound when the data is late);
+issue_aug = waiting for y + last chunk; epilogue = D ready -> state written."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "esn-ofdm-mimo_b200"))
+from esn_b200 import Reservoir  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 64
+N, ni, no, T = 512, 16, 8, 522
+rng = np.random.RandomState(42)
+W = rng.rand(N, N) - 0.5
+W[rng.rand(N, N) < 0.1] = 0
+W *= 0.9 / np.max(np.abs(np.linalg.eigvals(W)))
+res = Reservoir(W, rng.rand(N, ni) * 2 - 1, rng.rand(N, no) * 2 - 1, input_scaling=0.005 * np.ones(ni),
+                teacher_scaling=5e-7 * np.ones(no), noise=0.001)
+x = torch.randn(B, T, ni, device="cuda")
+rd = res.tc_prepare(torch.randn(1, no, N + ni, dtype=torch.float64, device="cuda") * 1e-6,
+                    res.input_scale_exponent(x))
+tl = torch.zeros(T + 1, 8, dtype=torch.int64, device="cuda")
+for _ in range(2):
+    res.predict_tc(x, rd, transient=10, timeline=tl)
+torch.cuda.synchronize()
+t = tl.cpu().numpy()[50:500]
+wait_state = t[:, 1] - t[:, 0]
+issue_main = t[:, 2] - t[:, 1]
+issue_aug = t[:, 3] - t[:, 2]
+epi = t[:, 5] - t[:, 4]
+d_to_epi = t[:, 4] - t[:, 3]
+step = t[1:, 0] - t[:-1, 0]
+mma_starved, prod_blocked = t[1:, 6], t[1:, 7]
+for name, v in (("step", step), ("mma ring-starved", mma_starved), ("producer blocked", prod_blocked), ("wait_state", wait_state), ("issue_main", issue_main), ("issue_aug", issue_aug),
+                ("issued->D ready", d_to_epi), ("epilogue(warp4)", epi)):
+    print(f"{name:18s} mean {v.mean():9.0f}  p10 {np.percentile(v, 10):9.0f}  p90 {np.percentile(v, 90):9.0f} cycles")

@@ -38,7 +38,7 @@ def _setup(n_res, n_in, n_out, seed, noise=0.001, feedback=True, in_scale=0.01, 
     return rng, (W, W_in, W_fb), aff, eng
 
 
-def _check(eng, Ws, aff, us, W_outs, gid, T, transient, noise, uni, state_tol=1e-5, out_tol=1e-4):
+def _check(eng, Ws, aff, us, W_outs, gid, T, transient, noise, uni, state_tol=1e-5, out_tol=1e-4, frames=None):
     W, W_in, W_fb = Ws
     y, ext = eng.predict(_cuda(us), _cuda(W_outs), transient=transient,
                          group_ids=None if gid is None else _cuda(gid.astype(np.int32)),
@@ -47,7 +47,7 @@ def _check(eng, Ws, aff, us, W_outs, gid, T, transient, noise, uni, state_tol=1e
     y, ext = y.double().cpu().numpy(), ext.double().cpu().numpy()
     N = W.shape[0]
     ws = wy = 0.0
-    for b in range(us.shape[0]):
+    for b in (range(us.shape[0]) if frames is None else frames):
         g = 0 if gid is None else gid[b]
         ref, st = orc.predict(W, W_in, W_fb, W_outs[g], us[b], transient, noise,
                               uni[b] if uni is not None else np.zeros((T, N)), return_states=True, **aff)
@@ -75,7 +75,7 @@ def test_tc_cfg3_shape_grouped_with_noise():
     host-supplied state noise."""
     c = cases.ESN_CASES["cfg3_4x8_n512"]
     rng, Ws, aff, eng = _setup(512, 16, 8, seed=42, noise=0.001, in_scale=0.005)
-    B, T = 64 + 9, c["T"]
+    B, T = 128 + 9, c["T"]                                # one full CTA-pair tile + a ragged one
     us = rng.randn(B, T, 16)
     # realistic readouts: train with the oracle on a pilot so W_out carries the ill-conditioning
     W_outs = []
@@ -84,9 +84,10 @@ def test_tc_cfg3_shape_grouped_with_noise():
         r = orc.fit(Ws[0], Ws[1], Ws[2], u, y, 10, 0.001, rng.rand(T - 1, 512), **aff)
         W_outs.append(r["W_out"])
     W_outs = np.stack(W_outs)
-    gid = np.array([0] * 64 + [1] * 9)
+    gid = np.array([0] * 128 + [1] * 9)
     uni = rng.rand(B, T, 512)
-    ws, wy = _check(eng, Ws, aff, us[:, :, :], W_outs, gid, T, 10, 0.001, uni)
+    ws, wy = _check(eng, Ws, aff, us, W_outs, gid, T, 10, 0.001, uni,
+                    frames=[0, 31, 63, 64, 100, 127, 128, 136])
     print("tc cfg3 worst state err %.2e, output err %.2e" % (ws, wy))
 
 
