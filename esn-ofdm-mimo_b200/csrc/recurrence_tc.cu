@@ -588,6 +588,11 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Signal-only remote arrive (no data published by this thread): relaxed, so no
+// MEMBAR.ALL.GPU is emitted (release.cluster costs one per arrive).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 template <bool SLEEP>
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
@@ -782,16 +787,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_p
         const unsigned char *yimg = p.readouts + (size_t)g * gm.readout_bytes + rank * 1024;
         const bool lead = elect_one();
         uint32_t item = 0;
+        long long *trace = (p.timeline && blockIdx.x == 0) ? p.timeline + (size_t)(p.T + 1) * 8 : nullptr;
+        int tr_i = -1;
         auto fetch = [&](const unsigned char *src, uint32_t bytes) {
             const int slot = item % NST;
             mbar_wait<false>(&bar_empty[slot], ((item / NST) & 1) ^ 1);
             if (lead) {
+                if (trace && tr_i >= 0 && tr_i < 64) trace[tr_i * 4 + 0] = clock64();   // slot free seen
                 mbar_expect_tx(&bar_full[slot], bytes);
                 bulk_g2s(ring + (size_t)slot * SLOT, src, bytes, &bar_full[slot]);
+                if (trace && tr_i >= 0 && tr_i < 64) trace[tr_i * 4 + 1] = clock64();   // copy issued
             }
+            if (tr_i >= 0) ++tr_i;
             ++item;
         };
         for (int it = 0; it <= p.T; ++it) {
+            tr_i = (it == 200) ? 0 : -1;
             for (int i = 0; i < 2 * C; ++i) fetch(yimg + (size_t)i * YTILE, 1024);      // 8 of the 16 output rows
             if (it == p.T) break;
             for (int j = 0; j < J; ++j)
@@ -809,7 +820,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_p
         for (uint32_t item = 0; item < total; ++item) {
             const int slot = item % NST;
             mbar_wait<false>(&bar_full[slot], (item / NST) & 1);
-            if (lead) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_full[slot]), 0));
+            if (lead) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&bar_full[slot]), 0));
         }
     } else if (warp == 3) {
         // ============ MMA issuer (CTA 0): one thread drives both tensor cores ============
@@ -819,9 +830,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_p
         const uint32_t lod = lo_delta >> 4;
         const bool stamp = p.timeline && blockIdx.x == 0 && lane == 0;
         uint32_t item = 0;
+        long long *trace = (p.timeline && blockIdx.x == 0) ? p.timeline + (size_t)(p.T + 1) * 8 : nullptr;
+        int tr_i = -1;
         auto chain = [&](bool readout, uint32_t d, int c, int h, int ks, bool first) {
             const int slot = item % NST;
-            mbar_wait_cluster<false>(&bar_full[slot], (item / NST) & 1);
+            mbar_wait<false>(&bar_full[slot], (item / NST) & 1);   // bulk-copy data only: no cluster acquire needed
+            if (trace && lane == 0 && tr_i >= 0 && tr_i < 64) trace[tr_i * 4 + 2] = clock64();   // data of both CTAs seen
             tc_fence_after();
             const uint32_t w = desc_lo(ring0 + slot * SLOT);
             const uint32_t x = hi0 + c * (STILE >> 4);
@@ -841,9 +855,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_p
                 umma2_commit_pair(&bar_empty[slot]);
             }
             __syncwarp();
+            if (trace && lane == 0 && tr_i >= 0 && tr_i < 64) trace[tr_i * 4 + 3] = clock64();   // MMAs + commit issued
+            if (tr_i >= 0) ++tr_i;
             ++item;
         };
         for (int it = 0; it <= p.T; ++it) {
+            tr_i = (it == 200) ? 0 : -1;
             if (stamp) p.timeline[it * 8 + 0] = clock64();
             mbar_wait_cluster<false>(&bar_state, it & 1);
             tc_fence_after();

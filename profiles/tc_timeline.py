@@ -26,11 +26,12 @@ res = Reservoir(W, rng.rand(N, ni) * 2 - 1, rng.rand(N, no) * 2 - 1, input_scali
 x = torch.randn(B, T, ni, device="cuda")
 rd = res.tc_prepare(torch.randn(1, no, N + ni, dtype=torch.float64, device="cuda") * 1e-6,
                     res.input_scale_exponent(x))
-tl = torch.zeros(T + 1, 8, dtype=torch.int64, device="cuda")
+tl = torch.zeros(T + 1 + 32, 8, dtype=torch.int64, device="cuda")   # + per-item trace of step 200
 for _ in range(2):
     res.predict_tc(x, rd, transient=10, timeline=tl)
 torch.cuda.synchronize()
-t = tl.cpu().numpy()[50:500]
+full = tl.cpu().numpy()
+t = full[50:500]
 wait_state = t[:, 1] - t[:, 0]
 issue_main = t[:, 2] - t[:, 1]
 issue_aug = t[:, 3] - t[:, 2]
@@ -41,3 +42,12 @@ mma_starved, prod_blocked = t[1:, 6], t[1:, 7]
 for name, v in (("step", step), ("mma ring-starved", mma_starved), ("producer blocked", prod_blocked), ("wait_state", wait_state), ("issue_main", issue_main), ("issue_aug", issue_aug),
                 ("issued->D ready", d_to_epi), ("epilogue(warp4)", epi)):
     print(f"{name:18s} mean {v.mean():9.0f}  p10 {np.percentile(v, 10):9.0f}  p90 {np.percentile(v, 90):9.0f} cycles")
+
+tr = full[T + 1:].reshape(-1, 4)[:56]
+if tr[:, 2].any():
+    t0 = tr[0, 0] if tr[0, 0] else tr[0, 2]
+    print("per-item trace of step 200 (cycles from the first stamp): slot_free_seen  copy_issued | data_seen  mmas_issued")
+    for i, r in enumerate(tr):
+        if r[2] == 0:
+            break
+        print(f"  item {i:2d}: {r[0]-t0:8d} {r[1]-t0:8d} | {r[2]-t0:8d} {r[3]-t0:8d}")
