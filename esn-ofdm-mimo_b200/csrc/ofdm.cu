@@ -428,5 +428,5 @@ extern "C" int esn_device_info(char *name, int n, int *major, int *minor) {
 
 // Host-callable copy of the device noise stream (tests pin the numpy restatement to it).
 extern "C" float esn_noise_uniform_host(unsigned long long seed, unsigned frame, unsigned row, unsigned neuron) {
-    return esn_noise_uniform(esn_noise_key(seed, frame, row), neuron);
+    return esn_noise_uniform(esn_noise_key(seed, frame, row), neuron, frame);
 }

@@ -250,6 +250,24 @@ __device__ __forceinline__ float tanh_f32(float z) {
     return copysignf(1.0f - __fdividef(2.0f, e + 1.0f), z);
 }
 
+// Branch-free tanh for |z| <= 3: [7/6] Pade approximant, error < 2.4e-7 relative up to
+// |z| = 2 and < 1e-6 up to 3 (checked against float64 tanh).  Larger arguments are rare
+// in an echo-state reservoir and are patched afterwards with tanh_large().
+__device__ __forceinline__ float tanh_pade(float z) {
+    const float z2 = z * z;
+    float num = z2 + 378.0f;
+    num = fmaf(num, z2, 17325.0f);
+    num = fmaf(num, z2, 135135.0f);
+    float den = fmaf(28.0f, z2, 3150.0f);
+    den = fmaf(den, z2, 62370.0f);
+    den = fmaf(den, z2, 135135.0f);
+    return __fdividef(num * z, den);
+}
+__device__ __forceinline__ float tanh_large(float z) {      // |z| > 3
+    const float e = __expf(2.0f * fabsf(z));
+    return copysignf(1.0f - __fdividef(2.0f, e + 1.0f), z);
+}
+
 // ------------------------------------------------------------- predict ------
 struct TcParams {
     int B, T, N, n_in, n_out, transient, feedback;
@@ -535,7 +553,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p
                                 const int b = tile0 + f;
                                 u = (b < p.B && n_ok) ? p.noise[((size_t)b * p.T + it) * p.N + n] : 0.5f;
                             } else {
-                                u = (float)(esn_mix32(keys[f] + nmul) >> 8) * (1.0f / 16777216.0f);
+                                const uint32_t hb = esn_mix32(keys[f] + nmul);
+                                u = (float)((f & 1) ? (hb >> 16) : (hb & 0xFFFFu)) * (1.0f / 65536.0f);
                             }
                             x = fmaf(u, p.noise_amp, x - 0.5f * p.noise_amp);
                         }
@@ -637,19 +656,102 @@ __device__ __forceinline__ void split_sts_cluster(uint32_t addr, uint32_t lo_del
     sts_cluster_u16(addr + lo_delta, __half_as_ushort(l));
 }
 
+// ---- pair-kernel state tile: MN-major (frames contiguous), SWIZZLE_128B -----------------
+// chunk c = 64 k-rows x 128 B (this CTA's 64 frames); 8-row atoms of 1024 B; inside an atom
+// the 16-byte granule (8 frames) g of row k sits at position g ^ (k & 7).  A thread that owns
+// neuron k therefore writes its 64 frames as eight 16-byte stores into one 128-byte row.
+__host__ __device__ inline int mn128_off(int k, int f) {          // k < 64 within the chunk, f < 64
+    return (k >> 3) * 1024 + (k & 7) * 128 + ((((f >> 3) & 7) ^ (k & 7)) << 4) + (f & 7) * 2;
+}
+__device__ __forceinline__ void sts_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {   // -> {lo half, hi half}
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t umma_idesc_major(int M, int N, int a_mn, int b_mn) {
+    return umma_idesc(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+}
+// MN-major SWIZZLE_128B descriptor, low word: start address, LBO = 0 (a second 64-wide MN block
+// aliases the first: only used by the readout chain, whose rows 64..127 are don't-care)
+__device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr) { return (saddr >> 4) & 0x3FFF; }
+
 constexpr int PF = 2 * FT;             // frames per CTA pair
+constexpr int SLOT2 = SLOT + 2048;     // pair-kernel ring slot: weight tile + up to two 1 KB readout half-tiles
+
+// One half (32 frames) of an epilogue thread's work: v[] = accumulators of its neuron for 32
+// consecutive frames -> tanh -> noise -> x 2^SX -> fp16 hi/lo, written as four 16-byte stores per
+// half (eight frames each) into the owner CTA's MN-major state tile.  Pade tanh for every element;
+// returns true if some |z| > 3 (the caller then patches with FIX = true, exact formula).
+template <bool DBG, bool FIX>
+__device__ __forceinline__ bool tc2_epilogue_half(const TcParams &p, const uint32_t (&v)[32], int it, int n, bool n_ok,
+                                                  int fbase, int half, bool full_tile, const uint32_t *keys,
+                                                  uint32_t nmul, uint32_t rowaddr, int kx, uint32_t lo_delta, int P) {
+    const float dscale = ldexpf(1.0f, -(SX + SW)), xscale = ldexpf(1.0f, SX);
+    const bool use_noise = p.noise_amp != 0.f;
+    const float amp16 = p.noise_amp * (1.0f / 65536.0f), ampoff = 0.5f * p.noise_amp;
+    bool big = false;
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {                      // granule of 8 frames
+        uint32_t hi2[4], lo2[4];
+        bool any_large = false;
+#pragma unroll
+        for (int pr = 0; pr < 4; ++pr) {                  // pair of frames
+            const int jj = g8 * 8 + pr * 2, f0 = half * 32 + jj;
+            uint32_t hb = 0;
+            if (use_noise && !(DBG && p.noise)) hb = esn_mix32(keys[f0 >> 1] + nmul);
+            float xs[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int f = f0 + e;
+                const float z = __uint_as_float(v[jj + e]) * dscale;
+                const bool large = fabsf(z) > 3.0f;
+                any_large |= large;
+                float x = (FIX && large) ? tanh_large(z) : tanh_pade(z);
+                if (use_noise) {
+                    if (DBG && p.noise) {
+                        const int b = fbase + f;
+                        const float u = (b < p.B && n_ok) ? p.noise[((size_t)b * p.T + it) * p.N + n] : 0.5f;
+                        x = fmaf(u, p.noise_amp, x - ampoff);
+                    } else {
+                        x = fmaf((float)(e ? (hb >> 16) : (hb & 0xFFFFu)), amp16, x - ampoff);
+                    }
+                }
+                if (!n_ok || (!full_tile && fbase + f >= p.B)) x = 0.f;
+                if (DBG && p.ext_out && n_ok && fbase + f < p.B)
+                    p.ext_out[((size_t)(fbase + f) * p.T + it) * P + n] = x;
+                xs[e] = x * xscale;
+            }
+            const uint32_t h = pack_h2(xs[0], xs[1]);
+            const __half2 hh = *reinterpret_cast<const __half2 *>(&h);
+            const float2 back = __half22float2(hh);
+            hi2[pr] = h;
+            lo2[pr] = pack_h2(xs[0] - back.x, xs[1] - back.y);
+        }
+        big |= any_large;
+        if (!FIX || any_large) {
+            const uint32_t a = rowaddr + ((uint32_t)((half * 4 + g8) ^ kx) << 4);
+            sts_cluster_v4(a, hi2[0], hi2[1], hi2[2], hi2[3]);
+            sts_cluster_v4(a + lo_delta, lo2[0], lo2[1], lo2[2], lo2[3]);
+        }
+    }
+    return big;
+}
 
 template <bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_predict_tc2(const TcParams p) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_d, bar_state, bar_y, bar_yready;
     __shared__ uint32_t s_tmem;
-    __shared__ uint32_t s_key[2][PF];        // noise keys of (pair frame, step), double-buffered by step parity
+    __shared__ uint32_t s_key[2][FT];        // noise keys of (frame pair of the 128-frame tile, step)
 
     const TcGeom gm = tc_geom(p.N, p.n_in);
     const int S = gm.S, C = gm.C, J = S >> 1;
     unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-    unsigned char *st_hi = base, *st_lo = base + (size_t)C * STILE, *ring = base + (size_t)2 * C * STILE;
+    unsigned char *st_hi = base, *ring = base + (size_t)2 * C * STILE;
     const uint32_t lo_delta = (uint32_t)C * STILE;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -681,7 +783,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_p
         for (int i = tid; i < FT * p.N; i += TC_THREADS) {
             const int f = i / p.N, n = i - f * p.N, b = tile0 + f;
             if (b < p.B)
-                split_sts(smem_u32(st_hi) + (n >> 6) * STILE + sw128_off(f, n & 63), lo_delta,
+                split_sts(smem_u32(st_hi) + (n >> 6) * STILE + mn128_off(n & 63, f), lo_delta,
                           p.x0[(size_t)b * p.N + n] * xscale);
         }
     }
@@ -693,13 +795,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_p
     const uint32_t tmem = s_tmem;
     const uint32_t r_state = mapa_u32(smem_u32(&bar_state), 0), r_yready = mapa_u32(smem_u32(&bar_yready), 0);
 
+    // Ring schedule of one step, identical in producer, relay and issuer.  Phase A: state chunks
+    // of accumulator group 0 -- each item also carries the readout half-tile(s) of its chunk (and,
+    // with chunk 0, of the aug chunk); phase B: state chunks of the other groups; phase C: aug chunk.
+    // The last step (it == T) only needs the readout, i.e. phase A without the weight tiles.
+
     if (warp < 2) {
         // ============ frame warps: thread = own frame; inputs, readout, noise keys ============
         const int f = warp * 32 + lane, b = tile0 + f;
         const bool live = b < p.B;
-        const uint32_t row = smem_u32(st_hi) + gm.ca * STILE + (f >> 3) * 1024 + (f & 7) * 128;
-        const int fx = f & 7;
-        const int ng = gm.UW >> 3, yg = gm.YO >> 3;
+        // aug chunk, MN-major: element (k, f) at (k>>3)*1024 + (k&7)*128 + (((f>>3)^(k&7))<<4) + (f&7)*2
+        const uint32_t augc = smem_u32(st_hi) + gm.ca * STILE + (f & 7) * 2;
+        const int fg = f >> 3;
+        auto aug_addr = [&](int k) { return augc + (k >> 3) * 1024 + (k & 7) * 128 + ((fg ^ (k & 7)) << 4); };
         const float su = ldexpf(1.0f, p.su), sy = ldexpf(1.0f, p.sy), ys = p.yscale[g];
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
         float cur[24], nxt[24];
@@ -717,21 +825,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_p
                 nxt[j] = v;
             }
         };
-        auto write_keys = [&](int r) {    // keys of both CTAs' frames (the epilogue serves all 128)
-            s_key[r & 1][f] = esn_noise_key(p.seed, (uint32_t)(pair0 + f), (uint32_t)r);
-            s_key[r & 1][f + FT] = esn_noise_key(p.seed, (uint32_t)(pair0 + f + FT), (uint32_t)r);
+        auto write_keys = [&](int r) {    // one key per frame pair of the whole 128-frame tile
+            s_key[r & 1][f] = esn_noise_key(p.seed, (uint32_t)(pair0 + 2 * f), (uint32_t)r);
         };
-        auto write_inputs = [&]() {
+        auto write_inputs = [&]() {       // columns [0,UW) <- u_it, [UW,2UW) <- u_{it-1}
 #pragma unroll
-            for (int gi = 0; gi < 3; ++gi) {
-                if (gi < ng) {
-#pragma unroll
-                    for (int blk = 0; blk < 2; ++blk) {
-                        const uint32_t a = row + (((gi + blk * ng) ^ fx) << 4);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            split_sts(a + e * 2, lo_delta, blk == 0 ? nxt[gi * 8 + e] : cur[gi * 8 + e]);
-                    }
+            for (int j = 0; j < 24; ++j) {
+                if (j < gm.UW) {
+                    split_sts(aug_addr(j), lo_delta, nxt[j]);
+                    split_sts(aug_addr(gm.UW + j), lo_delta, cur[j]);
                 }
             }
 #pragma unroll
@@ -747,7 +849,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_p
             if (it < p.T) load_row(it + 1);
             mbar_wait<true>(&bar_y, it & 1);
             tc_fence_after();
-            write_keys(it + 1);
+            write_keys(it + 1);           // every epilogue warp has finished step it-1 by now
             uint32_t yv[16];
             tmem_ld16(lane_base + YCOL, yv);
             tmem_ld_wait();
@@ -766,11 +868,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_p
             }
             if (it == p.T) break;
 #pragma unroll
-            for (int gi = 0; gi < 2; ++gi) {
-                const uint32_t a = row + (((yg + gi) ^ fx) << 4);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) split_sts(a + e * 2, lo_delta, p.feedback ? y[gi * 8 + e] * sy : 0.f);
-            }
+            for (int o = 0; o < 16; ++o) split_sts(aug_addr(gm.YO + o), lo_delta, p.feedback ? y[o] * sy : 0.f);
             fence_async_smem();
             tc_fence_before();
             __syncwarp();
@@ -784,39 +882,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_p
     } else if (warp == 2) {
         // ============ producer: this CTA's half of every tile, every step ============
         const unsigned char *wimg = p.weights;
-        const unsigned char *yimg = p.readouts + (size_t)g * gm.readout_bytes + rank * 1024;
+        const unsigned char *yimg = p.readouts + (size_t)g * gm.readout_bytes + rank * 1024;   // 8 of 16 output rows
         const bool lead = elect_one();
         uint32_t item = 0;
-        long long *trace = (p.timeline && blockIdx.x == 0) ? p.timeline + (size_t)(p.T + 1) * 8 : nullptr;
-        int tr_i = -1;
-        auto fetch = [&](const unsigned char *src, uint32_t bytes) {
+        // weight tile (slab s, chunk c, half h) and/or readout half-tiles into the next slot
+        auto fetch = [&](int s, int c, int h, bool w, bool y) {
             const int slot = item % NST;
             mbar_wait<false>(&bar_empty[slot], ((item / NST) & 1) ^ 1);
             if (lead) {
-                if (trace && tr_i >= 0 && tr_i < 64) trace[tr_i * 4 + 0] = clock64();   // slot free seen
-                mbar_expect_tx(&bar_full[slot], bytes);
-                bulk_g2s(ring + (size_t)slot * SLOT, src, bytes, &bar_full[slot]);
-                if (trace && tr_i >= 0 && tr_i < 64) trace[tr_i * 4 + 1] = clock64();   // copy issued
+                unsigned char *dst = ring + (size_t)slot * SLOT2;
+                const bool yaug = y && c == 0;
+                mbar_expect_tx(&bar_full[slot], (w ? SLOT : 0) + (y ? 1024 : 0) + (yaug ? 1024 : 0));
+                if (w) bulk_g2s(dst, wimg + ((size_t)(s * C + c) * 2 + h) * SLOT, SLOT, &bar_full[slot]);
+                if (y) bulk_g2s(dst + SLOT, yimg + (size_t)(c * 2 + h) * YTILE, 1024, &bar_full[slot]);
+                if (yaug) bulk_g2s(dst + SLOT + 1024, yimg + (size_t)((C - 1) * 2 + h) * YTILE, 1024, &bar_full[slot]);
             }
-            if (tr_i >= 0) ++tr_i;
             ++item;
         };
         for (int it = 0; it <= p.T; ++it) {
-            tr_i = (it == 200) ? 0 : -1;
-            for (int i = 0; i < 2 * C; ++i) fetch(yimg + (size_t)i * YTILE, 1024);      // 8 of the 16 output rows
-            if (it == p.T) break;
+            const bool last = it == p.T;
+            for (int c = 0; c < C - 1; ++c)
+                for (int h = 0; h < 2; ++h) fetch((int)rank, c, h, !last, true);
+            if (last) break;
+            for (int j = 1; j < J; ++j)
+                for (int c = 0; c < C - 1; ++c)
+                    for (int h = 0; h < 2; ++h) fetch(2 * j + (int)rank, c, h, true, false);
             for (int j = 0; j < J; ++j)
-                for (int i = 0; i < 2 * (C - 1); ++i)
-                    fetch(wimg + ((size_t)(2 * j + rank) * C * 2 + i) * SLOT, SLOT);
-            for (int j = 0; j < J; ++j)
-                for (int h = 0; h < 2; ++h)
-                    fetch(wimg + (((size_t)(2 * j + rank) * C + (C - 1)) * 2 + h) * SLOT, SLOT);
+                for (int h = 0; h < 2; ++h) fetch(2 * j + (int)rank, C - 1, h, true, false);
         }
     } else if (warp == 3 && rank == 1) {
         // ============ relay: tell the issuer in CTA 0 that this CTA's half has landed ============
         const bool lead = elect_one();
-        const int items_per_step = 2 * C + 2 * J * C;
-        const uint32_t total = (uint32_t)p.T * items_per_step + 2 * C;
+        const uint32_t total = (uint32_t)p.T * (2 * J * C) + 2 * (C - 1);
         for (uint32_t item = 0; item < total; ++item) {
             const int slot = item % NST;
             mbar_wait<false>(&bar_full[slot], (item / NST) & 1);
@@ -825,66 +922,71 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_p
     } else if (warp == 3) {
         // ============ MMA issuer (CTA 0): one thread drives both tensor cores ============
         const bool lead = elect_one();
-        const uint32_t id_main = umma_idesc(256, PF), id_y = umma_idesc(256, 16);
-        const uint32_t hi0 = desc_lo(smem_u32(st_hi)), ring0 = smem_u32(ring);
+        // state tile is MN-major: B operand of the main chain, A operand of the readout chain
+        const uint32_t id_main = umma_idesc_major(256, PF, 0, 1), id_y = umma_idesc_major(256, 16, 1, 0);
+        const uint32_t hi0 = desc_lo_mn(smem_u32(st_hi)), ring0 = smem_u32(ring);
         const uint32_t lod = lo_delta >> 4;
         const bool stamp = p.timeline && blockIdx.x == 0 && lane == 0;
-        uint32_t item = 0;
-        long long *trace = (p.timeline && blockIdx.x == 0) ? p.timeline + (size_t)(p.T + 1) * 8 : nullptr;
+        long long *trace = (p.timeline && blockIdx.x == 0 && lane == 0) ? p.timeline + (size_t)(p.T + 1) * 8 : nullptr;
         int tr_i = -1;
-        auto chain = [&](bool readout, uint32_t d, int c, int h, int ks, bool first) {
+        uint32_t item = 0;
+        // three MMAs per k-step for a hi tile (x_hi, x_lo) and one for a lo tile (x_hi)
+        auto mmas = [&](bool readout, uint32_t d, uint32_t w, uint32_t x, int h, int ks, bool first) {
+            const uint32_t idesc = readout ? id_y : id_main;
+#pragma unroll 4
+            for (int kk = 0; kk < ks; ++kk) {
+                // weights K-major: 16 k = 32 B; state MN-major: 16 k = two 1024-byte atoms
+                const uint32_t wk = w + kk * 2, xk = x + kk * 128;
+                const uint32_t acc = (first && kk == 0) ? 0u : 1u;
+                if (h == 0) {
+                    umma2_f16(d, readout ? xk : wk, readout ? wk : xk, idesc, acc);
+                    umma2_f16(d, readout ? xk + lod : wk, readout ? wk : xk + lod, idesc, 1u);
+                } else {
+                    umma2_f16(d, readout ? xk : wk, readout ? wk : xk, idesc, 1u);
+                }
+            }
+        };
+        auto consume = [&](int j, int c, int h, bool w, bool y) {
             const int slot = item % NST;
             mbar_wait<false>(&bar_full[slot], (item / NST) & 1);   // bulk-copy data only: no cluster acquire needed
-            if (trace && lane == 0 && tr_i >= 0 && tr_i < 64) trace[tr_i * 4 + 2] = clock64();   // data of both CTAs seen
+            if (trace && tr_i >= 0 && tr_i < 64) trace[tr_i * 4 + 2] = clock64();
             tc_fence_after();
-            const uint32_t w = desc_lo(ring0 + slot * SLOT);
-            const uint32_t x = hi0 + c * (STILE >> 4);
-            const uint32_t idesc = readout ? id_y : id_main;
             if (lead) {
-#pragma unroll 4
-                for (int kk = 0; kk < ks; ++kk) {
-                    const uint32_t wk = w + kk * 2, xk = x + kk * 2;
-                    const uint32_t acc = (first && kk == 0) ? 0u : 1u;
-                    if (h == 0) {
-                        umma2_f16(d, readout ? xk : wk, readout ? wk : xk, idesc, acc);
-                        umma2_f16(d, readout ? xk + lod : wk, readout ? wk : xk + lod, idesc, 1u);
-                    } else {
-                        umma2_f16(d, readout ? xk : wk, readout ? wk : xk, idesc, 1u);
-                    }
+                const uint32_t sl = desc_lo(ring0 + slot * SLOT2);
+                const uint32_t x = hi0 + c * (STILE >> 4);
+                if (w) mmas(false, tmem + j * PF, sl, x, h, c == C - 1 ? gm.kaug : 4, c == 0 && h == 0);
+                if (y) {
+                    mmas(true, tmem + YCOL, sl + (SLOT >> 4), x, h, 4, c == 0 && h == 0);
+                    if (c == 0)       // the aug chunk's share of the readout (u_{t-1} columns)
+                        mmas(true, tmem + YCOL, sl + ((SLOT + 1024) >> 4), hi0 + (C - 1) * (STILE >> 4), h, gm.YO / 16, false);
                 }
                 umma2_commit_pair(&bar_empty[slot]);
             }
             __syncwarp();
-            if (trace && lane == 0 && tr_i >= 0 && tr_i < 64) trace[tr_i * 4 + 3] = clock64();   // MMAs + commit issued
+            if (trace && tr_i >= 0 && tr_i < 64) trace[tr_i * 4 + 3] = clock64();
             if (tr_i >= 0) ++tr_i;
             ++item;
         };
         for (int it = 0; it <= p.T; ++it) {
+            const bool last = it == p.T;
             tr_i = (it == 200) ? 0 : -1;
             if (stamp) p.timeline[it * 8 + 0] = clock64();
             mbar_wait_cluster<false>(&bar_state, it & 1);
             tc_fence_after();
             if (stamp) p.timeline[it * 8 + 1] = clock64();
-            for (int c = 0; c < C; ++c) {
-                const int ks = (c == C - 1) ? gm.YO / 16 : 4;
-                chain(true, tmem + YCOL, c, 0, ks, c == 0);
-                chain(true, tmem + YCOL, c, 1, ks, false);
-            }
+            for (int c = 0; c < C - 1; ++c)
+                for (int h = 0; h < 2; ++h) consume(0, c, h, !last, true);
             if (lead) umma2_commit_pair(&bar_y);
             __syncwarp();
-            if (it == p.T) break;
-            for (int j = 0; j < J; ++j)
-                for (int c = 0; c < C - 1; ++c) {
-                    chain(false, tmem + j * PF, c, 0, 4, c == 0);
-                    chain(false, tmem + j * PF, c, 1, 4, false);
-                }
+            if (last) break;
+            for (int j = 1; j < J; ++j)
+                for (int c = 0; c < C - 1; ++c)
+                    for (int h = 0; h < 2; ++h) consume(j, c, h, true, false);
             if (stamp) p.timeline[it * 8 + 2] = clock64();
             mbar_wait_cluster<false>(&bar_yready, it & 1);
             tc_fence_after();
-            for (int j = 0; j < J; ++j) {
-                chain(false, tmem + j * PF, C - 1, 0, gm.kaug, false);
-                chain(false, tmem + j * PF, C - 1, 1, gm.kaug, false);
-            }
+            for (int j = 0; j < J; ++j)
+                for (int h = 0; h < 2; ++h) consume(j, C - 1, h, true, false);
             if (lead) umma2_commit_pair(&bar_d);
             __syncwarp();
             if (stamp) p.timeline[it * 8 + 3] = clock64();
@@ -895,51 +997,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_p
         if (j < J) {
             const int n = 256 * j + 128 * (int)rank + q * 32 + lane;   // neuron (TMEM lane of this CTA)
             const bool n_ok = n < p.N;
-            const int k = n & 63;
-            const float dscale = ldexpf(1.0f, -(SX + SW)), xscale = ldexpf(1.0f, SX);
+            const int k = n & 63, kx = k & 7;
             const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + j * PF + fh * FT;
-            const bool use_noise = p.noise_amp != 0.f;
             const uint32_t nmul = (uint32_t)n * 0xC2B2AE35U;
-            // state tile of the CTA that owns frames fh*64 .. fh*64+63 (cluster address; may be this CTA)
-            const uint32_t tile = mapa_u32(smem_u32(st_hi), (uint32_t)fh) + (n >> 6) * STILE + (k & 7) * 2;
+            // row k of chunk n>>6 in the state tile of the CTA that owns frames fh*64 .. fh*64+63
+            // (cluster address; may be this CTA): 128 bytes = this neuron's 64 frames
+            const uint32_t rowaddr = mapa_u32(smem_u32(st_hi), (uint32_t)fh) + (n >> 6) * STILE + (k >> 3) * 1024 + kx * 128;
             const int fbase = pair0 + fh * FT;
             const bool full_tile = fbase + FT <= p.B;
-            uint32_t goff[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) goff[i] = i * 128 + ((((k >> 3) & 7) ^ i) << 4);
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(r_state);
             for (int it = 0; it < p.T; ++it) {
                 mbar_wait<true>(&bar_d, it & 1);
                 tc_fence_after();
                 if (p.timeline && blockIdx.x == 0 && warp == 4 && lane == 0) p.timeline[it * 8 + 4] = clock64();
-                const uint32_t *keys = s_key[it & 1] + fh * FT;
+                const uint32_t *keys = s_key[it & 1] + fh * (FT / 2);
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     uint32_t v[32];
                     tmem_ld32(lane_base + half * 32, v);
                     tmem_ld_wait();
-                    const uint32_t hbase = tile + half * 4096;
-#pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) {
-                        const int f = half * 32 + jj;
-                        float x = tanh_f32(__uint_as_float(v[jj]) * dscale);
-                        if (use_noise) {
-                            float u;
-                            if (DBG && p.noise) {
-                                const int b = fbase + f;
-                                u = (b < p.B && n_ok) ? p.noise[((size_t)b * p.T + it) * p.N + n] : 0.5f;
-                            } else {
-                                u = (float)(esn_mix32(keys[f] + nmul) >> 8) * (1.0f / 16777216.0f);
-                            }
-                            x = fmaf(u, p.noise_amp, x - 0.5f * p.noise_amp);
-                        }
-                        if (!n_ok || (!full_tile && fbase + f >= p.B)) x = 0.f;
-                        if (DBG && p.ext_out && n_ok && fbase + f < p.B)
-                            p.ext_out[((size_t)(fbase + f) * p.T + it) * P + n] = x;
-                        split_sts_cluster(hbase + (jj >> 3) * 1024 + goff[jj & 7], lo_delta, x * xscale);
-                    }
+                    const bool big = tc2_epilogue_half<DBG, false>(p, v, it, n, n_ok, fbase, half, full_tile, keys, nmul,
+                                                                   rowaddr, kx, lo_delta, P);
+                    if (__any_sync(0xffffffffu, big))
+                        tc2_epilogue_half<DBG, true>(p, v, it, n, n_ok, fbase, half, full_tile, keys, nmul, rowaddr, kx,
+                                                     lo_delta, P);
                 }
+                if (p.timeline && blockIdx.x == 0 && warp == 4 && lane == 0) p.timeline[it * 8 + 6] = clock64();
                 asm volatile("fence.proxy.async;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
@@ -1009,6 +1093,7 @@ extern "C" int esn_tc_predict(const esn_tc_predict_args *a, void *stream) {
     if (gm.S % 2 == 0 && !a->single_cta) {
         // CTA-pair kernel (cta_group::2): 128 frames per 2-CTA cluster
         const int grid2 = 2 * ((a->B + PF - 1) / PF);
+        const size_t smem = (size_t)2 * gm.C * STILE + (size_t)NST * SLOT2 + 1024;
         if (dbg) {
             ESN_CUDA_TRY(cudaFuncSetAttribute(esn_predict_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             esn_predict_tc2<true><<<grid2, TC_THREADS, smem, (cudaStream_t)stream>>>(p);

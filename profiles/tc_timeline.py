@@ -38,8 +38,8 @@ issue_aug = t[:, 3] - t[:, 2]
 epi = t[:, 5] - t[:, 4]
 d_to_epi = t[:, 4] - t[:, 3]
 step = t[1:, 0] - t[:-1, 0]
-mma_starved, prod_blocked = t[1:, 6], t[1:, 7]
-for name, v in (("step", step), ("mma ring-starved", mma_starved), ("producer blocked", prod_blocked), ("wait_state", wait_state), ("issue_main", issue_main), ("issue_aug", issue_aug),
+epi_math = t[:, 6] - t[:, 4]
+for name, v in (("step", step), ("epilogue math+stores", epi_math), ("epilogue fence+arrive", t[:, 5] - t[:, 6]), ("wait_state", wait_state), ("issue_main", issue_main), ("issue_aug", issue_aug),
                 ("issued->D ready", d_to_epi), ("epilogue(warp4)", epi)):
     print(f"{name:18s} mean {v.mean():9.0f}  p10 {np.percentile(v, 10):9.0f}  p90 {np.percentile(v, 90):9.0f} cycles")
 
