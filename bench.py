@@ -139,17 +139,23 @@ def _cpu_state():
     return _CPU_STATE
 
 
-def cpu_throughput(frames_per_worker, workers):
+def cpu_throughput(frames_per_worker, workers, target_seconds=None):
     """OFDM symbols/s of the oracle port on `workers` host processes (1 BLAS
-    thread each; frames are independent, so this is the whole-host figure)."""
+    thread each; frames are independent, so this is the whole-host figure).
+    With `target_seconds` the sample is sized from a short calibration run."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
     with ctx.Pool(workers) as pool:
         pool.map(_cpu_worker, [(i, 1) for i in range(workers)])            # warm-up (weights, BLAS)
+        if target_seconds:
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, [(50 + i, 2) for i in range(workers)])
+            per_frame = (time.perf_counter() - t0) / 2
+            frames_per_worker = max(2, int(target_seconds / per_frame))
         t0 = time.perf_counter()
         pool.map(_cpu_worker, [(100 + i, frames_per_worker) for i in range(workers)])
         dt = time.perf_counter() - t0
-    return frames_per_worker * workers / dt, dt
+    return frames_per_worker * workers / dt, dt, frames_per_worker
 
 
 def run_reference(args):
@@ -163,7 +169,7 @@ def run_reference(args):
         cpu_throughput(1, workers)
     t_all = 0.0
     for _ in range(args.steps):
-        v, dt = cpu_throughput(fpw, workers)
+        v, dt, _ = cpu_throughput(fpw, workers)
         vals.append(v); t_all += dt
     value = float(np.mean(vals))
     line = {
@@ -233,8 +239,8 @@ def run_gpu(args):
     stream = torch.cuda.current_stream()
     path = args.path
     if path == "tc":
-        if per_group % 64:
-            raise SystemExit("--path tc needs --frames-per-block to be a multiple of 64")
+        if per_group % res.tc_tile_frames():
+            raise SystemExit(f"--path tc needs --frames-per-block to be a multiple of {res.tc_tile_frames()}")
         # fold the feedback into the weights per readout (part of training, untimed)
         readout = res.tc_prepare(W_out64, res.input_scale_exponent(frames))
         precision = "tc"
@@ -280,21 +286,36 @@ def run_gpu(args):
     kms = float(np.mean([a.elapsed_time(b) for a, b in kern_ms]))
     value = world * B * args.steps / (ms * 1e-3)
 
-    # ---- end to end: pinned host frames -> H2D -> detect -> D2H symbol indices ----
+    # ---- end to end: pinned host frames -> H2D -> detect -> D2H symbol indices, every step.
+    # Two device input buffers: the copy of step k+1 (copy stream) overlaps the kernels of step k.
     h_in = torch.empty((B, T_STEPS, ni), dtype=torch.float32).pin_memory()
     h_in.copy_(frames.cpu())
     h_out = torch.empty((B, CFG["N_sub"], CFG["N_t"]), dtype=torch.uint8).pin_memory()
-    d_in = torch.empty_like(frames)
-    for _ in range(2):
-        d_in.copy_(h_in, non_blocking=True)
-        h_out.copy_(step(d_in), non_blocking=True)
+    d_in = [torch.empty_like(frames), torch.empty_like(frames)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_loop(n):
+        for k in range(n):
+            buf = k & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[buf])          # kernels of step k-2 are done with this buffer
+                d_in[buf].copy_(h_in, non_blocking=True)
+                ready[buf].record(copy_stream)
+            stream.wait_event(ready[buf])
+            idx = step(d_in[buf])
+            consumed[buf].record(stream)
+            h_out.copy_(idx, non_blocking=True)
+
+    for e_ in consumed:
+        e_.record(stream)
+    e2e_loop(2)
     torch.cuda.synchronize()
     D.barrier()
     e0, e1 = ev(), ev()
     e0.record(stream)
-    for _ in range(args.steps):
-        d_in.copy_(h_in, non_blocking=True)
-        h_out.copy_(step(d_in), non_blocking=True)
+    e2e_loop(args.steps)
     e1.record(stream)
     torch.cuda.synchronize()
     D.barrier()
@@ -309,9 +330,9 @@ def run_gpu(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         workers = os.cpu_count() or 1
-        v, dt = cpu_throughput(args.cpu_frames_per_worker, workers)
+        v, dt, fpw = cpu_throughput(0, workers, target_seconds=args.cpu_seconds)
         cpu = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
-               "sample": f"{args.cpu_frames_per_worker * workers} frames of the same workload "
+               "sample": f"{fpw * workers} frames of the same workload "
                          f"({dt:.1f} s; numpy float64 oracle port, one process per core, 1 BLAS thread each)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -338,14 +359,14 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=148 * 64, help="frames per GPU per step")
-    ap.add_argument("--frames-per-block", type=int, default=64, help="frames sharing one trained readout")
+    ap.add_argument("--frames-per-block", type=int, default=128, help="frames sharing one trained readout")
     ap.add_argument("--path", default="tc", choices=["tc", "simt"], help="recurrence kernel: tensor cores or SIMT")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"], help="SIMT path precision")
-    ap.add_argument("--cpu-frames-per-worker", type=int, default=12)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="size of the CPU-baseline sample")
     ap.add_argument("--ref-frames-per-worker", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
