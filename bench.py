@@ -345,7 +345,7 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_in.numel() * 4),
                 "d2h_bytes_per_step": int(h_out.numel()), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": 2 * args.steps,
-        "roofline": {"bound": "tensor", "kernel": ("esn_predict_tc" if path == "tc" else "esn_recurrence_simt"), "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": ("esn_predict_tc2 (cta_group::2)" if path == "tc" else "esn_recurrence_simt"), "achieved": achieved,
                      "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"], "traffic": None,
                      "peak_source": pk["src"] + " bf16 sustained", "kernel_ms": kms,
                      "algorithmic_flop_per_symbol": algorithmic_flops_per_symbol(),
