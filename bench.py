@@ -44,6 +44,20 @@ def algorithmic_flops_per_symbol():
     return T_STEPS * (2 * N * (N + ni + no) + 2 * no * (N + ni))
 
 
+def recorded_traffic(kernel, frames):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full`
+    capture (profiles/ncu_traffic.json), if it was taken on this kernel and batch size."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        if t.get("kernel") in kernel and int(t.get("frames_per_launch", -1)) == int(frames):
+            return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -346,7 +360,10 @@ def run_gpu(args):
                 "d2h_bytes_per_step": int(h_out.numel()), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": 2 * args.steps,
         "roofline": {"bound": "tensor", "kernel": ("esn_predict_tc2 (cta_group::2)" if path == "tc" else "esn_recurrence_simt"), "achieved": achieved,
-                     "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"], "traffic": None,
+                     "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"],
+                     "traffic": recorded_traffic("esn_predict_tc2" if path == "tc" else "esn_recurrence_simt", B),
+                     "note": ("fp16 hi/lo split issues 3 MMAs per algorithmic MMA: pipe utilisation = 3 x frac"
+                              if path == "tc" else "SIMT FP32 FMA path; tensor peak shown for reference only"),
                      "peak_source": pk["src"] + " bf16 sustained", "kernel_ms": kms,
                      "algorithmic_flop_per_symbol": algorithmic_flops_per_symbol(),
                      "kernel_share_of_step": kms / (ms / args.steps)},
