@@ -304,6 +304,92 @@ __global__ void demap_count_kernel(const T *__restrict__ X_hat, size_t total, in
     block_add_counts(errs, near, counts);
 }
 
+// ---- workload generation on the device ------------------
+// One CTA per frame: symbol indices -> QAM -> N*IFFT -> CP -> *sqrt(Pi) -> soft PA clip
+// x/sqrt(1+(|x|/A)^2) -> per-link FIR channel -> + AWGN -> received samples y_cp, and the
+// real-valued ESN input rows (re/im interleaved per antenna, `delay` trailing zero rows).
+// Reference: system_model_2/OFDM_MIMO_2-2_NBF_LDPC.py:402-426, :430-433.  Gaussian noise comes
+// from `noise` [B][N+CP][N_r] complex standard normals when given (parity runs), else from the
+// counter hash (Box-Muller) keyed by (seed, frame, sample, antenna).
+template <typename T>
+__global__ void synth_frames_kernel(const uint8_t *__restrict__ tx_idx, const T *__restrict__ taps,
+                                    const int *__restrict__ chan_index, const T *__restrict__ Pi,
+                                    const T *__restrict__ A_clip, const T *__restrict__ noise, T noise_std,
+                                    unsigned long long seed, int N, int cp, int N_t, int N_r, int ntaps,
+                                    int qam_bits, int delay, T *__restrict__ x_cp_out, T *__restrict__ y_cp,
+                                    T *__restrict__ esn_in) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int L = N + cp, b = blockIdx.x, logn = ilog2(N);
+    T *re = reinterpret_cast<T *>(sm), *im = re + N, *twr = im + N, *twi = twr + N / 2;
+    T *xr = twi + N / 2, *xi = xr + (size_t)N_t * L;          // clipped Tx samples [N_t][L]
+    fft_make_twiddles(twr, twi, N);
+    const int side = 1 << (qam_bits / 2);
+    const T cs = (T)1 / sqrt_t((T)(2.0 * (side * side - 1) / 3.0));
+    const T sp = sqrt_t(Pi[b]), A = A_clip[b];
+    for (int tx = 0; tx < N_t; ++tx) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < N; k += blockDim.x) {
+            const int id = tx_idx[((size_t)b * N + k) * N_t + tx];
+            const int r = bitrev(k, logn);
+            re[r] = (T)(2 * (id / side) - (side - 1)) * cs;       // index = side*i_re + i_im
+            im[r] = (T)(2 * (id % side) - (side - 1)) * cs;
+        }
+        fft_inplace(re, im, twr, twi, N, logn, true);             // = N * ifft(X)
+        for (int t = threadIdx.x; t < L; t += blockDim.x) {
+            const int src = t < cp ? N - cp + t : t - cp;
+            const T vr = re[src] * sp, vi = im[src] * sp;
+            if (x_cp_out) {
+                const size_t o = (((size_t)b * L + t) * N_t + tx) * 2;
+                x_cp_out[o] = vr; x_cp_out[o + 1] = vi;
+            }
+            const T m2 = (vr * vr + vi * vi) / (A * A);
+            const T g = (T)1 / sqrt_t((T)1 + m2);
+            xr[tx * L + t] = vr * g; xi[tx * L + t] = vi * g;
+        }
+    }
+    __syncthreads();
+    const T *cb = taps + (size_t)(chan_index ? chan_index[b] : b) * N_r * N_t * ntaps * 2;
+    const int rows = L + delay;
+    for (int e = threadIdx.x; e < rows * N_r; e += blockDim.x) {
+        const int t = e / N_r, rx = e - t * N_r;
+        T yr = 0, yi = 0;
+        if (t < L) {
+            for (int tx = 0; tx < N_t; ++tx) {
+                const T *c = cb + ((size_t)(rx * N_t + tx) * ntaps) * 2;
+                for (int k = 0; k < ntaps && k <= t; ++k) {
+                    const T ar = c[2 * k], ai = c[2 * k + 1];
+                    const T br = xr[tx * L + t - k], bi = xi[tx * L + t - k];
+                    yr += ar * br - ai * bi; yi += ar * bi + ai * br;
+                }
+            }
+            T nr, ni;
+            if (noise) {
+                const size_t o = (((size_t)b * L + t) * N_r + rx) * 2;
+                nr = noise[o]; ni = noise[o + 1];
+            } else {
+                const uint32_t key = esn_noise_key(seed ^ 0xA5A5A5A5ULL, (uint32_t)(2 * b), (uint32_t)t);
+                const uint32_t h1 = esn_mix32(key + (uint32_t)rx * 0xC2B2AE35U);
+                const uint32_t h2 = esn_mix32(h1 ^ 0x68E31DA4U);
+                const T u1 = ((T)(h1 >> 8) + (T)0.5) * (T)(1.0 / 16777216.0);
+                const T u2 = (T)(h2 >> 8) * (T)(1.0 / 16777216.0);
+                const T rad = sqrt_t((T)-2 * (T)log((double)u1));
+                T sn, cn;
+                sincospi_t((T)2 * u2, &sn, &cn);
+                nr = rad * cn; ni = rad * sn;
+            }
+            yr += noise_std * nr; yi += noise_std * ni;
+            if (y_cp) {
+                const size_t o = (((size_t)b * L + t) * N_r + rx) * 2;
+                y_cp[o] = yr; y_cp[o + 1] = yi;
+            }
+        }
+        if (esn_in) {
+            const size_t o = ((size_t)b * rows + t) * 2 * N_r + 2 * rx;
+            esn_in[o] = yr; esn_in[o + 1] = yi;
+        }
+    }
+}
+
 template <typename K>
 inline int allow_smem(K kern, size_t smem) {
     if (smem > 48 * 1024)
@@ -406,6 +492,29 @@ extern "C" int ofdm_demap_count(int dtype, const void *X_hat, int B, int N, int 
     else if (dtype == ESN_F64)
         demap_count_kernel<double><<<blocks, 256, 0, st>>>((const double *)X_hat, total, qam_bits, idx, tx_idx, boundary_eps, counts);
     else return ESN_E_BADARG;
+    return esn_launch_status();
+}
+
+extern "C" int ofdm_synth_frames(int dtype, const uint8_t *tx_idx, const void *taps, const int32_t *chan_index,
+                                 const void *Pi, const void *A_clip, const void *noise, double noise_std,
+                                 unsigned long long seed, int B, int N, int cp, int N_t, int N_r, int ntaps,
+                                 int qam_bits, int delay, void *x_cp, void *y_cp, void *esn_in, void *stream) {
+    if (!tx_idx || !taps || !Pi || !A_clip || (!y_cp && !esn_in)) return ESN_E_BADARG;
+    if (B <= 0 || N_t <= 0 || N_r <= 0 || ntaps <= 0 || cp < 0 || cp >= N || delay < 0 || !pow2_ok(N)) return ESN_E_BADARG;
+    if (qam_bits != 2 && qam_bits != 4 && qam_bits != 6) return ESN_E_BADARG;
+    const size_t el = 3 * (size_t)N + 2 * (size_t)N_t * (N + cp);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == ESN_F32) {
+        if (int rc = allow_smem(synth_frames_kernel<float>, el * sizeof(float))) return rc;
+        synth_frames_kernel<float><<<B, fft_threads(N), el * sizeof(float), st>>>(
+            tx_idx, (const float *)taps, chan_index, (const float *)Pi, (const float *)A_clip, (const float *)noise,
+            (float)noise_std, seed, N, cp, N_t, N_r, ntaps, qam_bits, delay, (float *)x_cp, (float *)y_cp, (float *)esn_in);
+    } else if (dtype == ESN_F64) {
+        if (int rc = allow_smem(synth_frames_kernel<double>, el * sizeof(double))) return rc;
+        synth_frames_kernel<double><<<B, fft_threads(N), el * sizeof(double), st>>>(
+            tx_idx, (const double *)taps, chan_index, (const double *)Pi, (const double *)A_clip, (const double *)noise,
+            noise_std, seed, N, cp, N_t, N_r, ntaps, qam_bits, delay, (double *)x_cp, (double *)y_cp, (double *)esn_in);
+    } else return ESN_E_BADARG;
     return esn_launch_status();
 }
 

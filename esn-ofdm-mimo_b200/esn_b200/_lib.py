@@ -76,6 +76,8 @@ SIGNATURES = {
     "ofdm_rx_fft": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "ofdm_equalize": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "ofdm_chanest": (_i, [_i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _d, _vp, _vp, _vp]),
+    "ofdm_synth_frames": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _d, C.c_uint64, _i, _i, _i, _i, _i, _i, _i, _i,
+                               _vp, _vp, _vp, _vp]),
     "ofdm_demap_count": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp, _d, _vp, _vp]),
 }
 

@@ -112,3 +112,37 @@ def demap_count(X_hat, qam_bits, tx_idx=None, boundary_eps=0.0, counts=None, wan
     check(lib.ofdm_demap_count(_CODE[rd], ptr(_cplx_view(X_hat)), B, N, N_t, qam_bits, ptr(idx), ptr(tx_idx),
                                float(boundary_eps), ptr(counts), _stream()), "ofdm_demap_count")
     return idx, counts
+
+
+def synth_frames(tx_idx, taps, Pi, A_clip, N, cp, qam_bits, noise_std, delay=0, chan_index=None, noise=None,
+                 seed=0, dtype=torch.float32, want_x_cp=False, want_y_cp=True, want_esn_in=True):
+    """Workload generation on the device (bits/indices -> received frames).  tx_idx [B,N,N_t]
+    uint8, taps [n_chan,N_r,N_t,ntaps] complex, Pi / A_clip scalars or [B].  Returns a dict with
+    x_cp [B,N+cp,N_t], y_cp [B,N+cp,N_r] (complex) and esn_in [B,N+cp+delay,2N_r] (real)."""
+    lib = _lib.load()
+    dev = tx_idx.device
+    B, _, N_t = tx_idx.shape
+    cd = torch.complex64 if dtype == torch.float32 else torch.complex128
+    taps = taps.to(device=dev, dtype=cd).contiguous()
+    _, N_r, _, ntaps = taps.shape
+    tx_idx = tx_idx.to(torch.uint8).contiguous()
+    pi = torch.as_tensor(Pi, dtype=dtype, device=dev).reshape(-1)
+    pi = (pi.expand(B) if pi.numel() == 1 else pi).contiguous()
+    ac = torch.as_tensor(A_clip, dtype=dtype, device=dev).reshape(-1)
+    ac = (ac.expand(B) if ac.numel() == 1 else ac).contiguous()
+    if chan_index is not None:
+        chan_index = chan_index.to(device=dev, dtype=torch.int32).contiguous()
+    elif taps.shape[0] != B:
+        raise ValueError("chan_index required when fewer channel realisations than frames are given")
+    if noise is not None:
+        noise = noise.to(device=dev, dtype=cd).contiguous()
+    L = N + cp
+    x_cp = torch.empty((B, L, N_t), dtype=cd, device=dev) if want_x_cp else None
+    y_cp = torch.empty((B, L, N_r), dtype=cd, device=dev) if want_y_cp else None
+    esn_in = torch.empty((B, L + delay, 2 * N_r), dtype=dtype, device=dev) if want_esn_in else None
+    rv = lambda t: None if t is None else ptr(torch.view_as_real(t))    # noqa: E731
+    check(lib.ofdm_synth_frames(_CODE[dtype], ptr(tx_idx), rv(taps), ptr(chan_index), ptr(pi), ptr(ac), rv(noise),
+                                float(noise_std), int(seed) & 0xFFFFFFFFFFFFFFFF, B, N, cp, N_t, N_r, ntaps,
+                                qam_bits, int(delay), rv(x_cp), rv(y_cp), ptr(esn_in), _stream()),
+          "ofdm_synth_frames")
+    return dict(x_cp=x_cp, y_cp=y_cp, esn_in=esn_in)

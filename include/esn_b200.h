@@ -227,6 +227,17 @@ int ofdm_equalize(int dtype, const void *Y, const void *H, const int32_t *h_inde
 int ofdm_chanest(int dtype, const void *Y_LS, const void *X_LS, int B, int N, int N_r,
                  int N_t, const void *Pi, const void *isi_magnitude, int taps,
                  double No, void *H_LS, void *H_MMSE, void *stream);
+/* Workload generation: symbol indices -> QAM -> N*IFFT -> CP -> *sqrt(Pi)
+ * -> soft PA clip x/sqrt(1+(|x|/A)^2) -> FIR channel per link -> + noise_std * CN(0,2) -> y_cp
+ * [B][N+CP][N_r] complex and/or the real ESN input rows esn_in [B][N+CP+delay][2 N_r].
+ * Replaces system_model_2/OFDM_MIMO_2-2_NBF_LDPC.py:402-426 (Tx chain, lfilter, AWGN) and
+ * :430-433 (ESN input packing).  taps [n_chan][N_r][N_t][ntaps] complex, chan_index[b] or null
+ * (= b); noise [B][N+CP][N_r] complex standard normals or null (device counter stream `seed`);
+ * x_cp [B][N+CP][N_t] complex receives the unclipped Tx samples (the ESN teacher) or null. */
+int ofdm_synth_frames(int dtype, const uint8_t *tx_idx, const void *taps, const int32_t *chan_index,
+                      const void *Pi, const void *A_clip, const void *noise, double noise_std,
+                      unsigned long long seed, int B, int N, int cp, int N_t, int N_r, int ntaps,
+                      int qam_bits, int delay, void *x_cp, void *y_cp, void *esn_in, void *stream);
 int ofdm_demap_count(int dtype, const void *X_hat, int B, int N, int N_t, int qam_bits,
                      uint8_t *idx, const uint8_t *tx_idx, double boundary_eps,
                      unsigned long long *err_count, void *stream);

@@ -1,0 +1,141 @@
+"""GPU tests of the surrounding chain at link level: on-device frame synthesis against the
+oracle's generator, and a small BER-vs-SNR Monte-Carlo (train on the pilot, detect the data
+frames in one batched launch, demap + count on the device) against the oracle run on the very
+same bits, channels and noise.  "BER-vs-SNR curves must match" (BASELINE.json)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import esn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import __graft_entry__ as g
+    g.build()
+
+
+def _cuda(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def _host_block(rng, N, N_t, N_r, m, ebno_db, n_frames, isi=8, No=1e-5):
+    """Random bits, one channel draw and AWGN for n_frames frames (frame 0 = pilot)."""
+    cp = isi - 1
+    Pi = 10 ** (ebno_db / 10) * No
+    var_x = 10 ** (ebno_db / 10) * No * N
+    A = math.sqrt(var_x) * 10 ** (3 / 20)
+    mag = orc.isi_profile(isi)
+    c = orc.draw_channel(rng, N_r, N_t, mag, isi)
+    idx = rng.randint(0, 2 ** m, size=(n_frames, N, N_t))
+    nz = rng.randn(n_frames, N + cp, N_r) + 1j * rng.randn(n_frames, N + cp, N_r)
+    return dict(c=c, idx=idx, nz=nz, Pi=Pi, A=A, var_x=var_x, cp=cp, No=No, std=math.sqrt((N + cp) * No / 2))
+
+
+def _oracle_frames(blk, N, N_t, N_r, m):
+    const = orc.unit_qam_constellation(m)
+    xs, ys = [], []
+    for f in range(blk["idx"].shape[0]):
+        x_cp, x_nld = orc.tx_frame(const[blk["idx"][f]], N, blk["cp"], blk["Pi"], blk["A"])
+        y = np.zeros((N + blk["cp"], N_r), dtype=complex)
+        for nr in range(N_r):
+            for tx in range(N_t):
+                y[:, nr] += orc.fir_causal(blk["c"][nr, tx], x_nld[:, tx])
+        y += blk["std"] * blk["nz"][f]
+        xs.append(x_cp)
+        ys.append(y)
+    return np.stack(xs), np.stack(ys)
+
+
+@pytest.mark.parametrize("shape", [(32, 2, 2, 4), (64, 4, 8, 4), (128, 1, 2, 2), (512, 4, 8, 6)])
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_frame_synthesis_matches_oracle(shape, dt):
+    from esn_b200 import ofdm
+    N, N_t, N_r, m = shape
+    rng = np.random.RandomState(N + N_t)
+    blk = _host_block(rng, N, N_t, N_r, m, 15, 3)
+    x_ref, y_ref = _oracle_frames(blk, N, N_t, N_r, m)
+    rd = torch.float64 if dt == "f64" else torch.float32
+    out = ofdm.synth_frames(_cuda(blk["idx"].astype(np.uint8)), _cuda(blk["c"][None]), blk["Pi"], blk["A"], N,
+                            blk["cp"], m, blk["std"], delay=3, chan_index=torch.zeros(3, dtype=torch.int32),
+                            noise=_cuda(blk["nz"]), dtype=rd, want_x_cp=True)
+    tol = 1e-12 if dt == "f64" else 3e-6
+    assert rel_err(out["x_cp"].cpu().numpy(), x_ref) < tol
+    assert rel_err(out["y_cp"].cpu().numpy(), y_ref) < tol
+    ein = out["esn_in"].cpu().numpy()
+    for f in range(3):
+        assert rel_err(ein[f], orc.pack_rx(y_ref[f], 3)) < tol
+    assert np.all(ein[:, N + blk["cp"]:, :] == 0)
+
+
+def test_device_noise_stream_statistics():
+    from esn_b200 import ofdm
+    N, N_t, N_r, m = 256, 2, 4, 4
+    rng = np.random.RandomState(3)
+    blk = _host_block(rng, N, N_t, N_r, m, 12, 64)
+    kw = dict(chan_index=torch.zeros(64, dtype=torch.int32), dtype=torch.float32)
+    idx = _cuda(blk["idx"].astype(np.uint8))
+    clean = ofdm.synth_frames(idx, _cuda(blk["c"][None]), blk["Pi"], blk["A"], N, blk["cp"], m, 0.0, **kw)["y_cp"]
+    noisy = ofdm.synth_frames(idx, _cuda(blk["c"][None]), blk["Pi"], blk["A"], N, blk["cp"], m, blk["std"], seed=5,
+                              **kw)["y_cp"]
+    again = ofdm.synth_frames(idx, _cuda(blk["c"][None]), blk["Pi"], blk["A"], N, blk["cp"], m, blk["std"], seed=5,
+                              **kw)["y_cp"]
+    assert torch.equal(noisy, again)                       # counter stream: reproducible
+    n = ((noisy - clean) / blk["std"]).cpu().numpy().ravel()
+    assert abs(n.real.mean()) < 0.02 and abs(n.imag.mean()) < 0.02
+    assert abs(n.real.var() - 1) < 0.03 and abs(n.imag.var() - 1) < 0.03
+    assert abs(np.mean(n.real * n.imag)) < 0.02
+    assert abs(np.mean(n.real ** 4) - 3) < 0.2             # Gaussian kurtosis
+
+
+def test_ber_curve_matches_oracle():
+    """2x2, 32 subcarriers, 3 SNR points x 3 coherence blocks x 6 data frames: identical bits,
+    channels and noise on both sides; the GPU path's error counts must equal the oracle's except
+    for decisions within 1e-5 of a slicer boundary."""
+    from pyESN import ESN
+    from helper_mimo_esn_generic import trainMIMOESN_generic
+    from esn_b200 import ofdm
+    N, N_t, N_r, m, isi = 32, 2, 2, 4, 8
+    maxd = int(math.ceil(isi / 2) + 2)
+    const = orc.unit_qam_constellation(m)
+    n_data = 6
+    for ebno in (6, 15, 27):
+        err_gpu = err_cpu = near_total = 0
+        for blk_i in range(3):
+            rng = np.random.RandomState(1000 * ebno + blk_i)
+            blk = _host_block(rng, N, N_t, N_r, m, ebno, 1 + n_data, isi)
+            # frames on the device (pilot + data), in fp64 so both sides see the same samples
+            out = ofdm.synth_frames(_cuda(blk["idx"].astype(np.uint8)), _cuda(blk["c"][None]), blk["Pi"], blk["A"], N,
+                                    blk["cp"], m, blk["std"], chan_index=torch.zeros(1 + n_data, dtype=torch.int32),
+                                    noise=_cuda(blk["nz"]), dtype=torch.float64, want_x_cp=True)
+            x_cp, y_cp = out["x_cp"].cpu().numpy(), out["y_cp"].cpu().numpy()
+            kw = dict(n_inputs=2 * N_r, n_outputs=2 * N_t, n_reservoir=48, spectral_radius=0.9, sparsity=0.1,
+                      input_shift=np.zeros(2 * N_r), input_scaling=(0.005 / blk["var_x"] ** 0.5) * np.ones(2 * N_r),
+                      teacher_scaling=5e-7 * np.ones(2 * N_t), teacher_shift=np.zeros(2 * N_t),
+                      random_state=77 + blk_i, noise=0.0)
+            gpu, cpu = ESN(**kw), orc.OracleESN(**kw)
+            rg = trainMIMOESN_generic(gpu, 0, 0, maxd, blk["cp"], N, N_t, N_r, isi, y_cp[0], x_cp[0])
+            orc.train_generic(cpu, 0, 0, maxd, blk["cp"], N, N_t, N_r, isi, y_cp[0], x_cp[0])
+            d, nforget = int(rg[6]), int(rg[7])
+            frames = np.stack([orc.pack_rx(y_cp[1 + f], d) for f in range(n_data)])
+            tx_idx = blk["idx"][1:].astype(np.uint8)
+            y = gpu.predict_batched(_cuda(frames), _cuda(gpu.W_out[None]), transient=nforget, precision="fp64")
+            _, idx, counts = ofdm.unpack_fft_demap(y, N, N_t, blk["Pi"], m, tx_idx=_cuda(tx_idx), boundary_eps=1e-5)
+            err_gpu += int(counts[0])
+            near_total += int(counts[1])
+            for f in range(n_data):
+                p = cpu.predict(frames[f], nforget, continuation=False)
+                Xo = orc.esn_output_to_freq(p, N, N_t, blk["Pi"])
+                io = orc.hard_demap_indices(Xo, const)
+                err_cpu += int((orc.indices_to_bits(io, m) != orc.indices_to_bits(blk["idx"][1 + f], m)).sum())
+        assert abs(err_gpu - err_cpu) <= 4 * near_total, (ebno, err_gpu, err_cpu, near_total)
+        ber = err_gpu / (3 * n_data * N * N_t * m)
+        assert 0.0 <= ber <= 0.6
