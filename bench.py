@@ -216,6 +216,14 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     esn_b200.load()
 
+    # ---- link parameters of the block-fading template (OFDM_MIMO_2-2_NBF_LDPC.py:117-179) at one SNR point
+    ebno_db, No, isi = args.ebno, 1e-5, 8
+    Nsub, cp, d, N_t, N_r = CFG["N_sub"], CFG["cp"], CFG["delay"], CFG["N_t"], CFG["N_r"]
+    Pi = 10 ** (ebno_db / 10) * No
+    var_x = 10 ** (ebno_db / 10) * No * Nsub
+    A_clip = var_x ** 0.5 * 10 ** (3 / 20)
+    noise_std = ((Nsub + cp) * No / 2) ** 0.5
+
     # reservoir: numpy init on the host (bit-identical to pyESN for seed 42), uploaded once
     rng = np.random.RandomState(CFG["seed"])
     N, ni, no = CFG["n_res"], CFG["n_in"], CFG["n_out"]
@@ -224,31 +232,49 @@ def run_gpu(args):
     W *= CFG["rho"] / np.max(np.abs(np.linalg.eigvals(W)))
     W_in = rng.rand(N, ni) * 2 - 1
     W_fb = rng.rand(N, no) * 2 - 1
-    res = Reservoir(W, W_in, W_fb, input_scaling=CFG["in_scale"] * np.ones(ni), input_shift=np.zeros(ni),
-                    teacher_scaling=CFG["t_scale"] * np.ones(no), teacher_shift=np.zeros(no),
-                    noise=CFG["noise"], teacher_forcing=True, device=dev)
+    res = Reservoir(W, W_in, W_fb, input_scaling=(CFG["in_scale"] / var_x ** 0.5) * np.ones(ni),
+                    input_shift=np.zeros(ni), teacher_scaling=CFG["t_scale"] * np.ones(no),
+                    teacher_shift=np.zeros(no), noise=CFG["noise"], teacher_forcing=True, device=dev)
 
     B, per_group = args.frames, args.frames_per_block
     G = (B + per_group - 1) // per_group
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    # synthetic pilots -> one trained readout per coherence block (untimed setup, on the device)
-    pil_u = torch.randn((G, T_STEPS, ni), generator=gen, device=dev, dtype=torch.float64)
-    mix = torch.randn((ni, no), generator=gen, device=dev, dtype=torch.float64) / ni ** 0.5
-    pil_y = pil_u @ mix * 1e-2
+    # one Rayleigh channel draw per coherence block: 8 taps, exponential power-delay profile
+    mag = np.exp(-np.arange(isi) / ((isi - 1) / 9))
+    mag = torch.tensor(mag / mag.sum(), device=dev)
+    taps = (torch.randn((G, N_r, N_t, isi), generator=gen, device=dev, dtype=torch.float64)
+            + 1j * torch.randn((G, N_r, N_t, isi), generator=gen, device=dev, dtype=torch.float64)) / 2 ** 0.5
+    taps = taps * mag.sqrt()
+    # pilots -> one trained readout per block (untimed setup; fp64 harvest + Gram + Cholesky on the device)
+    pil_idx = torch.randint(0, 16, (G, Nsub, N_t), generator=gen, device=dev, dtype=torch.uint8)
+    pil = esn_b200.ofdm.synth_frames(pil_idx, taps, Pi, A_clip, Nsub, cp, CFG["qam_bits"], noise_std, delay=d,
+                                     seed=11 + rank, dtype=torch.float64, want_x_cp=True, want_y_cp=False)
+    pil_u = pil["esn_in"]
+    pil_y = torch.zeros((G, T_STEPS, no), dtype=torch.float64, device=dev)
+    pil_y[:, d:, :] = torch.view_as_real(pil["x_cp"]).reshape(G, Nsub + cp, no)      # teacher delayed by d rows
     W_out_parts = []
+    fit_ms = 0.0
     for g0 in range(0, G, 64):
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
         ext = res.harvest(pil_u[g0:g0 + 64], pil_y[g0:g0 + 64], precision="fp64", seed=7 + g0)
         w, info = res.train_readout(ext, pil_y[g0:g0 + 64], TRANSIENT)
+        f1.record()
+        torch.cuda.synchronize()
+        fit_ms += f0.elapsed_time(f1)
         assert int(info.abs().max()) == 0, "readout training failed"
         W_out_parts.append(w)
         del ext
     group_ids = (torch.arange(B, device=dev) // per_group).to(torch.int32)
     W_out64 = torch.cat(W_out_parts)
     del W_out_parts
-    frames = torch.randn((B, T_STEPS, ni), generator=gen, device=dev, dtype=torch.float32)
-    tx_idx = torch.randint(0, 16, (B, CFG["N_sub"], CFG["N_t"]), generator=gen, device=dev, dtype=torch.uint8)
-    Pi = 10 ** (15 / 10) * 1e-5
+    # data frames of every block through its channel, on the device
+    tx_idx = torch.randint(0, 16, (B, Nsub, N_t), generator=gen, device=dev, dtype=torch.uint8)
+    frames = esn_b200.ofdm.synth_frames(tx_idx, taps.to(torch.complex64), Pi, A_clip, Nsub, cp, CFG["qam_bits"],
+                                        noise_std, delay=d, chan_index=group_ids, seed=23 + rank,
+                                        dtype=torch.float32, want_y_cp=False)["esn_in"]
+    y_absmax = float((pil_y.abs().max() * CFG["t_scale"]).item())
     counts = torch.zeros(2, dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream()
     path = args.path
@@ -256,7 +282,7 @@ def run_gpu(args):
         if per_group % res.tc_tile_frames():
             raise SystemExit(f"--path tc needs --frames-per-block to be a multiple of {res.tc_tile_frames()}")
         # fold the feedback into the weights per readout (part of training, untimed)
-        readout = res.tc_prepare(W_out64, res.input_scale_exponent(frames))
+        readout = res.tc_prepare(W_out64, res.input_scale_exponent(frames), y_absmax=y_absmax)
         precision = "tc"
     else:
         readout = W_out64.to(torch.float32).contiguous()
@@ -336,6 +362,11 @@ def run_gpu(args):
     e2e_ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
 
+    counts.zero_()
+    step(frames)
+    torch.cuda.synchronize()
+    bit_errors = int(counts[0].item())           # summed over ranks by the allreduce inside step()
+    total_bits = world * B * Nsub * N_t * CFG["qam_bits"]
     if rank != 0:
         return
     pk = peaks()
@@ -354,6 +385,9 @@ def run_gpu(args):
         "vs_baseline": None, "dtype": ("f16x2-split/f32-accum" if path == "tc" else ("f32" if args.precision == "fp32" else "f64")), "data": "synthetic",
         "config": {"workload": "cfg3_4x8_16qam_nsub512_nres512_T522", "frames_per_gpu_per_step": B,
                    "frames_per_coherence_block": per_group, "readouts_per_gpu": G, "state_noise": "0.001 device counter stream",
+                   "link": f"block-fading Rayleigh 8 taps, 16-QAM, Eb/N0 {ebno_db} dB, soft PA clip 3 dB, frames synthesised on the device",
+                   "uncoded_ber_esn": bit_errors / total_bits,
+                   "readout_training": f"{G} pilots/GPU, fp64 harvest + Gram + Cholesky on the device, {fit_ms:.1f} ms (untimed setup)",
                    "recurrence_path": ("tcgen05 fp16 hi/lo split x3, fp32 accumulate in TMEM" if path == "tc" else "simt_" + args.precision), "parallelism": f"frames sharded x{world}",
                    "l2": f"inputs {frames.numel() * 4 / 2**20:.0f} MiB + outputs per step exceed the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_in.numel() * 4),
@@ -386,6 +420,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="size of the CPU-baseline sample")
     ap.add_argument("--ref-frames-per-worker", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ebno", type=float, default=15.0, help="Eb/N0 (dB) of the simulated link")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
