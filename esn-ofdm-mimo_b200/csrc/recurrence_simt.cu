@@ -12,6 +12,8 @@
 // into shared memory between steps; that keeps ONE state buffer on chip and
 // doubles the frame tile that fits.  The readout y_n = W_out [x_n; u_n] that the
 // free-running mode feeds back is fused between steps.
+#include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -321,6 +323,14 @@ int launch_any(const RecParams &p, cudaStream_t st) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // tuning aid: ESN_SIMT_CFG="BT,WN,KC" forces one of the instantiated tiles
+    int fb = 0, fw = 0, fk = 0;
+    if (const char *e = getenv("ESN_SIMT_CFG")) sscanf(e, "%d,%d,%d", &fb, &fw, &fk);
+#define FORCE(BT_, WN_, KC_)                                                            \
+    if (fb == BT_ && fw == WN_ && fk == KC_) return launch_cfg<T, BT_, WN_, KC_>(p, st, false);
+    FORCE(64, 2, 8) FORCE(32, 2, 16) FORCE(32, 2, 8) FORCE(16, 4, 16) FORCE(16, 4, 8) FORCE(8, 4, 16) FORCE(8, 4, 8)
+    FORCE(8, 2, 8) FORCE(8, 4, 4) FORCE(16, 4, 4) FORCE(16, 2, 8) FORCE(32, 1, 16)
+#undef FORCE
 #define TRY(BT_, WN_, KC_)                                                              \
     if ((p.B + BT_ - 1) / BT_ >= sms && launch_cfg<T, BT_, WN_, KC_>(p, st, true) == 0)  \
         return launch_cfg<T, BT_, WN_, KC_>(p, st, false);
@@ -329,6 +339,12 @@ int launch_any(const RecParams &p, cudaStream_t st) {
         return launch_cfg<T, BT_, WN_, KC_>(p, st, false);
     if (slabs128 == 1) {
         TRY(64, 1, 16) TRY(32, 1, 16) TRY(16, 1, 16) LAST(8, 1, 16)
+        return ESN_E_TOOLARGE;
+    }
+    if (sizeof(T) == 8) {
+        // fp64: measured on B200 (profiles/fit_bench.py, 1184 frames, N=512): (8,4,8) 46 ms,
+        // (8,4,16) 113 ms, (16,4,8) 62 ms, (32,2,8) 96 ms -> small tiles with KC=8 first
+        TRY(32, 2, 8) TRY(16, 4, 8) LAST(8, 4, 8) LAST(8, 2, 8) LAST(8, 4, 4)
         return ESN_E_TOOLARGE;
     }
     TRY(64, 2, 8) TRY(32, 2, 16) TRY(32, 2, 8) TRY(16, 4, 16) TRY(16, 4, 8)

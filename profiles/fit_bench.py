@@ -8,7 +8,7 @@ rng = np.random.RandomState(42)
 W = rng.rand(N, N) - 0.5; W[rng.rand(N, N) < 0.1] = 0; W *= 0.9/np.max(np.abs(np.linalg.eigvals(W)))
 res = Reservoir(W, rng.rand(N, ni)*2-1, rng.rand(N, no)*2-1, input_scaling=0.005*np.ones(ni), teacher_scaling=5e-7*np.ones(no), noise=0.001)
 def ev(): return torch.cuda.Event(enable_timing=True)
-for G in (74, 592, 1184):
+for G in (int(a) for a in (sys.argv[1:] or (74, 592, 1184))):
     u = torch.randn(G, T, ni, device="cuda", dtype=torch.float64)
     y = torch.randn(G, T, no, device="cuda", dtype=torch.float64)*1e-2
     for prec in ("fp64", "fp32"):
