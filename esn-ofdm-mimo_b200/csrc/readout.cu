@@ -166,7 +166,7 @@ __global__ void scaled_teacher_rows_kernel(const TY *__restrict__ teacher, const
 constexpr int NB = 32;
 constexpr int CH_THREADS = 256;
 
-__global__ void __launch_bounds__(CH_THREADS)
+__global__ void __launch_bounds__(CH_THREADS, 2)
 cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_all, int n, int n_rhs,
                           int *__restrict__ info_all) {
     double *A = Gall + (size_t)blockIdx.x * n * n;
