@@ -684,75 +684,173 @@ __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr) { return (saddr >
 
 constexpr int PF = 2 * FT;             // frames per CTA pair
 constexpr int SLOT2 = SLOT + 2048;     // pair-kernel ring slot: weight tile + up to two 1 KB readout half-tiles
+constexpr int YCOL2 = 256;             // TMEM column of the pair kernel's readout accumulator
 
-// One half (32 frames) of an epilogue thread's work: v[] = accumulators of its neuron for 32
-// consecutive frames -> tanh -> noise -> x 2^SX -> fp16 hi/lo, written as four 16-byte stores per
-// half (eight frames each) into the owner CTA's MN-major state tile.  Pade tanh for every element;
-// returns true if some |z| > 3 (the caller then patches with FIX = true, exact formula).
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): two lanes per instruction ----
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t a, uint32_t b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ void un2(uint64_t v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
+
+// 16-byte asynchronous store into a (possibly remote) CTA's shared memory; the destination CTA's
+// mbarrier counts the bytes (complete_tx), so the writer needs no fence and no arrive (STAS).
+__device__ __forceinline__ void stas_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                        uint32_t cluster_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(cluster_mbar) : "memory");
+}
+
+// Per-thread constants of the pair kernel's epilogue (zeroed for padded neurons, so that their
+// state stays exactly 0 without a select per element).
+struct EpiConst {
+    float dsc;        // 2^-(SX+SW): accumulator -> pre-activation
+    float amp16s;     // noise_amp 2^-16 2^SX : 16-bit uniform -> scaled noise
+    float ampoffs;    // noise_amp / 2 2^SX
+    float ampf;       // noise_amp 2^SX (host-noise path)
+};
+
+// One accumulator group of an epilogue thread: v[] = accumulators of its neuron for 32 consecutive
+// frames -> [7/6] Pade tanh -> noise -> x 2^SX -> fp16 hi/lo, written as four 16-byte stores per half
+// (eight frames each) into the owner CTA's MN-major state tile.  Two frames per instruction through
+// the packed fp32x2 pipe; the 2^SX pre-scale is folded into the numerator.  FIX = true (chosen by the
+// caller when some |z| > 3, rare in an echo-state reservoir) patches those elements with the exact
+// formula.  Every granule is stored exactly once: the destination barrier counts the bytes.
 template <bool DBG, bool FIX>
-__device__ __forceinline__ bool tc2_epilogue_half(const TcParams &p, const uint32_t (&v)[32], int it, int n, bool n_ok,
-                                                  int fbase, int half, bool full_tile, const uint32_t *keys,
-                                                  uint32_t nmul, uint32_t rowaddr, int kx, uint32_t lo_delta, int P) {
-    const float dscale = ldexpf(1.0f, -(SX + SW)), xscale = ldexpf(1.0f, SX);
+__device__ __forceinline__ void tc2_epilogue32(const TcParams &p, const uint32_t (&v)[32], int it, int n, bool n_ok,
+                                               int fbase, const uint32_t *keys, uint32_t nmul, uint32_t rowaddr,
+                                               int gsel, int kx, uint32_t lo_delta, int P, const EpiConst &ec,
+                                               uint32_t mbar) {
+    constexpr float XS = (float)(1 << SX);
     const bool use_noise = p.noise_amp != 0.f;
-    const float amp16 = p.noise_amp * (1.0f / 65536.0f), ampoff = 0.5f * p.noise_amp;
-    bool big = false;
+    const uint64_t dsc2 = pk2(ec.dsc, ec.dsc);
+    const uint64_t n0 = pk2(XS, XS), n1 = pk2(378.0f * XS, 378.0f * XS), n2 = pk2(17325.0f * XS, 17325.0f * XS),
+                   n3 = pk2(135135.0f * XS, 135135.0f * XS);
+    const uint64_t d0 = pk2(28.0f, 28.0f), d1 = pk2(3150.0f, 3150.0f), d2 = pk2(62370.0f, 62370.0f),
+                   d3 = pk2(135135.0f, 135135.0f);
+    const uint64_t amp2 = pk2(ec.amp16s, ec.amp16s), off2 = pk2(-ec.ampoffs, -ec.ampoffs);
 #pragma unroll
     for (int g8 = 0; g8 < 4; ++g8) {                      // granule of 8 frames
         uint32_t hi2[4], lo2[4];
-        bool any_large = false;
 #pragma unroll
         for (int pr = 0; pr < 4; ++pr) {                  // pair of frames
-            const int jj = g8 * 8 + pr * 2, f0 = half * 32 + jj;
-            uint32_t hb = 0;
-            if (use_noise && !(DBG && p.noise)) hb = esn_mix32(keys[f0 >> 1] + nmul);
-            float xs[2];
+            const int jj = g8 * 8 + pr * 2;
+            const uint64_t z = mul2(pk2u(v[jj], v[jj + 1]), dsc2);
+            const uint64_t z2 = mul2(z, z);
+            uint64_t num = fma2(z2, n0, n1);
+            num = fma2(num, z2, n2);
+            num = fma2(num, z2, n3);
+            uint64_t den = fma2(d0, z2, d1);
+            den = fma2(den, z2, d2);
+            den = fma2(den, z2, d3);
+            float za, zb, da, db;
+            un2(z, za, zb);
+            un2(den, da, db);
+            uint64_t nt = pk2(0.f, 0.f);                  // noise term, already x 2^SX
+            if (use_noise) {
+                if (DBG && p.noise) {
+                    float u[2];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int f = f0 + e;
-                const float z = __uint_as_float(v[jj + e]) * dscale;
-                const bool large = fabsf(z) > 3.0f;
-                any_large |= large;
-                float x = (FIX && large) ? tanh_large(z) : tanh_pade(z);
-                if (use_noise) {
-                    if (DBG && p.noise) {
-                        const int b = fbase + f;
-                        const float u = (b < p.B && n_ok) ? p.noise[((size_t)b * p.T + it) * p.N + n] : 0.5f;
-                        x = fmaf(u, p.noise_amp, x - ampoff);
-                    } else {
-                        x = fmaf((float)(e ? (hb >> 16) : (hb & 0xFFFFu)), amp16, x - ampoff);
+                    for (int e = 0; e < 2; ++e) {
+                        const int b = fbase + jj + e;
+                        u[e] = (b < p.B && n_ok) ? p.noise[((size_t)b * p.T + it) * p.N + n] : 0.5f;
                     }
+                    nt = pk2(fmaf(u[0], ec.ampf, -ec.ampoffs), fmaf(u[1], ec.ampf, -ec.ampoffs));
+                } else {
+                    const uint32_t hb = esn_mix32(keys[jj >> 1] + nmul);
+                    nt = fma2(pk2((float)(hb & 0xFFFFu), (float)(hb >> 16)), amp2, off2);
                 }
-                if (!n_ok || (!full_tile && fbase + f >= p.B)) x = 0.f;
-                if (DBG && p.ext_out && n_ok && fbase + f < p.B)
-                    p.ext_out[((size_t)(fbase + f) * p.T + it) * P + n] = x;
-                xs[e] = x * xscale;
             }
-            const uint32_t h = pack_h2(xs[0], xs[1]);
-            const __half2 hh = *reinterpret_cast<const __half2 *>(&h);
-            const float2 back = __half22float2(hh);
+            uint64_t xs = fma2(mul2(num, z), pk2(rcp_approx(da), rcp_approx(db)), nt);
+            if (FIX) {
+                float xa, xb, na, nb;
+                un2(xs, xa, xb);
+                un2(nt, na, nb);
+                if (fabsf(za) > 3.0f) xa = fmaf(tanh_large(za), n_ok ? XS : 0.f, na);
+                if (fabsf(zb) > 3.0f) xb = fmaf(tanh_large(zb), n_ok ? XS : 0.f, nb);
+                xs = pk2(xa, xb);
+            }
+            float xa, xb;
+            un2(xs, xa, xb);
+            if (DBG && p.ext_out && n_ok) {
+                const int b = fbase + jj;
+                if (b < p.B) p.ext_out[((size_t)b * p.T + it) * P + n] = xa * (1.0f / XS);
+                if (b + 1 < p.B) p.ext_out[((size_t)(b + 1) * p.T + it) * P + n] = xb * (1.0f / XS);
+            }
+            const uint32_t h = pack_h2(xa, xb);
+            const float2 back = __half22float2(*reinterpret_cast<const __half2 *>(&h));
+            float la, lb;
+            un2(sub2(xs, pk2(back.x, back.y)), la, lb);
             hi2[pr] = h;
-            lo2[pr] = pack_h2(xs[0] - back.x, xs[1] - back.y);
+            lo2[pr] = pack_h2(la, lb);
         }
-        big |= any_large;
-        if (!FIX || any_large) {
-            const uint32_t a = rowaddr + ((uint32_t)((half * 4 + g8) ^ kx) << 4);
-            sts_cluster_v4(a, hi2[0], hi2[1], hi2[2], hi2[3]);
-            sts_cluster_v4(a + lo_delta, lo2[0], lo2[1], lo2[2], lo2[3]);
-        }
+        const uint32_t a = rowaddr + ((uint32_t)((gsel + g8) ^ kx) << 4);
+        stas_v4(a, hi2[0], hi2[1], hi2[2], hi2[3], mbar);
+        stas_v4(a + lo_delta, lo2[0], lo2[1], lo2[2], lo2[3], mbar);
     }
-    return big;
 }
 
-template <bool DBG>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_predict_tc2(const TcParams p) {
+// Step schedule of the pair kernel (identical in producer, relay and issuer).  With two accumulator
+// groups (N_pad = 512) the epilogue finishes group 0 (neurons 0..255 = state chunks 0..3) first, so
+// the next step's MMAs over those chunks overlap the epilogue of group 1:
+//   wait tA (chunks 0..H1-1 rewritten in both CTAs; implies D0 drained)
+//     phase 1: chunks [0,H1) of group 0; each item also carries the readout half-tile of its chunk
+//   wait tB (all chunks + the input block rewritten, D1 drained)
+//     phase 2: chunks [H1,C-1) of group 0 (+ readout; the first item also carries the aug chunk's
+//              readout tile) -> commit y;  then every state chunk of the other groups, which hides
+//              the round trip of y through the frame warps (~6 K cycles)
+//   wait yready (y_{t-1} is in the state tile)
+//     phase 3: aug chunk of every group -> commit d
+// H1 = 4 for two groups, 0 for one (N_pad = 256: nothing to overlap with).
+//
+// State hand-off: the epilogue writes the new state with st.async (STAS) straight into the owner
+// CTA's tile; the owner's mbarriers tA / tB count the bytes (64 KB per accumulator group and CTA), so
+// the 16 epilogue warps neither fence nor arrive.  Warp 20 of each CTA posts the expected byte count
+// once per step and, in CTA 1, forwards the completion to the issuer in CTA 0 (fA / fB).
+constexpr int TC2_THREADS = 672;       // 21 warps: 0-1 frame, 2 producer, 3 issuer / relay, 4-19 epilogue, 20 poster
+constexpr uint32_t GROUP_BYTES = 2u * FT * 256u * 2u;   // hi + lo of 256 neurons x 64 frames
+
+template <bool DBG, bool TL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_predict_tc2(const TcParams p) {
     extern __shared__ unsigned char smem_dyn[];
-    __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_d, bar_state, bar_y, bar_yready;
+    __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_d, bar_tA, bar_tB, bar_fA, bar_fB, bar_y, bar_yready;
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t s_key[2][FT];        // noise keys of (frame pair of the 128-frame tile, step)
 
     const TcGeom gm = tc_geom(p.N, p.n_in);
     const int S = gm.S, C = gm.C, J = S >> 1;
+    const int H1 = J == 2 ? 4 : 0;
     unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     unsigned char *st_hi = base, *ring = base + (size_t)2 * C * STILE;
     const uint32_t lo_delta = (uint32_t)C * STILE;
@@ -763,14 +861,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_p
     const int tile0 = pair0 + (int)rank * FT;               // first frame owned by this CTA
     const int g = p.group_ids ? p.group_ids[min(pair0, p.B - 1)] : 0;
     const int P = p.N + p.n_in;
-    const int n_epi = 8 * J + 2;                            // arriving warps per CTA and step
+    const bool y128 = p.n_out <= 8;                         // readout as an M = 128 UMMA (64 frames per CTA)
+    const bool tl0 = TL && p.timeline && blockIdx.x == 0;
 
     if (tid == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(&bar_full[i], rank == 0 ? 2 : 1); mbar_init(&bar_empty[i], 1); }
         mbar_init(&bar_d, 1);
         mbar_init(&bar_y, 1);
         mbar_init(&bar_yready, 4);
-        mbar_init(&bar_state, 2 * n_epi);
+        mbar_init(&bar_tA, 1);                               // poster (+ GROUP_BYTES of st.async data)
+        mbar_init(&bar_tB, 1 + 2);                           // poster + this CTA's frame warps (+ data)
+        mbar_init(&bar_fA, 1);                               // CTA 1's tA / tB forwarded to the issuer
+        mbar_init(&bar_fB, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 3) {
@@ -778,12 +880,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_p
                      ::"r"(smem_u32(&s_tmem)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < 2 * C * STILE / 16; i += TC_THREADS)
+    for (int i = tid; i < 2 * C * STILE / 16; i += TC2_THREADS)
         reinterpret_cast<uint4 *>(base)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     if (p.x0) {
         const float xscale = ldexpf(1.0f, SX);
-        for (int i = tid; i < FT * p.N; i += TC_THREADS) {
+        for (int i = tid; i < FT * p.N; i += TC2_THREADS) {
             const int f = i / p.N, n = i - f * p.N, b = tile0 + f;
             if (b < p.B)
                 split_sts(smem_u32(st_hi) + (n >> 6) * STILE + mn128_off(n & 63, f), lo_delta,
@@ -796,12 +898,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_p
     cluster_sync_all();                   // peer barriers, TMEM and state tiles exist before any remote op
     tc_fence_after();
     const uint32_t tmem = s_tmem;
-    const uint32_t r_state = mapa_u32(smem_u32(&bar_state), 0), r_yready = mapa_u32(smem_u32(&bar_yready), 0);
-
-    // Ring schedule of one step, identical in producer, relay and issuer.  Phase A: state chunks
-    // of accumulator group 0 -- each item also carries the readout half-tile(s) of its chunk (and,
-    // with chunk 0, of the aug chunk); phase B: state chunks of the other groups; phase C: aug chunk.
-    // The last step (it == T) only needs the readout, i.e. phase A without the weight tiles.
+    const uint32_t r_yready = mapa_u32(smem_u32(&bar_yready), 0);
 
     if (warp < 2) {
         // ============ frame warps: thread = own frame; inputs, readout, noise keys ============
@@ -847,14 +944,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_p
         write_inputs();
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(r_state);
+        if (lane == 0) mbar_arrive(&bar_tB);
         for (int it = 0; it <= p.T; ++it) {
             if (it < p.T) load_row(it + 1);
             mbar_wait<true>(&bar_y, it & 1);
             tc_fence_after();
             write_keys(it + 1);           // every epilogue warp has finished step it-1 by now
             uint32_t yv[16];
-            tmem_ld16(lane_base + YCOL, yv);
+            if (y128) {
+                // M = 128 pair UMMA: lanes 0..63 = this CTA's frames, columns = outputs 0..7
+                uint32_t y8[8];
+                tmem_ld8(lane_base + YCOL2, y8);
+#pragma unroll
+                for (int o = 0; o < 8; ++o) { yv[o] = y8[o]; yv[o + 8] = 0u; }
+            } else {
+                tmem_ld16(lane_base + YCOL2, yv);
+            }
             tmem_ld_wait();
             float y[16];
 #pragma unroll
@@ -863,6 +968,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_p
                 if (it == 0) y[o] = (p.y0 && live && o < p.n_out) ? p.y0[(size_t)b * p.n_out + o] : 0.f;
                 if (o >= p.n_out) y[o] = 0.f;
             }
+            if (it < p.T) {               // feedback first: the issuer is waiting for it
+#pragma unroll
+                for (int o = 0; o < 16; ++o) split_sts(aug_addr(gm.YO + o), lo_delta, p.feedback ? y[o] * sy : 0.f);
+                fence_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(r_yready);
+            }
             if (it >= 1 && it - 1 >= p.transient && live) {
                 float *dst = p.y_out + ((size_t)b * (p.T - p.transient) + (it - 1 - p.transient)) * p.n_out;
 #pragma unroll
@@ -870,168 +983,216 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) esn_p
                     if (o < p.n_out) dst[o] = (y[o] - p.t_shift[o]) / p.t_scale[o];
             }
             if (it == p.T) break;
-#pragma unroll
-            for (int o = 0; o < 16; ++o) split_sts(aug_addr(gm.YO + o), lo_delta, p.feedback ? y[o] * sy : 0.f);
-            fence_async_smem();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(r_yready);
             mbar_wait<true>(&bar_d, it & 1);
             write_inputs();
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(r_state);
+            if (lane == 0) mbar_arrive(&bar_tB);
         }
     } else if (warp == 2) {
         // ============ producer: this CTA's half of every tile, every step ============
-        const unsigned char *wimg = p.weights;
-        const unsigned char *yimg = p.readouts + (size_t)g * gm.readout_bytes + rank * 1024;   // 8 of 16 output rows
-        const bool lead = elect_one();
-        uint32_t item = 0;
-        // weight tile (slab s, chunk c, half h) and/or readout half-tiles into the next slot
-        auto fetch = [&](int s, int c, int h, bool w, bool y) {
-            const int slot = item % NST;
-            mbar_wait<false>(&bar_empty[slot], ((item / NST) & 1) ^ 1);
-            if (lead) {
+        if (elect_one()) {
+            const unsigned char *wimg = p.weights;
+            const unsigned char *yimg = p.readouts + (size_t)g * gm.readout_bytes + rank * 1024;   // 8 of 16 output rows
+            uint32_t item = 0;
+            // weight tile (slab s, chunk c, half h) and/or readout half-tiles into the next slot
+            auto fetch = [&](int s, int c, int h, bool w, bool y) {
+                const int slot = item % NST;
+                mbar_wait<false>(&bar_empty[slot], ((item / NST) & 1) ^ 1);
                 unsigned char *dst = ring + (size_t)slot * SLOT2;
-                const bool yaug = y && c == 0;
+                const bool yaug = y && c == H1;
                 mbar_expect_tx(&bar_full[slot], (w ? SLOT : 0) + (y ? 1024 : 0) + (yaug ? 1024 : 0));
                 if (w) bulk_g2s(dst, wimg + ((size_t)(s * C + c) * 2 + h) * SLOT, SLOT, &bar_full[slot]);
                 if (y) bulk_g2s(dst + SLOT, yimg + (size_t)(c * 2 + h) * YTILE, 1024, &bar_full[slot]);
                 if (yaug) bulk_g2s(dst + SLOT + 1024, yimg + (size_t)((C - 1) * 2 + h) * YTILE, 1024, &bar_full[slot]);
-            }
-            ++item;
-        };
-        for (int it = 0; it <= p.T; ++it) {
-            const bool last = it == p.T;
-            for (int c = 0; c < C - 1; ++c)
-                for (int h = 0; h < 2; ++h) fetch((int)rank, c, h, !last, true);
-            if (last) break;
-            for (int j = 1; j < J; ++j)
+                ++item;
+            };
+            for (int it = 0; it <= p.T; ++it) {
+                const bool last = it == p.T;
                 for (int c = 0; c < C - 1; ++c)
-                    for (int h = 0; h < 2; ++h) fetch(2 * j + (int)rank, c, h, true, false);
-            for (int j = 0; j < J; ++j)
-                for (int h = 0; h < 2; ++h) fetch(2 * j + (int)rank, C - 1, h, true, false);
+                    for (int h = 0; h < 2; ++h) fetch((int)rank, c, h, !last, true);
+                if (last) break;
+                for (int j = 1; j < J; ++j)
+                    for (int c = 0; c < C - 1; ++c)
+                        for (int h = 0; h < 2; ++h) fetch(2 * j + (int)rank, c, h, true, false);
+                for (int j = 0; j < J; ++j)
+                    for (int h = 0; h < 2; ++h) fetch(2 * j + (int)rank, C - 1, h, true, false);
+            }
         }
     } else if (warp == 3 && rank == 1) {
         // ============ relay: tell the issuer in CTA 0 that this CTA's half has landed ============
-        const bool lead = elect_one();
-        const uint32_t total = (uint32_t)p.T * (2 * J * C) + 2 * (C - 1);
-        for (uint32_t item = 0; item < total; ++item) {
-            const int slot = item % NST;
-            mbar_wait<false>(&bar_full[slot], (item / NST) & 1);
-            if (lead) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&bar_full[slot]), 0));
+        if (elect_one()) {
+            const uint32_t total = (uint32_t)p.T * (2 * J * C) + 2 * (C - 1);
+            uint32_t r_full[NST];
+#pragma unroll
+            for (int i = 0; i < NST; ++i) r_full[i] = mapa_u32(smem_u32(&bar_full[i]), 0);
+            for (uint32_t item = 0; item < total; ++item) {
+                const int slot = item % NST;
+                mbar_wait<false>(&bar_full[slot], (item / NST) & 1);
+                mbar_arrive_cluster_relaxed(r_full[slot]);
+            }
         }
     } else if (warp == 3) {
         // ============ MMA issuer (CTA 0): one thread drives both tensor cores ============
-        const bool lead = elect_one();
-        // state tile is MN-major: B operand of the main chain, A operand of the readout chain
-        const uint32_t id_main = umma_idesc_major(256, PF, 0, 1), id_y = umma_idesc_major(256, 16, 1, 0);
-        const uint32_t hi0 = desc_lo_mn(smem_u32(st_hi)), ring0 = smem_u32(ring);
-        const uint32_t lod = lo_delta >> 4;
-        const bool stamp = p.timeline && blockIdx.x == 0 && lane == 0;
-        long long *trace = (p.timeline && blockIdx.x == 0 && lane == 0) ? p.timeline + (size_t)(p.T + 1) * 8 : nullptr;
-        int tr_i = -1;
-        uint32_t item = 0;
-        // three MMAs per k-step for a hi tile (x_hi, x_lo) and one for a lo tile (x_hi)
-        auto mmas = [&](bool readout, uint32_t d, uint32_t w, uint32_t x, int h, int ks, bool first) {
-            const uint32_t idesc = readout ? id_y : id_main;
+        if (elect_one()) {
+            // state tile is MN-major: B operand of the main chain, A operand of the readout chain
+            const uint32_t id_main = umma_idesc_major(256, PF, 0, 1), id_y = umma_idesc_major(y128 ? 128 : 256, 16, 1, 0);
+            const uint32_t hi0 = desc_lo_mn(smem_u32(st_hi)), ring0 = desc_lo(smem_u32(ring));
+            const uint32_t lod = lo_delta >> 4;
+            const uint32_t xaug = hi0 + (C - 1) * (STILE >> 4), dy = tmem + YCOL2;
+            long long *trace = tl0 ? p.timeline + (size_t)(p.T + 1) * 8 : nullptr;
+            int tr_i = -1;
+            uint32_t item = 0;
+            // hi weight tile: x_hi and x_lo against it (2 MMAs per k-step); lo weight tile: x_hi only.
+            // weights K-major: 16 k = 32 B; state MN-major: 16 k = two 1024-byte atoms.
+            auto main_hi = [&](uint32_t d, uint32_t w, uint32_t x, int ks, bool first) {
 #pragma unroll 4
-            for (int kk = 0; kk < ks; ++kk) {
-                // weights K-major: 16 k = 32 B; state MN-major: 16 k = two 1024-byte atoms
-                const uint32_t wk = w + kk * 2, xk = x + kk * 128;
-                const uint32_t acc = (first && kk == 0) ? 0u : 1u;
-                if (h == 0) {
-                    umma2_f16(d, readout ? xk : wk, readout ? wk : xk, idesc, acc);
-                    umma2_f16(d, readout ? xk + lod : wk, readout ? wk : xk + lod, idesc, 1u);
-                } else {
-                    umma2_f16(d, readout ? xk : wk, readout ? wk : xk, idesc, 1u);
+                for (int kk = 0; kk < ks; ++kk) {
+                    umma2_f16(d, w + kk * 2, x + kk * 128, id_main, (first && kk == 0) ? 0u : 1u);
+                    umma2_f16(d, w + kk * 2, x + kk * 128 + lod, id_main, 1u);
                 }
-            }
-        };
-        auto consume = [&](int j, int c, int h, bool w, bool y) {
-            const int slot = item % NST;
-            mbar_wait<false>(&bar_full[slot], (item / NST) & 1);   // bulk-copy data only: no cluster acquire needed
-            if (trace && tr_i >= 0 && tr_i < 64) trace[tr_i * 4 + 2] = clock64();
-            tc_fence_after();
-            if (lead) {
-                const uint32_t sl = desc_lo(ring0 + slot * SLOT2);
+            };
+            auto main_lo = [&](uint32_t d, uint32_t w, uint32_t x, int ks) {
+#pragma unroll 4
+                for (int kk = 0; kk < ks; ++kk) umma2_f16(d, w + kk * 2, x + kk * 128, id_main, 1u);
+            };
+            auto y_hi = [&](uint32_t w, uint32_t x, int ks, bool first) {
+#pragma unroll 4
+                for (int kk = 0; kk < ks; ++kk) {
+                    umma2_f16(dy, x + kk * 128, w + kk * 2, id_y, (first && kk == 0) ? 0u : 1u);
+                    umma2_f16(dy, x + kk * 128 + lod, w + kk * 2, id_y, 1u);
+                }
+            };
+            auto y_lo = [&](uint32_t w, uint32_t x, int ks) {
+#pragma unroll 4
+                for (int kk = 0; kk < ks; ++kk) umma2_f16(dy, x + kk * 128, w + kk * 2, id_y, 1u);
+            };
+            // one state chunk = two ring items (hi tile, lo tile), each with its readout half-tiles
+            auto chunk = [&](uint32_t d, int c, bool w, bool y) {
                 const uint32_t x = hi0 + c * (STILE >> 4);
-                if (w) mmas(false, tmem + j * PF, sl, x, h, c == C - 1 ? gm.kaug : 4, c == 0 && h == 0);
-                if (y) {
-                    mmas(true, tmem + YCOL, sl + (SLOT >> 4), x, h, 4, c == 0 && h == 0);
-                    if (c == 0)       // the aug chunk's share of the readout (u_{t-1} columns)
-                        mmas(true, tmem + YCOL, sl + ((SLOT + 1024) >> 4), hi0 + (C - 1) * (STILE >> 4), h, gm.YO / 16, false);
+                const int ks = c == C - 1 ? gm.kaug : 4;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int slot = item % NST;
+                    mbar_wait<false>(&bar_full[slot], (item / NST) & 1);   // bulk-copy data only: no cluster acquire needed
+                    if (TL && trace && tr_i >= 0 && tr_i < 64) trace[tr_i * 4 + 2] = clock64();
+                    tc_fence_after();
+                    const uint32_t sl = ring0 + slot * (SLOT2 >> 4);
+                    if (h == 0) {
+                        if (w) main_hi(d, sl, x, ks, c == 0);
+                        if (y) {
+                            y_hi(sl + (SLOT >> 4), x, 4, c == 0);
+                            if (c == H1) y_hi(sl + ((SLOT + 1024) >> 4), xaug, gm.YO / 16, false);
+                        }
+                    } else {
+                        if (w) main_lo(d, sl, x, ks);
+                        if (y) {
+                            y_lo(sl + (SLOT >> 4), x, 4);
+                            if (c == H1) y_lo(sl + ((SLOT + 1024) >> 4), xaug, gm.YO / 16);
+                        }
+                    }
+                    umma2_commit_pair(&bar_empty[slot]);
+                    if (TL && trace && tr_i >= 0 && tr_i < 64) trace[tr_i * 4 + 3] = clock64();
+                    if (TL && tr_i >= 0) ++tr_i;
+                    ++item;
                 }
-                umma2_commit_pair(&bar_empty[slot]);
-            }
-            __syncwarp();
-            if (trace && tr_i >= 0 && tr_i < 64) trace[tr_i * 4 + 3] = clock64();
-            if (tr_i >= 0) ++tr_i;
-            ++item;
-        };
-        for (int it = 0; it <= p.T; ++it) {
-            const bool last = it == p.T;
-            tr_i = (it == 200) ? 0 : -1;
-            if (stamp) p.timeline[it * 8 + 0] = clock64();
-            mbar_wait_cluster<false>(&bar_state, it & 1);
-            tc_fence_after();
-            if (stamp) p.timeline[it * 8 + 1] = clock64();
-            for (int c = 0; c < C - 1; ++c)
-                for (int h = 0; h < 2; ++h) consume(0, c, h, !last, true);
-            if (lead) umma2_commit_pair(&bar_y);
-            __syncwarp();
-            if (last) break;
-            for (int j = 1; j < J; ++j)
-                for (int c = 0; c < C - 1; ++c)
-                    for (int h = 0; h < 2; ++h) consume(j, c, h, true, false);
-            if (stamp) p.timeline[it * 8 + 2] = clock64();
-            mbar_wait_cluster<false>(&bar_yready, it & 1);
-            tc_fence_after();
-            for (int j = 0; j < J; ++j)
-                for (int h = 0; h < 2; ++h) consume(j, C - 1, h, true, false);
-            if (lead) umma2_commit_pair(&bar_d);
-            __syncwarp();
-            if (stamp) p.timeline[it * 8 + 3] = clock64();
-        }
-    } else if (warp >= 4) {
-        // ============ epilogue: TMEM -> tanh -> noise -> fp16 hi/lo -> owner CTA's state tile ============
-        const int e = warp - 4, q = warp & 3, cg = e >> 2, j = cg >> 1, fh = cg & 1;
-        if (j < J) {
-            const int n = 256 * j + 128 * (int)rank + q * 32 + lane;   // neuron (TMEM lane of this CTA)
-            const bool n_ok = n < p.N;
-            const int k = n & 63, kx = k & 7;
-            const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + j * PF + fh * FT;
-            const uint32_t nmul = (uint32_t)n * 0xC2B2AE35U;
-            // row k of chunk n>>6 in the state tile of the CTA that owns frames fh*64 .. fh*64+63
-            // (cluster address; may be this CTA): 128 bytes = this neuron's 64 frames
-            const uint32_t rowaddr = mapa_u32(smem_u32(st_hi), (uint32_t)fh) + (n >> 6) * STILE + (k >> 3) * 1024 + kx * 128;
-            const int fbase = pair0 + fh * FT;
-            const bool full_tile = fbase + FT <= p.B;
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(r_state);
-            for (int it = 0; it < p.T; ++it) {
-                mbar_wait<true>(&bar_d, it & 1);
+            };
+            for (int it = 0; it <= p.T; ++it) {
+                const bool last = it == p.T;
+                if (TL) tr_i = (it == 200) ? 0 : -1;
+                if (tl0) p.timeline[it * 8 + 0] = clock64();
+                if (H1) {
+                    mbar_wait<false>(&bar_tA, it & 1);
+                    mbar_wait_cluster<false>(&bar_fA, it & 1);
+                    fence_async_smem();
+                    tc_fence_after();
+                    if (tl0) p.timeline[it * 8 + 1] = clock64();
+                    for (int c = 0; c < H1; ++c) chunk(tmem, c, !last, true);
+                }
+                if (tl0) p.timeline[it * 8 + 2] = clock64();
+                mbar_wait<false>(&bar_tB, it & 1);
+                mbar_wait_cluster<false>(&bar_fB, it & 1);
+                fence_async_smem();
                 tc_fence_after();
-                if (p.timeline && blockIdx.x == 0 && warp == 4 && lane == 0) p.timeline[it * 8 + 4] = clock64();
-                const uint32_t *keys = s_key[it & 1] + fh * (FT / 2);
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t v[32];
-                    tmem_ld32(lane_base + half * 32, v);
-                    tmem_ld_wait();
-                    const bool big = tc2_epilogue_half<DBG, false>(p, v, it, n, n_ok, fbase, half, full_tile, keys, nmul,
-                                                                   rowaddr, kx, lo_delta, P);
-                    if (__any_sync(0xffffffffu, big))
-                        tc2_epilogue_half<DBG, true>(p, v, it, n, n_ok, fbase, half, full_tile, keys, nmul, rowaddr, kx,
-                                                     lo_delta, P);
+                if (tl0) p.timeline[it * 8 + 3] = clock64();
+                for (int c = H1; c < C - 1; ++c) chunk(tmem, c, !last, true);
+                umma2_commit_pair(&bar_y);
+                if (last) break;
+                for (int j = 1; j < J; ++j)
+                    for (int c = 0; c < C - 1; ++c) chunk(tmem + j * PF, c, true, false);
+                if (tl0) p.timeline[it * 8 + 7] = clock64();
+                mbar_wait_cluster<false>(&bar_yready, it & 1);
+                tc_fence_after();
+                for (int j = 0; j < J; ++j) chunk(tmem + j * PF, C - 1, true, false);
+                umma2_commit_pair(&bar_d);
+            }
+        }
+    } else if (warp == 20) {
+        // ============ poster / forwarder: expected bytes of every state hand-off ============
+        if (elect_one()) {
+            const uint32_t bytesA = H1 ? GROUP_BYTES : 0u, bytesB = (uint32_t)(J - (H1 ? 1 : 0)) * GROUP_BYTES;
+            const uint32_t r_fA = mapa_u32(smem_u32(&bar_fA), 0), r_fB = mapa_u32(smem_u32(&bar_fB), 0);
+            for (int it = 0; it <= p.T; ++it) {
+                // phase it of tA / tB: the initial state (it = 0, no data) or the epilogue of step it-1
+                if (H1) { if (it == 0) mbar_arrive(&bar_tA); else mbar_expect_tx(&bar_tA, bytesA); }
+                if (it == 0) mbar_arrive(&bar_tB); else mbar_expect_tx(&bar_tB, bytesB);
+                if (rank == 1) {
+                    if (H1) {
+                        mbar_wait<false>(&bar_tA, it & 1);
+                        fence_async_smem();
+                        mbar_arrive_cluster_relaxed(r_fA);
+                    }
+                    mbar_wait<false>(&bar_tB, it & 1);
+                    fence_async_smem();
+                    mbar_arrive_cluster_relaxed(r_fB);
+                } else {
+                    if (H1) mbar_wait<true>(&bar_tA, it & 1);     // do not post phase it+1 before phase it is over
+                    mbar_wait<true>(&bar_tB, it & 1);
                 }
-                if (p.timeline && blockIdx.x == 0 && warp == 4 && lane == 0) p.timeline[it * 8 + 6] = clock64();
-                asm volatile("fence.proxy.async;" ::: "memory");
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(r_state);
-                if (p.timeline && blockIdx.x == 0 && warp == 4 && lane == 0) p.timeline[it * 8 + 5] = clock64();
+            }
+        }
+    } else {
+        // ============ epilogue: TMEM -> tanh -> noise -> fp16 hi/lo -> owner CTA's state tile ============
+        // warp (q, fq): TMEM lane quarter q (32 neurons of every group), frames 32 fq .. 32 fq + 31 of
+        // the pair's 128 (owner CTA fq >> 1); groups in order.
+        const int e = warp - 4, q = warp & 3, fq = e >> 2, fh = fq >> 1;
+        const int nl = 128 * (int)rank + q * 32 + lane;             // neuron within its group
+        const uint32_t lane_tm = tmem + ((uint32_t)(q * 32) << 16) + fq * 32;
+        const uint32_t own = mapa_u32(smem_u32(st_hi), (uint32_t)fh);
+        const uint32_t own_tA = mapa_u32(smem_u32(&bar_tA), (uint32_t)fh), own_tB = mapa_u32(smem_u32(&bar_tB), (uint32_t)fh);
+        const int fbase = pair0 + fq * 32;
+        const int kx = nl & 7;                                     // (n & 63) & 7 for every group
+        const float amp = p.noise_amp;
+        const bool st4 = tl0 && warp == 4 && lane == 0;
+        for (int it = 0; it < p.T; ++it) {
+            mbar_wait<true>(&bar_d, it & 1);
+            tc_fence_after();
+            if (st4) p.timeline[it * 8 + 4] = clock64();
+            const uint32_t *keys = s_key[it & 1] + fq * 16;
+#pragma unroll 1
+            for (int j = 0; j < J; ++j) {
+                const int n = 256 * j + nl;
+                const bool n_ok = n < p.N;
+                EpiConst ec;
+                ec.dsc = n_ok ? ldexpf(1.0f, -(SX + SW)) : 0.f;
+                ec.ampf = n_ok ? amp * (float)(1 << SX) : 0.f;
+                ec.amp16s = ec.ampf * (1.0f / 65536.0f);
+                ec.ampoffs = 0.5f * ec.ampf;
+                const uint32_t nmul = (uint32_t)n * 0xC2B2AE35U;
+                const int k = n & 63;
+                const uint32_t rowaddr = own + (n >> 6) * STILE + (k >> 3) * 1024 + kx * 128;
+                const uint32_t mbar = (H1 && j == 0) ? own_tA : own_tB;
+                uint32_t v[32];
+                tmem_ld32(lane_tm + (uint32_t)(j * PF), v);
+                tmem_ld_wait();
+                float m = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) m = fmaxf(m, fmaxf(fabsf(__uint_as_float(v[i])), fabsf(__uint_as_float(v[i + 1]))));
+                if (!__any_sync(0xffffffffu, m * ec.dsc > 3.0f))
+                    tc2_epilogue32<DBG, false>(p, v, it, n, n_ok, fbase, keys, nmul, rowaddr, (fq & 1) * 4, kx, lo_delta, P, ec, mbar);
+                else
+                    tc2_epilogue32<DBG, true>(p, v, it, n, n_ok, fbase, keys, nmul, rowaddr, (fq & 1) * 4, kx, lo_delta, P, ec, mbar);
+                if (st4) p.timeline[it * 8 + 5 + j] = clock64();
             }
         }
     }
@@ -1097,13 +1258,15 @@ extern "C" int esn_tc_predict(const esn_tc_predict_args *a, void *stream) {
         // CTA-pair kernel (cta_group::2): 128 frames per 2-CTA cluster
         const int grid2 = 2 * ((a->B + PF - 1) / PF);
         const size_t smem = (size_t)2 * gm.C * STILE + (size_t)NST * SLOT2 + 1024;
-        if (dbg) {
-            ESN_CUDA_TRY(cudaFuncSetAttribute(esn_predict_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            esn_predict_tc2<true><<<grid2, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
-        } else {
-            ESN_CUDA_TRY(cudaFuncSetAttribute(esn_predict_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            esn_predict_tc2<false><<<grid2, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
-        }
+        auto launch = [&](auto kern) -> int {
+            ESN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid2, TC2_THREADS, smem, (cudaStream_t)stream>>>(p);
+            return 0;
+        };
+        int rc;
+        if (dbg) rc = a->timeline ? launch(esn_predict_tc2<true, true>) : launch(esn_predict_tc2<true, false>);
+        else rc = a->timeline ? launch(esn_predict_tc2<false, true>) : launch(esn_predict_tc2<false, false>);
+        if (rc) return rc;
         return esn_launch_status();
     }
     const int grid = (a->B + FT - 1) / FT;

@@ -2,9 +2,9 @@
 """Per-step phase timing of the tensor-core recurrence kernel (CTA 0), from the
 kernel's own SM-clock stamps (esn_tc_predict_args.timeline).  Run on the GPU box:
     python profiles/tc_timeline.py [frames]
-Columns (cycles): wait_state = MMA thread idle until the state tile is ready;
-issue_main = issuing readout + main chain (ring-bound when the data is late);
-issue_aug = waiting for y + last chunk; epilogue = D ready -> state written."""
+Rows (cycles): the issuer's waits for the two state barriers (sA: chunks 0-3 rewritten,
+sB: everything rewritten), its issue phases (ring-bound when the data is late) and the two
+halves of the epilogue (warp 4)."""
 import os
 import sys
 
@@ -32,16 +32,17 @@ for _ in range(2):
 torch.cuda.synchronize()
 full = tl.cpu().numpy()
 t = full[50:500]
-wait_state = t[:, 1] - t[:, 0]
-issue_main = t[:, 2] - t[:, 1]
-issue_aug = t[:, 3] - t[:, 2]
-epi = t[:, 5] - t[:, 4]
-d_to_epi = t[:, 4] - t[:, 3]
 step = t[1:, 0] - t[:-1, 0]
-epi_math = t[:, 6] - t[:, 4]
-for name, v in (("step", step), ("epilogue math+stores", epi_math), ("epilogue fence+arrive", t[:, 5] - t[:, 6]), ("wait_state", wait_state), ("issue_main", issue_main), ("issue_aug", issue_aug),
-                ("issued->D ready", d_to_epi), ("epilogue(warp4)", epi)):
-    print(f"{name:18s} mean {v.mean():9.0f}  p10 {np.percentile(v, 10):9.0f}  p90 {np.percentile(v, 90):9.0f} cycles")
+rows = (("step", step),
+        ("wait sA (group-0 state)", t[:, 1] - t[:, 0]),
+        ("phase 1 issue (g0 c0-3 + y)", t[:, 2] - t[:, 1]),
+        ("wait sB (all state)", t[:, 3] - t[:, 2]),
+        ("phase 2 issue (g0 c4-7 + y, g1)", t[:, 7] - t[:, 3]),
+        ("wait y + aug -> epilogue start", t[:, 4] - t[:, 7]),
+        ("epilogue group 0 (+arrive)", t[:, 5] - t[:, 4]),
+        ("epilogue group 1 (+arrive)", t[:, 6] - t[:, 5]))
+for name, v in rows:
+    print(f"{name:32s} mean {v.mean():9.0f}  p10 {np.percentile(v, 10):9.0f}  p90 {np.percentile(v, 90):9.0f} cycles")
 
 tr = full[T + 1:].reshape(-1, 4)[:56]
 if tr[:, 2].any():
