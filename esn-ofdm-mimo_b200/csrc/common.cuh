@@ -15,11 +15,11 @@ static inline int esn_launch_status() {
     return e == cudaSuccess ? 0 : (int)e;
 }
 
-// Counter-hash state noise.  One 32-bit hash serves the two frames of a pair
-// (frame >> 1): the even frame takes the low 16 bits, the odd frame the high 16, so
-// a thread that owns one neuron and walks over frames pays one hash per two values.
-// uniform = bits * 2^-16 in [0,1).  The same integer recipe is restated in
-// esn_b200/noise.py so tests can feed the oracle the identical stream.
+// Counter-hash state noise.  One key per (frame, time step); one 32-bit hash serves the two
+// neurons of a pair (neuron >> 1): the even neuron takes the low 16 bits, the odd neuron the high
+// 16, so a thread that owns one frame and walks over neurons pays one hash per two values.
+// uniform = bits * 2^-16 in [0,1).  The same integer recipe is restated in esn_b200/noise.py so
+// tests can feed the oracle the identical stream.
 __host__ __device__ __forceinline__ uint32_t esn_mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU;
     x ^= x >> 15; x *= 0x846ca68bU;
@@ -27,15 +27,15 @@ __host__ __device__ __forceinline__ uint32_t esn_mix32(uint32_t x) {
     return x;
 }
 __host__ __device__ __forceinline__ uint32_t esn_noise_key(uint64_t seed, uint32_t frame, uint32_t row) {
-    uint32_t k = esn_mix32((uint32_t)seed + 0x9E3779B9U * (frame >> 1));
+    uint32_t k = esn_mix32((uint32_t)seed + 0x9E3779B9U * frame);
     return esn_mix32(k ^ (row * 0x85EBCA6BU + (uint32_t)(seed >> 32)));
 }
 __host__ __device__ __forceinline__ uint32_t esn_noise_bits(uint32_t key, uint32_t neuron) {
-    return esn_mix32(key + neuron * 0xC2B2AE35U);        // low half: even frame, high half: odd frame
+    return esn_mix32(key + (neuron >> 1) * 0xC2B2AE35U);   // low half: even neuron, high half: odd neuron
 }
-__host__ __device__ __forceinline__ float esn_noise_uniform(uint32_t key, uint32_t neuron, uint32_t frame) {
+__host__ __device__ __forceinline__ float esn_noise_uniform(uint32_t key, uint32_t neuron) {
     const uint32_t h = esn_noise_bits(key, neuron);
-    return (float)((frame & 1u) ? (h >> 16) : (h & 0xFFFFu)) * (1.0f / 65536.0f);
+    return (float)((neuron & 1u) ? (h >> 16) : (h & 0xFFFFu)) * (1.0f / 65536.0f);
 }
 
 template <typename T> struct esn_cplx { T re, im; };

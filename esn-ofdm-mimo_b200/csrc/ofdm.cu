@@ -367,7 +367,7 @@ __global__ void synth_frames_kernel(const uint8_t *__restrict__ tx_idx, const T 
                 const size_t o = (((size_t)b * L + t) * N_r + rx) * 2;
                 nr = noise[o]; ni = noise[o + 1];
             } else {
-                const uint32_t key = esn_noise_key(seed ^ 0xA5A5A5A5ULL, (uint32_t)(2 * b), (uint32_t)t);
+                const uint32_t key = esn_noise_key(seed ^ 0xA5A5A5A5ULL, (uint32_t)b, (uint32_t)t);
                 const uint32_t h1 = esn_mix32(key + (uint32_t)rx * 0xC2B2AE35U);
                 const uint32_t h2 = esn_mix32(h1 ^ 0x68E31DA4U);
                 const T u1 = ((T)(h1 >> 8) + (T)0.5) * (T)(1.0 / 16777216.0);
@@ -537,5 +537,5 @@ extern "C" int esn_device_info(char *name, int n, int *major, int *minor) {
 
 // Host-callable copy of the device noise stream (tests pin the numpy restatement to it).
 extern "C" float esn_noise_uniform_host(unsigned long long seed, unsigned frame, unsigned row, unsigned neuron) {
-    return esn_noise_uniform(esn_noise_key(seed, frame, row), neuron, frame);
+    return esn_noise_uniform(esn_noise_key(seed, frame, row), neuron);
 }

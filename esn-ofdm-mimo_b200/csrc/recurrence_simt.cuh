@@ -228,7 +228,7 @@ esn_recurrence_simt(const RecParams p) {
                                 if (use_noise) {
                                     T u;
                                     if (noise) u = noise[((size_t)b * noise_rows + nrow) * N + nn];
-                                    else u = (T)esn_noise_uniform(esn_noise_key(p.seed, (uint32_t)b, (uint32_t)nrow), (uint32_t)nn, (uint32_t)b);
+                                    else u = (T)esn_noise_uniform(esn_noise_key(p.seed, (uint32_t)b, (uint32_t)nrow), (uint32_t)nn);
                                     x += namp * (u - (T)0.5);
                                 }
                                 if (ext) ext[((size_t)b * p.T + n) * P + nn] = x;

@@ -47,7 +47,7 @@ constexpr int YCOL = 256;              // TMEM column of the readout accumulator
 
 struct TcGeom {
     int S, C, UW, YO, ca, kaug;        // slabs, 64-wide K chunks, input block width, y column offset, aug chunk, k-steps in aug chunk
-    size_t weight_bytes, readout_bytes;
+    size_t weight_bytes, readout_tile_bytes, readout_bytes;   // readout image = UMMA tiles + fp32 input-block table [16][24]
 };
 
 __host__ __device__ inline TcGeom tc_geom(int N, int n_in) {
@@ -59,7 +59,8 @@ __host__ __device__ inline TcGeom tc_geom(int N, int n_in) {
     g.ca = 2 * g.S;
     g.kaug = g.YO / 16 + 1;
     g.weight_bytes = (size_t)g.S * g.C * 2 * SLOT;
-    g.readout_bytes = (size_t)g.C * 2 * YTILE;
+    g.readout_tile_bytes = (size_t)g.C * 2 * YTILE;
+    g.readout_bytes = g.readout_tile_bytes + 16 * 24 * sizeof(float);
     return g;
 }
 
@@ -138,6 +139,13 @@ __global__ void tc_prepare_readout_kernel(const double *__restrict__ W_out, int 
         }
         unsigned char *tile = out + ((size_t)(k >> 6) * 2) * YTILE;
         store_split(tile, tile + YTILE, sw128_off(o, k & 63), v);
+    }
+    // input block of the readout in fp32, same units as the tiles (the pair kernel adds W_out_u u_{t-1}
+    // on the CUDA cores): tab[o][i] = W_out[o][N + i] 2^(SX + so - su)
+    float *tab = reinterpret_cast<float *>(out + gm.readout_tile_bytes);
+    for (int e = threadIdx.x; e < 16 * 24; e += blockDim.x) {
+        const int o = e / 24, i = e % 24;
+        tab[e] = (o < n_out && i < n_in) ? (float)ldexp(w[(size_t)o * P + N + i], SX + so - su) : 0.f;
     }
 }
 
@@ -525,7 +533,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p
             const float dscale = ldexpf(1.0f, -(SX + SW)), xscale = ldexpf(1.0f, SX);
             const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + s * FT;
             const bool use_noise = p.noise_amp != 0.f;
-            const uint32_t nmul = (uint32_t)n * 0xC2B2AE35U;
+            const uint32_t nmul = (uint32_t)(n >> 1) * 0xC2B2AE35U;
             const uint32_t tile = smem_u32(st_hi) + (n >> 6) * STILE + (k & 7) * 2;
             uint32_t goff[8];                              // row-in-group + swizzled granule offsets
 #pragma unroll
@@ -554,7 +562,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p
                                 u = (b < p.B && n_ok) ? p.noise[((size_t)b * p.T + it) * p.N + n] : 0.5f;
                             } else {
                                 const uint32_t hb = esn_mix32(keys[f] + nmul);
-                                u = (float)((f & 1) ? (hb >> 16) : (hb & 0xFFFFu)) * (1.0f / 65536.0f);
+                                u = (float)((n & 1) ? (hb >> 16) : (hb & 0xFFFFu)) * (1.0f / 65536.0f);
                             }
                             x = fmaf(u, p.noise_amp, x - 0.5f * p.noise_amp);
                         }
@@ -580,17 +588,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p
 }
 
 
-// =====================================================================================
-// Pair kernel: two CTAs of a cluster (one TPC) work as one 256-row tensor core
-// (tcgen05 cta_group::2).  The pair owns 128 frames; CTA r keeps the state tile of its
-// own 64 frames (the N-half of the B operand) and streams only ITS half of every weight
-// tile (neuron slabs 2j + r), so each SM moves half the bytes per step and each UMMA
-// does four times the work of the single-CTA kernel's (M = 256 x N = 128).  The
-// accumulator of CTA r holds its 128 neurons for all 128 frames, so the epilogue sends
-// half of the new state to the peer CTA through distributed shared memory
-// (st.shared::cluster, ~20 B/cycle, measured in profiles/probes/dsmem_store_probe.cu).
-// Barriers that collect arrivals from both CTAs live in CTA 0 (the MMA issuer).
-// =====================================================================================
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -683,8 +680,9 @@ __device__ __forceinline__ uint32_t umma_idesc_major(int M, int N, int a_mn, int
 __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr) { return (saddr >> 4) & 0x3FFF; }
 
 constexpr int PF = 2 * FT;             // frames per CTA pair
-constexpr int SLOT2 = SLOT + 2048;     // pair-kernel ring slot: weight tile + up to two 1 KB readout half-tiles
-constexpr int YCOL2 = 256;             // TMEM column of the pair kernel's readout accumulator
+constexpr int SLOT2 = SLOT + 2048;     // pair-kernel ring slot: weight tile (128 rows) + up to 16 readout rows
+constexpr int X1ROWS = 72;             // B rows per CTA of the first X MMA (N = 144); the second takes 56 + readout rows
+constexpr int XCOL = 0, RCOL = 128, YCOL2 = 160;   // TMEM columns: X neurons [0,128), readout [128,144), Y neurons [160,288)
 
 // ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): two lanes per instruction ----
 __device__ __forceinline__ uint64_t pk2(float a, float b) {
@@ -723,52 +721,56 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr) : "memory");
 }
-
-// 16-byte asynchronous store into a (possibly remote) CTA's shared memory; the destination CTA's
-// mbarrier counts the bytes (complete_tx), so the writer needs no fence and no arrive (STAS).
-__device__ __forceinline__ void stas_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
-                                        uint32_t cluster_mbar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
-                 ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(cluster_mbar) : "memory");
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// (a, b) pre-scaled -> packed fp16 hi pair and lo pair
+__device__ __forceinline__ void split_pair(uint64_t xs, uint32_t &h, uint32_t &l) {
+    float xa, xb, la, lb;
+    un2(xs, xa, xb);
+    h = pack_h2(xa, xb);
+    const float2 back = __half22float2(*reinterpret_cast<const __half2 *>(&h));
+    un2(sub2(xs, pk2(back.x, back.y)), la, lb);
+    l = pack_h2(la, lb);
 }
 
-// Per-thread constants of the pair kernel's epilogue (zeroed for padded neurons, so that their
-// state stays exactly 0 without a select per element).
-struct EpiConst {
-    float dsc;        // 2^-(SX+SW): accumulator -> pre-activation
-    float amp16s;     // noise_amp 2^-16 2^SX : 16-bit uniform -> scaled noise
-    float ampoffs;    // noise_amp / 2 2^SX
-    float ampf;       // noise_amp 2^SX (host-noise path)
+// Per-thread constants of the pair kernel's epilogue.
+struct EpiStep {
+    uint32_t key;          // noise key of (frame, step)
+    float dsc;             // 2^-(SX+SW): accumulator -> pre-activation
+    float amp16s;          // noise_amp 2^-16 2^SX : 16-bit uniform -> scaled noise
+    float ampoffs;         // noise_amp / 2 2^SX
+    float ampf;            // noise_amp 2^SX (host-noise path)
 };
 
-// One accumulator group of an epilogue thread: v[] = accumulators of its neuron for 32 consecutive
-// frames -> [7/6] Pade tanh -> noise -> x 2^SX -> fp16 hi/lo, written as four 16-byte stores per half
-// (eight frames each) into the owner CTA's MN-major state tile.  Two frames per instruction through
-// the packed fp32x2 pipe; the 2^SX pre-scale is folded into the numerator.  FIX = true (chosen by the
+// One block of an epilogue thread: v[] = accumulators of ITS frame for the 32 consecutive neurons
+// n0 .. n0+31 -> [7/6] Pade tanh -> noise -> x 2^SX -> fp16 hi/lo, written as four 16-byte stores per
+// half into the frame's row of the K-major state tile.  Two neurons per instruction through the
+// packed fp32x2 pipe; the 2^SX pre-scale is folded into the numerator.  FIX = true (chosen by the
 // caller when some |z| > 3, rare in an echo-state reservoir) patches those elements with the exact
-// formula.  Every granule is stored exactly once: the destination barrier counts the bytes.
-template <bool DBG, bool FIX>
-__device__ __forceinline__ void tc2_epilogue32(const TcParams &p, const uint32_t (&v)[32], int it, int n, bool n_ok,
-                                               int fbase, const uint32_t *keys, uint32_t nmul, uint32_t rowaddr,
-                                               int gsel, int kx, uint32_t lo_delta, int P, const EpiConst &ec,
-                                               uint32_t mbar) {
+// formula.  PAD = block crosses the end of the reservoir (padded neurons stay exactly zero).
+template <bool DBG, bool FIX, bool PAD>
+__device__ __forceinline__ void tc2_epilogue32(const TcParams &p, const uint32_t (&v)[32], int it, int n0, int b, bool live,
+                                               uint32_t rowaddr, int fx, uint32_t lo_delta, int P, const EpiStep &es) {
     constexpr float XS = (float)(1 << SX);
     const bool use_noise = p.noise_amp != 0.f;
-    const uint64_t dsc2 = pk2(ec.dsc, ec.dsc);
-    const uint64_t n0 = pk2(XS, XS), n1 = pk2(378.0f * XS, 378.0f * XS), n2 = pk2(17325.0f * XS, 17325.0f * XS),
+    const uint64_t dsc2 = pk2(es.dsc, es.dsc);
+    const uint64_t n0c = pk2(XS, XS), n1 = pk2(378.0f * XS, 378.0f * XS), n2 = pk2(17325.0f * XS, 17325.0f * XS),
                    n3 = pk2(135135.0f * XS, 135135.0f * XS);
     const uint64_t d0 = pk2(28.0f, 28.0f), d1 = pk2(3150.0f, 3150.0f), d2 = pk2(62370.0f, 62370.0f),
                    d3 = pk2(135135.0f, 135135.0f);
-    const uint64_t amp2 = pk2(ec.amp16s, ec.amp16s), off2 = pk2(-ec.ampoffs, -ec.ampoffs);
+    const uint64_t amp2 = pk2(es.amp16s, es.amp16s), off2 = pk2(-es.ampoffs, -es.ampoffs);
+    const uint32_t hkey = es.key + (uint32_t)(n0 >> 1) * 0xC2B2AE35U;
+    const int g0 = (n0 & 63) >> 3;
 #pragma unroll
-    for (int g8 = 0; g8 < 4; ++g8) {                      // granule of 8 frames
+    for (int g8 = 0; g8 < 4; ++g8) {                      // granule of 8 neurons
         uint32_t hi2[4], lo2[4];
 #pragma unroll
-        for (int pr = 0; pr < 4; ++pr) {                  // pair of frames
-            const int jj = g8 * 8 + pr * 2;
+        for (int pr = 0; pr < 4; ++pr) {                  // pair of neurons
+            const int jj = g8 * 8 + pr * 2, n = n0 + jj;
             const uint64_t z = mul2(pk2u(v[jj], v[jj + 1]), dsc2);
             const uint64_t z2 = mul2(z, z);
-            uint64_t num = fma2(z2, n0, n1);
+            uint64_t num = fma2(z2, n0c, n1);
             num = fma2(num, z2, n2);
             num = fma2(num, z2, n3);
             uint64_t den = fma2(d0, z2, d1);
@@ -782,75 +784,83 @@ __device__ __forceinline__ void tc2_epilogue32(const TcParams &p, const uint32_t
                 if (DBG && p.noise) {
                     float u[2];
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int b = fbase + jj + e;
-                        u[e] = (b < p.B && n_ok) ? p.noise[((size_t)b * p.T + it) * p.N + n] : 0.5f;
-                    }
-                    nt = pk2(fmaf(u[0], ec.ampf, -ec.ampoffs), fmaf(u[1], ec.ampf, -ec.ampoffs));
+                    for (int e = 0; e < 2; ++e)
+                        u[e] = (live && n + e < p.N) ? p.noise[((size_t)b * p.T + it) * p.N + n + e] : 0.5f;
+                    nt = pk2(fmaf(u[0], es.ampf, -es.ampoffs), fmaf(u[1], es.ampf, -es.ampoffs));
                 } else {
-                    const uint32_t hb = esn_mix32(keys[jj >> 1] + nmul);
+                    const uint32_t hb = esn_mix32(hkey + (uint32_t)(jj >> 1) * 0xC2B2AE35U);
                     nt = fma2(pk2((float)(hb & 0xFFFFu), (float)(hb >> 16)), amp2, off2);
                 }
             }
             uint64_t xs = fma2(mul2(num, z), pk2(rcp_approx(da), rcp_approx(db)), nt);
-            if (FIX) {
+            if (FIX || PAD) {
                 float xa, xb, na, nb;
                 un2(xs, xa, xb);
                 un2(nt, na, nb);
-                if (fabsf(za) > 3.0f) xa = fmaf(tanh_large(za), n_ok ? XS : 0.f, na);
-                if (fabsf(zb) > 3.0f) xb = fmaf(tanh_large(zb), n_ok ? XS : 0.f, nb);
+                if (FIX && fabsf(za) > 3.0f) xa = fmaf(tanh_large(za), XS, na);
+                if (FIX && fabsf(zb) > 3.0f) xb = fmaf(tanh_large(zb), XS, nb);
+                if (PAD && n >= p.N) xa = 0.f;
+                if (PAD && n + 1 >= p.N) xb = 0.f;
                 xs = pk2(xa, xb);
             }
-            float xa, xb;
-            un2(xs, xa, xb);
-            if (DBG && p.ext_out && n_ok) {
-                const int b = fbase + jj;
-                if (b < p.B) p.ext_out[((size_t)b * p.T + it) * P + n] = xa * (1.0f / XS);
-                if (b + 1 < p.B) p.ext_out[((size_t)(b + 1) * p.T + it) * P + n] = xb * (1.0f / XS);
+            if (DBG && p.ext_out && live) {
+                float xa, xb;
+                un2(xs, xa, xb);
+                if (n < p.N) p.ext_out[((size_t)b * p.T + it) * P + n] = xa * (1.0f / XS);
+                if (n + 1 < p.N) p.ext_out[((size_t)b * p.T + it) * P + n + 1] = xb * (1.0f / XS);
             }
-            const uint32_t h = pack_h2(xa, xb);
-            const float2 back = __half22float2(*reinterpret_cast<const __half2 *>(&h));
-            float la, lb;
-            un2(sub2(xs, pk2(back.x, back.y)), la, lb);
-            hi2[pr] = h;
-            lo2[pr] = pack_h2(la, lb);
+            split_pair(xs, hi2[pr], lo2[pr]);
         }
-        const uint32_t a = rowaddr + ((uint32_t)((gsel + g8) ^ kx) << 4);
-        stas_v4(a, hi2[0], hi2[1], hi2[2], hi2[3], mbar);
-        stas_v4(a + lo_delta, lo2[0], lo2[1], lo2[2], lo2[3], mbar);
+        const uint32_t a = rowaddr + ((uint32_t)((g0 + g8) ^ fx) << 4);
+        sts_v4(a, hi2[0], hi2[1], hi2[2], hi2[3]);
+        sts_v4(a + lo_delta, lo2[0], lo2[1], lo2[2], lo2[3]);
     }
 }
 
-// Step schedule of the pair kernel (identical in producer, relay and issuer).  With two accumulator
-// groups (N_pad = 512) the epilogue finishes group 0 (neurons 0..255 = state chunks 0..3) first, so
-// the next step's MMAs over those chunks overlap the epilogue of group 1:
-//   wait tA (chunks 0..H1-1 rewritten in both CTAs; implies D0 drained)
-//     phase 1: chunks [0,H1) of group 0; each item also carries the readout half-tile of its chunk
-//   wait tB (all chunks + the input block rewritten, D1 drained)
-//     phase 2: chunks [H1,C-1) of group 0 (+ readout; the first item also carries the aug chunk's
-//              readout tile) -> commit y;  then every state chunk of the other groups, which hides
-//              the round trip of y through the frame warps (~6 K cycles)
-//   wait yready (y_{t-1} is in the state tile)
-//     phase 3: aug chunk of every group -> commit d
-// H1 = 4 for two groups, 0 for one (N_pad = 256: nothing to overlap with).
+// =====================================================================================
+// Pair kernel: two CTAs of a cluster (one TPC) work as one tensor core (tcgen05 cta_group::2).
+// The pair owns 128 frames, 64 per CTA.  FRAMES are the M side: per step
+//     D[frame, neuron] = [x_{t-1} | u_t | y_{t-1}][frame, :] . [W | W_in | W_fb]^T
+//   A = the CTA's own state tile [64 frames x K] (K-major), resident in shared memory and rewritten
+//       in place by the epilogue -- with the frames on the M side every accumulator row a CTA reads
+//       back belongs to one of ITS frames, so the new state never crosses to the peer CTA;
+//   B = weight rows, N-split over the pair: CTA r streams the slabs 2j + r of the shared L2-resident
+//       image (each SM moves half the bytes) through a ring of bulk-copy slots;
+//   D = fp32 in TMEM; for M = 128 the hardware keeps the columns of CTA 0's rows in lanes 0..63 and
+//       those of CTA 1's rows in lanes 64..127 (same TMEM columns).
+// The readout y_{t-1} = W_out[g] [x_{t-1}; u_{t-1}] rides along: its state part is appended to CTA 0's
+// B rows of the X items (72 + (56 + UO) rows = N 144 + N 128/144 instead of one N = 256 MMA, no extra
+// instruction), lands in TMEM columns [128, 128+UO) of lanes 0..63, and the frame warps add the input
+// part W_out_u u_{t-1} in fp32.  They write y into the aug chunk, whose items (W_in, W_fb) come last.
 //
-// State hand-off: the epilogue writes the new state with st.async (STAS) straight into the owner
-// CTA's tile; the owner's mbarriers tA / tB count the bytes (64 KB per accumulator group and CTA), so
-// the 16 epilogue warps neither fence nor arrive.  Warp 20 of each CTA posts the expected byte count
-// once per step and, in CTA 1, forwards the completion to the issuer in CTA 0 (fA / fB).
-constexpr int TC2_THREADS = 672;       // 21 warps: 0-1 frame, 2 producer, 3 issuer / relay, 4-19 epilogue, 20 poster
-constexpr uint32_t GROUP_BYTES = 2u * FT * 256u * 2u;   // hi + lo of 256 neurons x 64 frames
+// Step schedule (identical in producer, relay and issuer); X = slab r (+ readout rows) = neurons
+// 0..255, Y = slab 2 + r = neurons 256..511.  The epilogue finishes the X neurons (= state chunks 0..3)
+// first:
+//   wait tA (chunks 0..3 rewritten in both CTAs, X accumulators drained) -> X items of chunks 0..3,
+//                                                         overlapping the epilogue of the Y neurons
+//   wait tB (everything rewritten)  -> X items of chunks 4..7 -> commit y
+//                                   -> Y items of chunks 0..7 (hide the round trip of y)
+//   wait yready                     -> aug items of X and Y  -> commit d
+// With one group (N_pad = 256) there are only X items and nothing to overlap.
+// Warps (640 threads, 5 per scheduler = 96 registers): 0-1 frame warps (thread = frame: inputs,
+// readout, feedback), 2 producer, 3 issuer (CTA 0) / relay (CTA 1), 4-19 epilogue (thread = frame x
+// 32-neuron block).  The state barriers tA / tB / yready live in CTA 0 (the issuer); a warp fences its
+// own shared-memory writes (fence.proxy.async.shared::cta) and then arrives -- CTA 1's warps with a
+// relaxed remote arrive, since what they publish stays in their own CTA for their own tensor core.
+// =====================================================================================
+constexpr int TC2_THREADS = 640;
 
 template <bool DBG, bool TL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_predict_tc2(const TcParams p) {
     extern __shared__ unsigned char smem_dyn[];
-    __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_d, bar_tA, bar_tB, bar_fA, bar_fB, bar_y, bar_yready;
+    __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_d, bar_y, bar_tA, bar_tB, bar_yready;
     __shared__ uint32_t s_tmem;
-    __shared__ uint32_t s_key[2][FT];        // noise keys of (frame pair of the 128-frame tile, step)
+    __shared__ float s_wu[16 * 24];          // W_out_u of this pair's readout (accumulator units)
 
     const TcGeom gm = tc_geom(p.N, p.n_in);
     const int S = gm.S, C = gm.C, J = S >> 1;
     const int H1 = J == 2 ? 4 : 0;
+    const int UO = p.n_out <= 8 ? 8 : 16;                    // readout rows appended in CTA 0
     unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     unsigned char *st_hi = base, *ring = base + (size_t)2 * C * STILE;
     const uint32_t lo_delta = (uint32_t)C * STILE;
@@ -861,18 +871,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_
     const int tile0 = pair0 + (int)rank * FT;               // first frame owned by this CTA
     const int g = p.group_ids ? p.group_ids[min(pair0, p.B - 1)] : 0;
     const int P = p.N + p.n_in;
-    const bool y128 = p.n_out <= 8;                         // readout as an M = 128 UMMA (64 frames per CTA)
     const bool tl0 = TL && p.timeline && blockIdx.x == 0;
 
     if (tid == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(&bar_full[i], rank == 0 ? 2 : 1); mbar_init(&bar_empty[i], 1); }
         mbar_init(&bar_d, 1);
         mbar_init(&bar_y, 1);
-        mbar_init(&bar_yready, 4);
-        mbar_init(&bar_tA, 1);                               // poster (+ GROUP_BYTES of st.async data)
-        mbar_init(&bar_tB, 1 + 2);                           // poster + this CTA's frame warps (+ data)
-        mbar_init(&bar_fA, 1);                               // CTA 1's tA / tB forwarded to the issuer
-        mbar_init(&bar_fB, 1);
+        mbar_init(&bar_yready, 2 * 2);                       // frame warps of both CTAs (used in CTA 0)
+        mbar_init(&bar_tA, 2 * 16);                          // epilogue warps of both CTAs (used in CTA 0)
+        mbar_init(&bar_tB, 2 * (16 + 2));                    // + frame warps
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 3) {
@@ -880,39 +887,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_
                      ::"r"(smem_u32(&s_tmem)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < 2 * C * STILE / 16; i += TC2_THREADS)
+    // state tiles and ring start as zeros (the readout rows of CTA 1's slots are never written)
+    for (int i = tid; i < (2 * C * STILE + NST * SLOT2) / 16; i += TC2_THREADS)
         reinterpret_cast<uint4 *>(base)[i] = make_uint4(0, 0, 0, 0);
+    {
+        const float *tab = reinterpret_cast<const float *>(p.readouts + (size_t)g * gm.readout_bytes + gm.readout_tile_bytes);
+        for (int i = tid; i < 16 * 24; i += TC2_THREADS) s_wu[i] = tab[i];
+    }
     __syncthreads();
-    if (p.x0) {
+    if (p.x0) {                                             // continuation: x_{-1} = x0
         const float xscale = ldexpf(1.0f, SX);
         for (int i = tid; i < FT * p.N; i += TC2_THREADS) {
             const int f = i / p.N, n = i - f * p.N, b = tile0 + f;
             if (b < p.B)
-                split_sts(smem_u32(st_hi) + (n >> 6) * STILE + mn128_off(n & 63, f), lo_delta,
+                split_sts(smem_u32(st_hi) + (n >> 6) * STILE + sw128_off(f, n & 63), lo_delta,
                           p.x0[(size_t)b * p.N + n] * xscale);
         }
     }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                   // peer barriers, TMEM and state tiles exist before any remote op
+    cluster_sync_all();                   // peer barriers and TMEM exist before any remote op
     tc_fence_after();
     const uint32_t tmem = s_tmem;
-    const uint32_t r_yready = mapa_u32(smem_u32(&bar_yready), 0);
+    const uint32_t r_tA = mapa_u32(smem_u32(&bar_tA), 0), r_tB = mapa_u32(smem_u32(&bar_tB), 0),
+                   r_yr = mapa_u32(smem_u32(&bar_yready), 0);
+    // arrive on a barrier of CTA 0 after fencing this warp's shared-memory writes
+    auto arrive0 = [&](uint64_t *local, uint32_t remote) {
+        if (rank == 0) mbar_arrive(local);
+        else mbar_arrive_cluster_relaxed(remote);
+    };
 
     if (warp < 2) {
-        // ============ frame warps: thread = own frame; inputs, readout, noise keys ============
+        // ============ frame warps: thread = own frame; inputs, readout, feedback ============
         const int f = warp * 32 + lane, b = tile0 + f;
         const bool live = b < p.B;
-        // aug chunk, MN-major: element (k, f) at (k>>3)*1024 + (k&7)*128 + (((f>>3)^(k&7))<<4) + (f&7)*2
-        const uint32_t augc = smem_u32(st_hi) + gm.ca * STILE + (f & 7) * 2;
-        const int fg = f >> 3;
-        auto aug_addr = [&](int k) { return augc + (k >> 3) * 1024 + (k & 7) * 128 + ((fg ^ (k & 7)) << 4); };
+        const uint32_t row = smem_u32(st_hi) + gm.ca * STILE + (f >> 3) * 1024 + (f & 7) * 128;
+        const int fx = f & 7, ng = gm.UW >> 3, yg = gm.YO >> 3;
         const float su = ldexpf(1.0f, p.su), sy = ldexpf(1.0f, p.sy), ys = p.yscale[g];
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        float cur[24], nxt[24];
+        const uint32_t lane_tm = tmem + ((uint32_t)(warp * 32) << 16) + RCOL;
+        float cur[24], nxt[24], ut[16];   // u_it, u_{it+1} (scaled 2^su), W_out_u u_{it-1} (accumulator units)
 #pragma unroll
         for (int j = 0; j < 24; ++j) { cur[j] = 0.f; nxt[j] = 0.f; }
+#pragma unroll
+        for (int o = 0; o < 16; ++o) ut[o] = 0.f;
         auto load_row = [&](int r) {
 #pragma unroll
             for (int j = 0; j < 24; ++j) {
@@ -925,56 +943,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_
                 nxt[j] = v;
             }
         };
-        auto write_keys = [&](int r) {    // one key per frame pair of the whole 128-frame tile
-            s_key[r & 1][f] = esn_noise_key(p.seed, (uint32_t)(pair0 + 2 * f), (uint32_t)r);
-        };
-        auto write_inputs = [&]() {       // columns [0,UW) <- u_it, [UW,2UW) <- u_{it-1}
+        // granule gi of 8 aug-chunk columns of this frame's row <- eight pre-scaled values
+        auto store8 = [&](int gi, const float *v8) {
+            uint32_t h[4], l[4];
 #pragma unroll
-            for (int j = 0; j < 24; ++j) {
-                if (j < gm.UW) {
-                    split_sts(aug_addr(j), lo_delta, nxt[j]);
-                    split_sts(aug_addr(gm.UW + j), lo_delta, cur[j]);
-                }
-            }
+            for (int e = 0; e < 4; ++e) split_pair(pk2(v8[2 * e], v8[2 * e + 1]), h[e], l[e]);
+            const uint32_t a = row + ((uint32_t)(gi ^ fx) << 4);
+            sts_v4(a, h[0], h[1], h[2], h[3]);
+            sts_v4(a + lo_delta, l[0], l[1], l[2], l[3]);
+        };
+        auto write_inputs = [&]() {       // columns [0,UW) <- nxt; then cur = nxt
+#pragma unroll
+            for (int gi = 0; gi < 3; ++gi)
+                if (gi < ng) store8(gi, nxt + gi * 8);
 #pragma unroll
             for (int j = 0; j < 24; ++j) cur[j] = nxt[j];
         };
         load_row(0);
-        write_keys(0);
         write_inputs();
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_tB);
+        if (lane == 0) arrive0(&bar_tB, r_tB);
         for (int it = 0; it <= p.T; ++it) {
             if (it < p.T) load_row(it + 1);
             mbar_wait<true>(&bar_y, it & 1);
             tc_fence_after();
-            write_keys(it + 1);           // every epilogue warp has finished step it-1 by now
-            uint32_t yv[16];
-            if (y128) {
-                // M = 128 pair UMMA: lanes 0..63 = this CTA's frames, columns = outputs 0..7
-                uint32_t y8[8];
-                tmem_ld8(lane_base + YCOL2, y8);
-#pragma unroll
-                for (int o = 0; o < 8; ++o) { yv[o] = y8[o]; yv[o + 8] = 0u; }
-            } else {
-                tmem_ld16(lane_base + YCOL2, yv);
-            }
-            tmem_ld_wait();
             float y[16];
+            {
+                uint32_t yv[16];
+                if (UO == 8) {
+                    uint32_t y8[8];
+                    tmem_ld8(lane_tm, y8);
 #pragma unroll
-            for (int o = 0; o < 16; ++o) {
-                y[o] = __uint_as_float(yv[o]) * ys;
-                if (it == 0) y[o] = (p.y0 && live && o < p.n_out) ? p.y0[(size_t)b * p.n_out + o] : 0.f;
-                if (o >= p.n_out) y[o] = 0.f;
+                    for (int o = 0; o < 8; ++o) { yv[o] = y8[o]; yv[o + 8] = 0u; }
+                } else {
+                    tmem_ld16(lane_tm, yv);
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int o = 0; o < 16; ++o) {
+                    y[o] = (__uint_as_float(yv[o]) + ut[o]) * ys;
+                    if (it == 0) y[o] = (p.y0 && live && o < p.n_out) ? p.y0[(size_t)b * p.n_out + o] : 0.f;
+                    if (o >= p.n_out) y[o] = 0.f;
+                }
             }
             if (it < p.T) {               // feedback first: the issuer is waiting for it
+                float ysc[16];
 #pragma unroll
-                for (int o = 0; o < 16; ++o) split_sts(aug_addr(gm.YO + o), lo_delta, p.feedback ? y[o] * sy : 0.f);
+                for (int o = 0; o < 16; ++o) ysc[o] = p.feedback ? y[o] * sy : 0.f;
+                store8(yg, ysc);
+                if (UO == 16) store8(yg + 1, ysc + 8);
                 fence_async_smem();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(r_yready);
+                if (lane == 0) arrive0(&bar_yready, r_yr);
             }
             if (it >= 1 && it - 1 >= p.transient && live) {
                 float *dst = p.y_out + ((size_t)b * (p.T - p.transient) + (it - 1 - p.transient)) * p.n_out;
@@ -983,40 +1005,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_
                     if (o < p.n_out) dst[o] = (y[o] - p.t_shift[o]) / p.t_scale[o];
             }
             if (it == p.T) break;
-            mbar_wait<true>(&bar_d, it & 1);
+            // input part of the NEXT readout: W_out_u u_it (cur), in accumulator units
+#pragma unroll
+            for (int o = 0; o < 16; ++o) {
+                float a = 0.f;
+                if (o < UO) {
+#pragma unroll
+                    for (int i = 0; i < 24; ++i)
+                        if (i < gm.UW) a = fmaf(s_wu[o * 24 + i], cur[i], a);
+                }
+                ut[o] = a;
+            }
+            mbar_wait<true>(&bar_d, it & 1);     // the MMAs of step it have read the aug chunk
             write_inputs();
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_tB);
+            if (lane == 0) arrive0(&bar_tB, r_tB);
         }
     } else if (warp == 2) {
         // ============ producer: this CTA's half of every tile, every step ============
         if (elect_one()) {
             const unsigned char *wimg = p.weights;
-            const unsigned char *yimg = p.readouts + (size_t)g * gm.readout_bytes + rank * 1024;   // 8 of 16 output rows
+            const unsigned char *yimg = p.readouts + (size_t)g * gm.readout_bytes;
+            const uint32_t ybytes = (uint32_t)UO * 128u;
             uint32_t item = 0;
-            // weight tile (slab s, chunk c, half h) and/or readout half-tiles into the next slot
-            auto fetch = [&](int s, int c, int h, bool w, bool y) {
+            // weight tile (slab s, chunk c, half h) [+ in CTA 0 the readout rows of (c, h)] into the next slot
+            auto fetch = [&](int s, int c, int h, bool y) {
                 const int slot = item % NST;
                 mbar_wait<false>(&bar_empty[slot], ((item / NST) & 1) ^ 1);
                 unsigned char *dst = ring + (size_t)slot * SLOT2;
-                const bool yaug = y && c == H1;
-                mbar_expect_tx(&bar_full[slot], (w ? SLOT : 0) + (y ? 1024 : 0) + (yaug ? 1024 : 0));
-                if (w) bulk_g2s(dst, wimg + ((size_t)(s * C + c) * 2 + h) * SLOT, SLOT, &bar_full[slot]);
-                if (y) bulk_g2s(dst + SLOT, yimg + (size_t)(c * 2 + h) * YTILE, 1024, &bar_full[slot]);
-                if (yaug) bulk_g2s(dst + SLOT + 1024, yimg + (size_t)((C - 1) * 2 + h) * YTILE, 1024, &bar_full[slot]);
+                y = y && rank == 0;
+                mbar_expect_tx(&bar_full[slot], SLOT + (y ? ybytes : 0u));
+                bulk_g2s(dst, wimg + ((size_t)(s * C + c) * 2 + h) * SLOT, SLOT, &bar_full[slot]);
+                if (y) bulk_g2s(dst + SLOT, yimg + (size_t)(c * 2 + h) * YTILE, ybytes, &bar_full[slot]);
                 ++item;
             };
             for (int it = 0; it <= p.T; ++it) {
-                const bool last = it == p.T;
                 for (int c = 0; c < C - 1; ++c)
-                    for (int h = 0; h < 2; ++h) fetch((int)rank, c, h, !last, true);
-                if (last) break;
+                    for (int h = 0; h < 2; ++h) fetch((int)rank, c, h, true);
+                if (it == p.T) break;
                 for (int j = 1; j < J; ++j)
                     for (int c = 0; c < C - 1; ++c)
-                        for (int h = 0; h < 2; ++h) fetch(2 * j + (int)rank, c, h, true, false);
+                        for (int h = 0; h < 2; ++h) fetch(2 * j + (int)rank, c, h, false);
                 for (int j = 0; j < J; ++j)
-                    for (int h = 0; h < 2; ++h) fetch(2 * j + (int)rank, C - 1, h, true, false);
+                    for (int h = 0; h < 2; ++h) fetch(2 * j + (int)rank, C - 1, h, false);
             }
         }
     } else if (warp == 3 && rank == 1) {
@@ -1035,60 +1067,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_
     } else if (warp == 3) {
         // ============ MMA issuer (CTA 0): one thread drives both tensor cores ============
         if (elect_one()) {
-            // state tile is MN-major: B operand of the main chain, A operand of the readout chain
-            const uint32_t id_main = umma_idesc_major(256, PF, 0, 1), id_y = umma_idesc_major(y128 ? 128 : 256, 16, 1, 0);
-            const uint32_t hi0 = desc_lo_mn(smem_u32(st_hi)), ring0 = desc_lo(smem_u32(ring));
+            const uint32_t id_x1 = umma_idesc(128, 2 * X1ROWS), id_x2 = umma_idesc(128, 2 * (128 - X1ROWS + UO)),
+                           id_y = umma_idesc(128, 256);
+            const uint32_t hi0 = desc_lo(smem_u32(st_hi)), ring0 = desc_lo(smem_u32(ring));
             const uint32_t lod = lo_delta >> 4;
-            const uint32_t xaug = hi0 + (C - 1) * (STILE >> 4), dy = tmem + YCOL2;
+            const uint32_t dx1 = tmem + XCOL, dx2 = tmem + XCOL + X1ROWS, dy = tmem + YCOL2;
+            const int ku = (gm.UW + 15) / 16, ky = gm.YO / 16;     // aug chunk: k-steps [0,ku) = u_t, ky = y_{t-1}
             long long *trace = tl0 ? p.timeline + (size_t)(p.T + 1) * 8 : nullptr;
             int tr_i = -1;
             uint32_t item = 0;
-            // hi weight tile: x_hi and x_lo against it (2 MMAs per k-step); lo weight tile: x_hi only.
-            // weights K-major: 16 k = 32 B; state MN-major: 16 k = two 1024-byte atoms.
-            auto main_hi = [&](uint32_t d, uint32_t w, uint32_t x, int ks, bool first) {
-#pragma unroll 4
-                for (int kk = 0; kk < ks; ++kk) {
-                    umma2_f16(d, w + kk * 2, x + kk * 128, id_main, (first && kk == 0) ? 0u : 1u);
-                    umma2_f16(d, w + kk * 2, x + kk * 128 + lod, id_main, 1u);
-                }
-            };
-            auto main_lo = [&](uint32_t d, uint32_t w, uint32_t x, int ks) {
-#pragma unroll 4
-                for (int kk = 0; kk < ks; ++kk) umma2_f16(d, w + kk * 2, x + kk * 128, id_main, 1u);
-            };
-            auto y_hi = [&](uint32_t w, uint32_t x, int ks, bool first) {
-#pragma unroll 4
-                for (int kk = 0; kk < ks; ++kk) {
-                    umma2_f16(dy, x + kk * 128, w + kk * 2, id_y, (first && kk == 0) ? 0u : 1u);
-                    umma2_f16(dy, x + kk * 128 + lod, w + kk * 2, id_y, 1u);
-                }
-            };
-            auto y_lo = [&](uint32_t w, uint32_t x, int ks) {
-#pragma unroll 4
-                for (int kk = 0; kk < ks; ++kk) umma2_f16(dy, x + kk * 128, w + kk * 2, id_y, 1u);
-            };
-            // one state chunk = two ring items (hi tile, lo tile), each with its readout half-tiles
-            auto chunk = [&](uint32_t d, int c, bool w, bool y) {
+            // one state chunk against one slab = two ring items: the hi weight tile meets x_hi and x_lo,
+            // the lo weight tile x_hi only.  16 k = 32 bytes in both K-major operands.
+            auto chunk = [&](int c, bool xitem) {
                 const uint32_t x = hi0 + c * (STILE >> 4);
-                const int ks = c == C - 1 ? gm.kaug : 4;
+                const bool aug = c == C - 1;
+                const int ks = aug ? ku + 1 : 4;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int slot = item % NST;
                     mbar_wait<false>(&bar_full[slot], (item / NST) & 1);   // bulk-copy data only: no cluster acquire needed
                     if (TL && trace && tr_i >= 0 && tr_i < 64) trace[tr_i * 4 + 2] = clock64();
                     tc_fence_after();
-                    const uint32_t sl = ring0 + slot * (SLOT2 >> 4);
-                    if (h == 0) {
-                        if (w) main_hi(d, sl, x, ks, c == 0);
-                        if (y) {
-                            y_hi(sl + (SLOT >> 4), x, 4, c == 0);
-                            if (c == H1) y_hi(sl + ((SLOT + 1024) >> 4), xaug, gm.YO / 16, false);
-                        }
-                    } else {
-                        if (w) main_lo(d, sl, x, ks);
-                        if (y) {
-                            y_lo(sl + (SLOT >> 4), x, 4);
-                            if (c == H1) y_lo(sl + ((SLOT + 1024) >> 4), xaug, gm.YO / 16);
+                    const uint32_t w = ring0 + slot * (SLOT2 >> 4), w2 = w + ((X1ROWS * 128) >> 4);
+#pragma unroll 4
+                    for (int kk = 0; kk < ks; ++kk) {
+                        const uint32_t ko = (uint32_t)((aug && kk == ku) ? ky : kk) * 2;
+                        const uint32_t a = x + ko, acc = (c == 0 && h == 0 && kk == 0) ? 0u : 1u;
+                        if (xitem) {
+                            umma2_f16(dx1, a, w + ko, id_x1, acc);
+                            umma2_f16(dx2, a, w2 + ko, id_x2, acc);
+                            if (h == 0) {
+                                umma2_f16(dx1, a + lod, w + ko, id_x1, 1u);
+                                umma2_f16(dx2, a + lod, w2 + ko, id_x2, 1u);
+                            }
+                        } else {
+                            umma2_f16(dy, a, w + ko, id_y, acc);
+                            if (h == 0) umma2_f16(dy, a + lod, w + ko, id_y, 1u);
                         }
                     }
                     umma2_commit_pair(&bar_empty[slot]);
@@ -1098,100 +1112,77 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_
                 }
             };
             for (int it = 0; it <= p.T; ++it) {
-                const bool last = it == p.T;
                 if (TL) tr_i = (it == 200) ? 0 : -1;
                 if (tl0) p.timeline[it * 8 + 0] = clock64();
                 if (H1) {
-                    mbar_wait<false>(&bar_tA, it & 1);
-                    mbar_wait_cluster<false>(&bar_fA, it & 1);
-                    fence_async_smem();
+                    mbar_wait_cluster<false>(&bar_tA, it & 1);
                     tc_fence_after();
                     if (tl0) p.timeline[it * 8 + 1] = clock64();
-                    for (int c = 0; c < H1; ++c) chunk(tmem, c, !last, true);
+                    for (int c = 0; c < H1; ++c) chunk(c, true);
                 }
                 if (tl0) p.timeline[it * 8 + 2] = clock64();
-                mbar_wait<false>(&bar_tB, it & 1);
-                mbar_wait_cluster<false>(&bar_fB, it & 1);
-                fence_async_smem();
+                mbar_wait_cluster<false>(&bar_tB, it & 1);
                 tc_fence_after();
                 if (tl0) p.timeline[it * 8 + 3] = clock64();
-                for (int c = H1; c < C - 1; ++c) chunk(tmem, c, !last, true);
+                for (int c = H1; c < C - 1; ++c) chunk(c, true);
                 umma2_commit_pair(&bar_y);
-                if (last) break;
+                if (it == p.T) break;
                 for (int j = 1; j < J; ++j)
-                    for (int c = 0; c < C - 1; ++c) chunk(tmem + j * PF, c, true, false);
+                    for (int c = 0; c < C - 1; ++c) chunk(c, false);
                 if (tl0) p.timeline[it * 8 + 7] = clock64();
                 mbar_wait_cluster<false>(&bar_yready, it & 1);
                 tc_fence_after();
-                for (int j = 0; j < J; ++j) chunk(tmem + j * PF, C - 1, true, false);
+                for (int j = 0; j < J; ++j) chunk(C - 1, j == 0);
                 umma2_commit_pair(&bar_d);
             }
         }
-    } else if (warp == 20) {
-        // ============ poster / forwarder: expected bytes of every state hand-off ============
-        if (elect_one()) {
-            const uint32_t bytesA = H1 ? GROUP_BYTES : 0u, bytesB = (uint32_t)(J - (H1 ? 1 : 0)) * GROUP_BYTES;
-            const uint32_t r_fA = mapa_u32(smem_u32(&bar_fA), 0), r_fB = mapa_u32(smem_u32(&bar_fB), 0);
-            for (int it = 0; it <= p.T; ++it) {
-                // phase it of tA / tB: the initial state (it = 0, no data) or the epilogue of step it-1
-                if (H1) { if (it == 0) mbar_arrive(&bar_tA); else mbar_expect_tx(&bar_tA, bytesA); }
-                if (it == 0) mbar_arrive(&bar_tB); else mbar_expect_tx(&bar_tB, bytesB);
-                if (rank == 1) {
-                    if (H1) {
-                        mbar_wait<false>(&bar_tA, it & 1);
-                        fence_async_smem();
-                        mbar_arrive_cluster_relaxed(r_fA);
-                    }
-                    mbar_wait<false>(&bar_tB, it & 1);
-                    fence_async_smem();
-                    mbar_arrive_cluster_relaxed(r_fB);
-                } else {
-                    if (H1) mbar_wait<true>(&bar_tA, it & 1);     // do not post phase it+1 before phase it is over
-                    mbar_wait<true>(&bar_tB, it & 1);
-                }
-            }
-        }
     } else {
-        // ============ epilogue: TMEM -> tanh -> noise -> fp16 hi/lo -> owner CTA's state tile ============
-        // warp (q, fq): TMEM lane quarter q (32 neurons of every group), frames 32 fq .. 32 fq + 31 of
-        // the pair's 128 (owner CTA fq >> 1); groups in order.
-        const int e = warp - 4, q = warp & 3, fq = e >> 2, fh = fq >> 1;
-        const int nl = 128 * (int)rank + q * 32 + lane;             // neuron within its group
-        const uint32_t lane_tm = tmem + ((uint32_t)(q * 32) << 16) + fq * 32;
-        const uint32_t own = mapa_u32(smem_u32(st_hi), (uint32_t)fh);
-        const uint32_t own_tA = mapa_u32(smem_u32(&bar_tA), (uint32_t)fh), own_tB = mapa_u32(smem_u32(&bar_tB), (uint32_t)fh);
-        const int fbase = pair0 + fq * 32;
-        const int kx = nl & 7;                                     // (n & 63) & 7 for every group
-        const float amp = p.noise_amp;
+        // ============ epilogue: TMEM -> tanh -> noise -> fp16 hi/lo -> own state tile ============
+        // warp (q, cq): TMEM lanes 32 q .. 32 q + 31 = frames 32 (q & 1) .. of this CTA, columns of the rows
+        // that CTA hl = q >> 1 supplied (slabs hl and 2 + hl); 32-neuron block cq of each 128-column group.
+        const int e = warp - 4, q = warp & 3, cq = e >> 2, hl = q >> 1;
+        const int f = 32 * (q & 1) + lane, b = tile0 + f;
+        const bool live = b < p.B;
+        const int fx = f & 7;
+        const uint32_t lane_tm = tmem + ((uint32_t)(q * 32) << 16) + 32 * cq;
+        const uint32_t frow = smem_u32(st_hi) + (f >> 3) * 1024 + fx * 128;
         const bool st4 = tl0 && warp == 4 && lane == 0;
+        EpiStep es;
+        es.dsc = ldexpf(1.0f, -(SX + SW));
+        es.ampf = p.noise_amp * (float)(1 << SX);
+        es.amp16s = es.ampf * (1.0f / 65536.0f);
+        es.ampoffs = 0.5f * es.ampf;
+        __syncwarp();
+        if (lane == 0) {                                   // initial state is in place
+            if (H1) arrive0(&bar_tA, r_tA);
+            arrive0(&bar_tB, r_tB);
+        }
         for (int it = 0; it < p.T; ++it) {
+            es.key = esn_noise_key(p.seed, (uint32_t)b, (uint32_t)it);
             mbar_wait<true>(&bar_d, it & 1);
             tc_fence_after();
             if (st4) p.timeline[it * 8 + 4] = clock64();
-            const uint32_t *keys = s_key[it & 1] + fq * 16;
 #pragma unroll 1
             for (int j = 0; j < J; ++j) {
-                const int n = 256 * j + nl;
-                const bool n_ok = n < p.N;
-                EpiConst ec;
-                ec.dsc = n_ok ? ldexpf(1.0f, -(SX + SW)) : 0.f;
-                ec.ampf = n_ok ? amp * (float)(1 << SX) : 0.f;
-                ec.amp16s = ec.ampf * (1.0f / 65536.0f);
-                ec.ampoffs = 0.5f * ec.ampf;
-                const uint32_t nmul = (uint32_t)n * 0xC2B2AE35U;
-                const int k = n & 63;
-                const uint32_t rowaddr = own + (n >> 6) * STILE + (k >> 3) * 1024 + kx * 128;
-                const uint32_t mbar = (H1 && j == 0) ? own_tA : own_tB;
+                const int n0 = 256 * j + 128 * hl + 32 * cq;
                 uint32_t v[32];
-                tmem_ld32(lane_tm + (uint32_t)(j * PF), v);
+                tmem_ld32(lane_tm + (uint32_t)(j == 0 ? XCOL : YCOL2), v);
                 tmem_ld_wait();
+                const uint32_t rowaddr = frow + (n0 >> 6) * STILE;
                 float m = 0.f;
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) m = fmaxf(m, fmaxf(fabsf(__uint_as_float(v[i])), fabsf(__uint_as_float(v[i + 1]))));
-                if (!__any_sync(0xffffffffu, m * ec.dsc > 3.0f))
-                    tc2_epilogue32<DBG, false>(p, v, it, n, n_ok, fbase, keys, nmul, rowaddr, (fq & 1) * 4, kx, lo_delta, P, ec, mbar);
-                else
-                    tc2_epilogue32<DBG, true>(p, v, it, n, n_ok, fbase, keys, nmul, rowaddr, (fq & 1) * 4, kx, lo_delta, P, ec, mbar);
+                const bool big = __any_sync(0xffffffffu, m * es.dsc > 3.0f);
+                if (n0 + 32 <= p.N) {
+                    if (!big) tc2_epilogue32<DBG, false, false>(p, v, it, n0, b, live, rowaddr, fx, lo_delta, P, es);
+                    else tc2_epilogue32<DBG, true, false>(p, v, it, n0, b, live, rowaddr, fx, lo_delta, P, es);
+                } else {
+                    tc2_epilogue32<DBG, true, true>(p, v, it, n0, b, live, rowaddr, fx, lo_delta, P, es);
+                }
+                fence_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (H1 && j == 0) arrive0(&bar_tA, r_tA); else arrive0(&bar_tB, r_tB); }
                 if (st4) p.timeline[it * 8 + 5 + j] = clock64();
             }
         }

@@ -18,17 +18,16 @@ def _mix32(x):
 
 
 def device_noise_uniforms(seed, B, steps, N, first_frame=0):
-    """uniforms[b, row, neuron] in [0,1), exactly as the kernels draw them: one
-    hash per (frame pair, row, neuron); even frame = low 16 bits, odd = high 16."""
+    """uniforms[b, row, neuron] in [0,1), exactly as the kernels draw them: one key
+    per (frame, row), one hash per neuron pair; even neuron = low 16 bits, odd = high 16."""
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     lo, hi = np.uint64(seed & 0xFFFFFFFF), np.uint64(seed >> 32)
-    frames = np.arange(B, dtype=np.uint64) + np.uint64(first_frame)
-    b = (frames >> np.uint64(1))[:, None, None]
-    odd = (frames & np.uint64(1)).astype(bool)[:, None, None]
+    b = (np.arange(B, dtype=np.uint64) + np.uint64(first_frame))[:, None, None]
     r = np.arange(steps, dtype=np.uint64)[None, :, None]
     n = np.arange(N, dtype=np.uint64)[None, None, :]
+    odd = (n & np.uint64(1)).astype(bool)
     k = _mix32(lo + ((np.uint64(0x9E3779B9) * b) & _M))
     k = _mix32(k ^ ((((r * np.uint64(0x85EBCA6B)) & _M) + hi) & _M))
-    h = _mix32(k + ((n * np.uint64(0xC2B2AE35)) & _M))
+    h = _mix32(k + (((n >> np.uint64(1)) * np.uint64(0xC2B2AE35)) & _M))
     bits = np.where(odd, h >> np.uint64(16), h & np.uint64(0xFFFF))
     return bits.astype(np.float64) / 65536.0
