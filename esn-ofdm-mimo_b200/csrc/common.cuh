@@ -30,8 +30,15 @@ __host__ __device__ __forceinline__ uint32_t esn_noise_key(uint64_t seed, uint32
     uint32_t k = esn_mix32((uint32_t)seed + 0x9E3779B9U * frame);
     return esn_mix32(k ^ (row * 0x85EBCA6BU + (uint32_t)(seed >> 32)));
 }
+// 32 noise bits of a neuron pair from the (well mixed) key plus the pair index: one xorshift, one
+// 32 x 32 -> 64 bit multiply, high word folded onto the low word -- 5 instructions per two values.
+__host__ __device__ __forceinline__ uint32_t esn_fold32(uint32_t x) {
+    x ^= x >> 16;
+    const uint64_t m = (uint64_t)x * 0x9E3779B1U;
+    return (uint32_t)m ^ (uint32_t)(m >> 32);
+}
 __host__ __device__ __forceinline__ uint32_t esn_noise_bits(uint32_t key, uint32_t neuron) {
-    return esn_mix32(key + (neuron >> 1) * 0xC2B2AE35U);   // low half: even neuron, high half: odd neuron
+    return esn_fold32(key + (neuron >> 1) * 0xC2B2AE35U);   // low half: even neuron, high half: odd neuron
 }
 __host__ __device__ __forceinline__ float esn_noise_uniform(uint32_t key, uint32_t neuron) {
     const uint32_t h = esn_noise_bits(key, neuron);

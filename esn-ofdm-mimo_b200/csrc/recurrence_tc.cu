@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p
                                 const int b = tile0 + f;
                                 u = (b < p.B && n_ok) ? p.noise[((size_t)b * p.T + it) * p.N + n] : 0.5f;
                             } else {
-                                const uint32_t hb = esn_mix32(keys[f] + nmul);
+                                const uint32_t hb = esn_fold32(keys[f] + nmul);
                                 u = (float)((n & 1) ? (hb >> 16) : (hb & 0xFFFFu)) * (1.0f / 65536.0f);
                             }
                             x = fmaf(u, p.noise_amp, x - 0.5f * p.noise_amp);
@@ -682,7 +682,7 @@ __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr) { return (saddr >
 constexpr int PF = 2 * FT;             // frames per CTA pair
 constexpr int SLOT2 = SLOT + 2048;     // pair-kernel ring slot: weight tile (128 rows) + up to 16 readout rows
 constexpr int X1ROWS = 72;             // B rows per CTA of the first X MMA (N = 144); the second takes 56 + readout rows
-constexpr int XCOL = 0, RCOL = 128, YCOL2 = 160;   // TMEM columns: X neurons [0,128), readout [128,144), Y neurons [160,288)
+// TMEM columns: neuron group j at [128 j, 128 j + 128); the readout follows the last group (the X group)
 
 // ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): two lanes per instruction ----
 __device__ __forceinline__ uint64_t pk2(float a, float b) {
@@ -743,14 +743,14 @@ struct EpiStep {
     float ampf;            // noise_amp 2^SX (host-noise path)
 };
 
-// One block of an epilogue thread: v[] = accumulators of ITS frame for the 32 consecutive neurons
-// n0 .. n0+31 -> [7/6] Pade tanh -> noise -> x 2^SX -> fp16 hi/lo, written as four 16-byte stores per
+// One block of an epilogue thread: v[] = accumulators of ITS frame for the NE consecutive neurons
+// n0 .. n0+NE-1 -> [7/6] Pade tanh -> noise -> x 2^SX -> fp16 hi/lo, written as four 16-byte stores per
 // half into the frame's row of the K-major state tile.  Two neurons per instruction through the
 // packed fp32x2 pipe; the 2^SX pre-scale is folded into the numerator.  FIX = true (chosen by the
 // caller when some |z| > 3, rare in an echo-state reservoir) patches those elements with the exact
 // formula.  PAD = block crosses the end of the reservoir (padded neurons stay exactly zero).
-template <bool DBG, bool FIX, bool PAD>
-__device__ __forceinline__ void tc2_epilogue32(const TcParams &p, const uint32_t (&v)[32], int it, int n0, int b, bool live,
+template <bool DBG, bool FIX, bool PAD, int NE>
+__device__ __forceinline__ void tc2_epilogue_blk(const TcParams &p, const uint32_t (&v)[NE], int it, int n0, int b, bool live,
                                                uint32_t rowaddr, int fx, uint32_t lo_delta, int P, const EpiStep &es) {
     constexpr float XS = (float)(1 << SX);
     const bool use_noise = p.noise_amp != 0.f;
@@ -763,7 +763,7 @@ __device__ __forceinline__ void tc2_epilogue32(const TcParams &p, const uint32_t
     const uint32_t hkey = es.key + (uint32_t)(n0 >> 1) * 0xC2B2AE35U;
     const int g0 = (n0 & 63) >> 3;
 #pragma unroll
-    for (int g8 = 0; g8 < 4; ++g8) {                      // granule of 8 neurons
+    for (int g8 = 0; g8 < NE / 8; ++g8) {                 // granule of 8 neurons
         uint32_t hi2[4], lo2[4];
 #pragma unroll
         for (int pr = 0; pr < 4; ++pr) {                  // pair of neurons
@@ -788,7 +788,7 @@ __device__ __forceinline__ void tc2_epilogue32(const TcParams &p, const uint32_t
                         u[e] = (live && n + e < p.N) ? p.noise[((size_t)b * p.T + it) * p.N + n + e] : 0.5f;
                     nt = pk2(fmaf(u[0], es.ampf, -es.ampoffs), fmaf(u[1], es.ampf, -es.ampoffs));
                 } else {
-                    const uint32_t hb = esn_mix32(hkey + (uint32_t)(jj >> 1) * 0xC2B2AE35U);
+                    const uint32_t hb = esn_fold32(hkey + (uint32_t)(jj >> 1) * 0xC2B2AE35U);
                     nt = fma2(pk2((float)(hb & 0xFFFFu), (float)(hb >> 16)), amp2, off2);
                 }
             }
@@ -833,15 +833,17 @@ __device__ __forceinline__ void tc2_epilogue32(const TcParams &p, const uint32_t
 // instruction), lands in TMEM columns [128, 128+UO) of lanes 0..63, and the frame warps add the input
 // part W_out_u u_{t-1} in fp32.  They write y into the aug chunk, whose items (W_in, W_fb) come last.
 //
-// Step schedule (identical in producer, relay and issuer); X = slab r (+ readout rows) = neurons
-// 0..255, Y = slab 2 + r = neurons 256..511.  The epilogue finishes the X neurons (= state chunks 0..3)
-// first:
-//   wait tA (chunks 0..3 rewritten in both CTAs, X accumulators drained) -> X items of chunks 0..3,
-//                                                         overlapping the epilogue of the Y neurons
-//   wait tB (everything rewritten)  -> X items of chunks 4..7 -> commit y
-//                                   -> Y items of chunks 0..7 (hide the round trip of y)
-//   wait yready                     -> aug items of X and Y  -> commit d
-// With one group (N_pad = 256) there are only X items and nothing to overlap.
+// Step schedule (identical in producer, relay and issuer).  Neuron group G0 = slabs r (neurons 0..255,
+// one N = 256 MMA per k-step), G1 = slabs 2 + r (+ readout rows in CTA 0; neurons 256..511).  The
+// epilogue rewrites the state in the order chunks {0,2}, chunks {1,3}, chunks 4..7, so that the next
+// step's MMAs start as early as possible and overlap the rest of the epilogue:
+//   wait tA0 (chunks 0, 2 rewritten in both CTAs; G0 accumulators drained) -> G0 items of chunks 0, 2
+//   wait tA1 (chunks 1, 3 rewritten)                                       -> G0 items of chunks 1, 3
+//   wait tD1 (G1 accumulators drained)                                     -> G1 items of chunks 0..3
+//   wait tB  (everything rewritten)  -> G1 items of chunks 4..7 -> commit y
+//                                    -> G0 items of chunks 4..6 (hide the round trip of y)
+//   wait yready                      -> aug items of G0 and G1, G0 item of chunk 7 -> commit d
+// With one group (N_pad = 256) the only group carries the readout and nothing overlaps.
 // Warps (640 threads, 5 per scheduler = 96 registers): 0-1 frame warps (thread = frame: inputs,
 // readout, feedback), 2 producer, 3 issuer (CTA 0) / relay (CTA 1), 4-19 epilogue (thread = frame x
 // 32-neuron block).  The state barriers tA / tB / yready live in CTA 0 (the issuer); a warp fences its
@@ -853,14 +855,15 @@ constexpr int TC2_THREADS = 640;
 template <bool DBG, bool TL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_predict_tc2(const TcParams p) {
     extern __shared__ unsigned char smem_dyn[];
-    __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_d, bar_y, bar_tA, bar_tB, bar_yready;
+    __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_d, bar_y, bar_tA0, bar_tA1, bar_tD1, bar_tB, bar_yready;
     __shared__ uint32_t s_tmem;
     __shared__ float s_wu[16 * 24];          // W_out_u of this pair's readout (accumulator units)
 
     const TcGeom gm = tc_geom(p.N, p.n_in);
     const int S = gm.S, C = gm.C, J = S >> 1;
-    const int H1 = J == 2 ? 4 : 0;
+    const bool two = J == 2;                                 // two neuron groups: G0 plain, G1 with the readout
     const int UO = p.n_out <= 8 ? 8 : 16;                    // readout rows appended in CTA 0
+    const int XC = two ? 128 : 0, RC = XC + 128;             // TMEM columns of the readout group and of the readout
     unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     unsigned char *st_hi = base, *ring = base + (size_t)2 * C * STILE;
     const uint32_t lo_delta = (uint32_t)C * STILE;
@@ -878,7 +881,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_
         mbar_init(&bar_d, 1);
         mbar_init(&bar_y, 1);
         mbar_init(&bar_yready, 2 * 2);                       // frame warps of both CTAs (used in CTA 0)
-        mbar_init(&bar_tA, 2 * 16);                          // epilogue warps of both CTAs (used in CTA 0)
+        mbar_init(&bar_tA0, 2 * 16);                         // epilogue warps of both CTAs (used in CTA 0)
+        mbar_init(&bar_tA1, 2 * 16);
+        mbar_init(&bar_tD1, 2 * 16);
         mbar_init(&bar_tB, 2 * (16 + 2));                    // + frame warps
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -910,8 +915,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_
     cluster_sync_all();                   // peer barriers and TMEM exist before any remote op
     tc_fence_after();
     const uint32_t tmem = s_tmem;
-    const uint32_t r_tA = mapa_u32(smem_u32(&bar_tA), 0), r_tB = mapa_u32(smem_u32(&bar_tB), 0),
-                   r_yr = mapa_u32(smem_u32(&bar_yready), 0);
+    const uint32_t r_tA0 = mapa_u32(smem_u32(&bar_tA0), 0), r_tA1 = mapa_u32(smem_u32(&bar_tA1), 0),
+                   r_tD1 = mapa_u32(smem_u32(&bar_tD1), 0),
+                   r_tB = mapa_u32(smem_u32(&bar_tB), 0), r_yr = mapa_u32(smem_u32(&bar_yready), 0);
     // arrive on a barrier of CTA 0 after fencing this warp's shared-memory writes
     auto arrive0 = [&](uint64_t *local, uint32_t remote) {
         if (rank == 0) mbar_arrive(local);
@@ -925,7 +931,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_
         const uint32_t row = smem_u32(st_hi) + gm.ca * STILE + (f >> 3) * 1024 + (f & 7) * 128;
         const int fx = f & 7, ng = gm.UW >> 3, yg = gm.YO >> 3;
         const float su = ldexpf(1.0f, p.su), sy = ldexpf(1.0f, p.sy), ys = p.yscale[g];
-        const uint32_t lane_tm = tmem + ((uint32_t)(warp * 32) << 16) + RCOL;
+        const uint32_t lane_tm = tmem + ((uint32_t)(warp * 32) << 16) + RC;
         float cur[24], nxt[24], ut[16];   // u_it, u_{it+1} (scaled 2^su), W_out_u u_{it-1} (accumulator units)
 #pragma unroll
         for (int j = 0; j < 24; ++j) { cur[j] = 0.f; nxt[j] = 0.f; }
@@ -1036,19 +1042,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_
                 unsigned char *dst = ring + (size_t)slot * SLOT2;
                 y = y && rank == 0;
                 mbar_expect_tx(&bar_full[slot], SLOT + (y ? ybytes : 0u));
-                bulk_g2s(dst, wimg + ((size_t)(s * C + c) * 2 + h) * SLOT, SLOT, &bar_full[slot]);
+                const unsigned char *src = wimg + ((size_t)(s * C + c) * 2 + h) * SLOT;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4)            // four requests in flight per tile
+                    bulk_g2s(dst + q4 * (SLOT / 4), src + q4 * (SLOT / 4), SLOT / 4, &bar_full[slot]);
                 if (y) bulk_g2s(dst + SLOT, yimg + (size_t)(c * 2 + h) * YTILE, ybytes, &bar_full[slot]);
                 ++item;
             };
+            auto chunk = [&](int j, int c) {          // the two items (hi, lo) of slab 2j + r, chunk c
+                for (int h = 0; h < 2; ++h) fetch(2 * j + (int)rank, c, h, j == J - 1 && c < C - 1);
+            };
             for (int it = 0; it <= p.T; ++it) {
-                for (int c = 0; c < C - 1; ++c)
-                    for (int h = 0; h < 2; ++h) fetch((int)rank, c, h, true);
-                if (it == p.T) break;
-                for (int j = 1; j < J; ++j)
-                    for (int c = 0; c < C - 1; ++c)
-                        for (int h = 0; h < 2; ++h) fetch(2 * j + (int)rank, c, h, false);
-                for (int j = 0; j < J; ++j)
-                    for (int h = 0; h < 2; ++h) fetch(2 * j + (int)rank, C - 1, h, false);
+                const bool last = it == p.T;
+                if (two && !last) { chunk(0, 0); chunk(0, 2); chunk(0, 1); chunk(0, 3); }
+                for (int c = 0; c < C - 1; ++c) chunk(J - 1, c);
+                if (last) break;
+                if (two) { chunk(0, 4); chunk(0, 5); chunk(0, 6); }
+                for (int j = 0; j < J; ++j) chunk(j, C - 1);
+                if (two) chunk(0, 7);
             }
         }
     } else if (warp == 3 && rank == 1) {
@@ -1071,13 +1082,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_
                            id_y = umma_idesc(128, 256);
             const uint32_t hi0 = desc_lo(smem_u32(st_hi)), ring0 = desc_lo(smem_u32(ring));
             const uint32_t lod = lo_delta >> 4;
-            const uint32_t dx1 = tmem + XCOL, dx2 = tmem + XCOL + X1ROWS, dy = tmem + YCOL2;
+            const uint32_t dx1 = tmem + XC, dx2 = tmem + XC + X1ROWS, dy = tmem;
             const int ku = (gm.UW + 15) / 16, ky = gm.YO / 16;     // aug chunk: k-steps [0,ku) = u_t, ky = y_{t-1}
             long long *trace = tl0 ? p.timeline + (size_t)(p.T + 1) * 8 : nullptr;
             int tr_i = -1;
             uint32_t item = 0;
             // one state chunk against one slab = two ring items: the hi weight tile meets x_hi and x_lo,
-            // the lo weight tile x_hi only.  16 k = 32 bytes in both K-major operands.
+            // the lo weight tile x_hi only.  16 k = 32 bytes in both K-major operands.  xitem: the readout
+            // group (two MMAs per k-step: rows 0..71 and rows 72..127 + readout rows of the slot).
             auto chunk = [&](int c, bool xitem) {
                 const uint32_t x = hi0 + c * (STILE >> 4);
                 const bool aug = c == C - 1;
@@ -1112,39 +1124,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_
                 }
             };
             for (int it = 0; it <= p.T; ++it) {
+                const bool last = it == p.T;
                 if (TL) tr_i = (it == 200) ? 0 : -1;
                 if (tl0) p.timeline[it * 8 + 0] = clock64();
-                if (H1) {
-                    mbar_wait_cluster<false>(&bar_tA, it & 1);
+                if (two && !last) {
+                    mbar_wait_cluster<false>(&bar_tA0, it & 1);
                     tc_fence_after();
                     if (tl0) p.timeline[it * 8 + 1] = clock64();
-                    for (int c = 0; c < H1; ++c) chunk(c, true);
+                    chunk(0, false);
+                    chunk(2, false);
+                    mbar_wait_cluster<false>(&bar_tA1, it & 1);
+                    tc_fence_after();
+                    chunk(1, false);
+                    chunk(3, false);
+                    mbar_wait_cluster<false>(&bar_tD1, it & 1);      // G1 accumulators have been read
+                    tc_fence_after();
+                    for (int c = 0; c < 4; ++c) chunk(c, true);
                 }
                 if (tl0) p.timeline[it * 8 + 2] = clock64();
                 mbar_wait_cluster<false>(&bar_tB, it & 1);
                 tc_fence_after();
                 if (tl0) p.timeline[it * 8 + 3] = clock64();
-                for (int c = H1; c < C - 1; ++c) chunk(c, true);
+                for (int c = (two && !last) ? 4 : 0; c < C - 1; ++c) chunk(c, true);
                 umma2_commit_pair(&bar_y);
-                if (it == p.T) break;
-                for (int j = 1; j < J; ++j)
-                    for (int c = 0; c < C - 1; ++c) chunk(c, false);
+                if (last) break;
+                if (two) { chunk(4, false); chunk(5, false); chunk(6, false); }
                 if (tl0) p.timeline[it * 8 + 7] = clock64();
                 mbar_wait_cluster<false>(&bar_yready, it & 1);
                 tc_fence_after();
-                for (int j = 0; j < J; ++j) chunk(C - 1, j == 0);
+                if (two) chunk(C - 1, false);
+                chunk(C - 1, true);
+                if (two) chunk(7, false);
                 umma2_commit_pair(&bar_d);
             }
         }
     } else {
         // ============ epilogue: TMEM -> tanh -> noise -> fp16 hi/lo -> own state tile ============
         // warp (q, cq): TMEM lanes 32 q .. 32 q + 31 = frames 32 (q & 1) .. of this CTA, columns of the rows
-        // that CTA hl = q >> 1 supplied (slabs hl and 2 + hl); 32-neuron block cq of each 128-column group.
+        // that CTA hl = q >> 1 supplied (slabs hl and 2 + hl).  Two groups: G0 in two 16-neuron blocks
+        // (columns 16 cq and 64 + 16 cq: chunks 2 hl and 2 hl + 1), then 32 neurons of G1 (columns 32 cq).
         const int e = warp - 4, q = warp & 3, cq = e >> 2, hl = q >> 1;
         const int f = 32 * (q & 1) + lane, b = tile0 + f;
         const bool live = b < p.B;
         const int fx = f & 7;
-        const uint32_t lane_tm = tmem + ((uint32_t)(q * 32) << 16) + 32 * cq;
+        const uint32_t lane_tm = tmem + ((uint32_t)(q * 32) << 16);
         const uint32_t frow = smem_u32(st_hi) + (f >> 3) * 1024 + fx * 128;
         const bool st4 = tl0 && warp == 4 && lane == 0;
         EpiStep es;
@@ -1152,9 +1175,53 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_
         es.ampf = p.noise_amp * (float)(1 << SX);
         es.amp16s = es.ampf * (1.0f / 65536.0f);
         es.ampoffs = 0.5f * es.ampf;
+        // publish a block: fence this warp's shared-memory writes, then arrive on CTA 0's barrier
+        auto publish = [&](uint64_t *local, uint32_t remote) {
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) arrive0(local, remote);
+        };
+        auto block16 = [&](int it, int col, int n0) {
+            uint32_t v[16];
+            tmem_ld16(lane_tm + (uint32_t)col, v);
+            tmem_ld_wait();
+            float m = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) m = fmaxf(m, fmaxf(fabsf(__uint_as_float(v[i])), fabsf(__uint_as_float(v[i + 1]))));
+            const bool big = __any_sync(0xffffffffu, m * es.dsc > 3.0f);
+            const uint32_t rowaddr = frow + (n0 >> 6) * STILE;
+            if (n0 + 16 <= p.N) {
+                if (!big) tc2_epilogue_blk<DBG, false, false, 16>(p, v, it, n0, b, live, rowaddr, fx, lo_delta, P, es);
+                else tc2_epilogue_blk<DBG, true, false, 16>(p, v, it, n0, b, live, rowaddr, fx, lo_delta, P, es);
+            } else {
+                tc2_epilogue_blk<DBG, true, true, 16>(p, v, it, n0, b, live, rowaddr, fx, lo_delta, P, es);
+            }
+        };
+        auto block32 = [&](int it, int col, int n0) {
+            uint32_t v[32];
+            tmem_ld32(lane_tm + (uint32_t)col, v);
+            tmem_ld_wait();
+            if (two) {                                     // G1 accumulators drained: its MMAs over chunks 0..3 may start
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) arrive0(&bar_tD1, r_tD1);
+            }
+            float m = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) m = fmaxf(m, fmaxf(fabsf(__uint_as_float(v[i])), fabsf(__uint_as_float(v[i + 1]))));
+            const bool big = __any_sync(0xffffffffu, m * es.dsc > 3.0f);
+            const uint32_t rowaddr = frow + (n0 >> 6) * STILE;
+            if (n0 + 32 <= p.N) {
+                if (!big) tc2_epilogue_blk<DBG, false, false, 32>(p, v, it, n0, b, live, rowaddr, fx, lo_delta, P, es);
+                else tc2_epilogue_blk<DBG, true, false, 32>(p, v, it, n0, b, live, rowaddr, fx, lo_delta, P, es);
+            } else {
+                tc2_epilogue_blk<DBG, true, true, 32>(p, v, it, n0, b, live, rowaddr, fx, lo_delta, P, es);
+            }
+        };
         __syncwarp();
         if (lane == 0) {                                   // initial state is in place
-            if (H1) arrive0(&bar_tA, r_tA);
+            if (two) { arrive0(&bar_tA0, r_tA0); arrive0(&bar_tA1, r_tA1); arrive0(&bar_tD1, r_tD1); }
             arrive0(&bar_tB, r_tB);
         }
         for (int it = 0; it < p.T; ++it) {
@@ -1162,29 +1229,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_
             mbar_wait<true>(&bar_d, it & 1);
             tc_fence_after();
             if (st4) p.timeline[it * 8 + 4] = clock64();
-#pragma unroll 1
-            for (int j = 0; j < J; ++j) {
-                const int n0 = 256 * j + 128 * hl + 32 * cq;
-                uint32_t v[32];
-                tmem_ld32(lane_tm + (uint32_t)(j == 0 ? XCOL : YCOL2), v);
-                tmem_ld_wait();
-                const uint32_t rowaddr = frow + (n0 >> 6) * STILE;
-                float m = 0.f;
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) m = fmaxf(m, fmaxf(fabsf(__uint_as_float(v[i])), fabsf(__uint_as_float(v[i + 1]))));
-                const bool big = __any_sync(0xffffffffu, m * es.dsc > 3.0f);
-                if (n0 + 32 <= p.N) {
-                    if (!big) tc2_epilogue32<DBG, false, false>(p, v, it, n0, b, live, rowaddr, fx, lo_delta, P, es);
-                    else tc2_epilogue32<DBG, true, false>(p, v, it, n0, b, live, rowaddr, fx, lo_delta, P, es);
-                } else {
-                    tc2_epilogue32<DBG, true, true>(p, v, it, n0, b, live, rowaddr, fx, lo_delta, P, es);
-                }
-                fence_async_smem();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) { if (H1 && j == 0) arrive0(&bar_tA, r_tA); else arrive0(&bar_tB, r_tB); }
-                if (st4) p.timeline[it * 8 + 5 + j] = clock64();
+            if (two) {
+                block16(it, 16 * cq, 128 * hl + 16 * cq);
+                publish(&bar_tA0, r_tA0);
+                if (st4) p.timeline[it * 8 + 5] = clock64();
+                block16(it, 64 + 16 * cq, 128 * hl + 64 + 16 * cq);
+                publish(&bar_tA1, r_tA1);
+                block32(it, 128 + 32 * cq, 256 + 128 * hl + 32 * cq);
+            } else {
+                block32(it, 32 * cq, 128 * hl + 32 * cq);
             }
+            publish(&bar_tB, r_tB);
+            if (st4) p.timeline[it * 8 + 6] = clock64();
         }
     }
     tc_fence_before();

@@ -28,6 +28,9 @@ def device_noise_uniforms(seed, B, steps, N, first_frame=0):
     odd = (n & np.uint64(1)).astype(bool)
     k = _mix32(lo + ((np.uint64(0x9E3779B9) * b) & _M))
     k = _mix32(k ^ ((((r * np.uint64(0x85EBCA6B)) & _M) + hi) & _M))
-    h = _mix32(k + (((n >> np.uint64(1)) * np.uint64(0xC2B2AE35)) & _M))
+    x = (k + (((n >> np.uint64(1)) * np.uint64(0xC2B2AE35)) & _M)) & _M
+    x ^= x >> np.uint64(16)
+    m = x * np.uint64(0x9E3779B1)                      # 32 x 32 -> 64 bit product, high word folded onto the low
+    h = (m & _M) ^ (m >> np.uint64(32))
     bits = np.where(odd, h >> np.uint64(16), h & np.uint64(0xFFFF))
     return bits.astype(np.float64) / 65536.0
