@@ -30,6 +30,7 @@
 // 2 weight-ring producer, 3 MMA issuer + TMEM owner, 4-19 epilogue
 // (TMEM -> tanh -> noise -> fp16 hi/lo -> swizzled state tile).
 #include <algorithm>
+#include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through the runtime)
 #include "common.cuh"
 #include <cuda_fp16.h>
 
@@ -724,6 +725,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// 2-D tiled bulk tensor copy global -> this CTA's shared memory whose completion (complete_tx) is
+// signalled on an mbarrier of EITHER CTA of the pair (cta_group::2): both halves of a ring item report
+// to the issuer's barrier in CTA 0, no relay hop.
+__device__ __forceinline__ void tma2_g2s(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t cluster_mbar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(cluster_mbar) : "memory");
+}
+
 // (a, b) pre-scaled -> packed fp16 hi pair and lo pair
 __device__ __forceinline__ void split_pair(uint64_t xs, uint32_t &h, uint32_t &l) {
     float xa, xb, la, lb;
@@ -853,7 +862,8 @@ __device__ __forceinline__ void tc2_epilogue_blk(const TcParams &p, const uint32
 constexpr int TC2_THREADS = 640;
 
 template <bool DBG, bool TL>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_predict_tc2(const TcParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
+esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_y) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_d, bar_y, bar_tA0, bar_tA1, bar_tD1, bar_tB, bar_yready;
     __shared__ uint32_t s_tmem;
@@ -877,7 +887,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_
     const bool tl0 = TL && p.timeline && blockIdx.x == 0;
 
     if (tid == 0) {
-        for (int i = 0; i < NST; ++i) { mbar_init(&bar_full[i], rank == 0 ? 2 : 1); mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < NST; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
         mbar_init(&bar_d, 1);
         mbar_init(&bar_y, 1);
         mbar_init(&bar_yready, 2 * 2);                       // frame warps of both CTAs (used in CTA 0)
@@ -1030,23 +1040,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_
         }
     } else if (warp == 2) {
         // ============ producer: this CTA's half of every tile, every step ============
+        // Tensor-map bulk copies (rows of 512 bytes of the pre-swizzled images) that complete on CTA 0's
+        // full barrier; CTA 0's producer posts the byte count of both halves.
         if (elect_one()) {
-            const unsigned char *wimg = p.weights;
-            const unsigned char *yimg = p.readouts + (size_t)g * gm.readout_bytes;
             const uint32_t ybytes = (uint32_t)UO * 128u;
+            const int yrow0 = (int)(((size_t)g * gm.readout_bytes) / 512);
+            const uint32_t ring_s = smem_u32(ring);
+            uint32_t r_full[NST];
+#pragma unroll
+            for (int i = 0; i < NST; ++i) r_full[i] = mapa_u32(smem_u32(&bar_full[i]), 0);
             uint32_t item = 0;
             // weight tile (slab s, chunk c, half h) [+ in CTA 0 the readout rows of (c, h)] into the next slot
             auto fetch = [&](int s, int c, int h, bool y) {
                 const int slot = item % NST;
                 mbar_wait<false>(&bar_empty[slot], ((item / NST) & 1) ^ 1);
-                unsigned char *dst = ring + (size_t)slot * SLOT2;
-                y = y && rank == 0;
-                mbar_expect_tx(&bar_full[slot], SLOT + (y ? ybytes : 0u));
-                const unsigned char *src = wimg + ((size_t)(s * C + c) * 2 + h) * SLOT;
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4)            // four requests in flight per tile
-                    bulk_g2s(dst + q4 * (SLOT / 4), src + q4 * (SLOT / 4), SLOT / 4, &bar_full[slot]);
-                if (y) bulk_g2s(dst + SLOT, yimg + (size_t)(c * 2 + h) * YTILE, ybytes, &bar_full[slot]);
+                const uint32_t dst = ring_s + (uint32_t)slot * SLOT2;
+                if (rank == 0) mbar_expect_tx(&bar_full[slot], 2u * SLOT + (y ? ybytes : 0u));
+                tma2_g2s(dst, &map_w, 0, ((s * C + c) * 2 + h) * (SLOT / 512), r_full[slot]);
+                if (y && rank == 0) tma2_g2s(dst + SLOT, &map_y, 0, yrow0 + (c * 2 + h) * (YTILE / 512), r_full[slot]);
                 ++item;
             };
             auto chunk = [&](int j, int c) {          // the two items (hi, lo) of slab 2j + r, chunk c
@@ -1063,18 +1074,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) esn_
             }
         }
     } else if (warp == 3 && rank == 1) {
-        // ============ relay: tell the issuer in CTA 0 that this CTA's half has landed ============
-        if (elect_one()) {
-            const uint32_t total = (uint32_t)p.T * (2 * J * C) + 2 * (C - 1);
-            uint32_t r_full[NST];
-#pragma unroll
-            for (int i = 0; i < NST; ++i) r_full[i] = mapa_u32(smem_u32(&bar_full[i]), 0);
-            for (uint32_t item = 0; item < total; ++item) {
-                const int slot = item % NST;
-                mbar_wait<false>(&bar_full[slot], (item / NST) & 1);
-                mbar_arrive_cluster_relaxed(r_full[slot]);
-            }
-        }
+        // (CTA 1 has no issuer: its tensor core is driven from CTA 0)
     } else if (warp == 3) {
         // ============ MMA issuer (CTA 0): one thread drives both tensor cores ============
         if (elect_one()) {
@@ -1305,9 +1305,34 @@ extern "C" int esn_tc_predict(const esn_tc_predict_args *a, void *stream) {
         // CTA-pair kernel (cta_group::2): 128 frames per 2-CTA cluster
         const int grid2 = 2 * ((a->B + PF - 1) / PF);
         const size_t smem = (size_t)2 * gm.C * STILE + (size_t)NST * SLOT2 + 1024;
+        // tensor maps over the two images, as rows of 512 bytes (they are pre-swizzled: plain copies)
+        typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static encode_fn encode = nullptr;
+        if (!encode) {
+            void *fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            ESN_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+            if (!fn || qres != cudaDriverEntryPointSuccess) return ESN_E_UNSUPPORTED;
+            encode = (encode_fn)fn;
+        }
+        auto make_map = [&](CUtensorMap *m, const void *base, size_t bytes, unsigned box_rows) -> bool {
+            const cuuint64_t dims[2] = {256, (cuuint64_t)(bytes / 512)};
+            const cuuint64_t strides[1] = {512};
+            const cuuint32_t box[2] = {256, box_rows}, estr[2] = {1, 1};
+            return encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        };
+        if (a->n_groups <= 0) return ESN_E_BADARG;
+        CUtensorMap map_w, map_y;
+        if (!make_map(&map_w, a->weights, gm.weight_bytes, SLOT / 512) ||
+            !make_map(&map_y, a->readouts, (size_t)a->n_groups * gm.readout_bytes, (a->n_out <= 8 ? 8u : 16u) * 128u / 512u))
+            return ESN_E_BADARG;
         auto launch = [&](auto kern) -> int {
             ESN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid2, TC2_THREADS, smem, (cudaStream_t)stream>>>(p);
+            kern<<<grid2, TC2_THREADS, smem, (cudaStream_t)stream>>>(p, map_w, map_y);
             return 0;
         };
         int rc;
