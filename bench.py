@@ -199,7 +199,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def bind_to_gpu_numa(local):
@@ -282,11 +282,12 @@ def run_gpu(args):
     pil_y[:, d:, :] = torch.view_as_real(pil["x_cp"]).reshape(G, Nsub + cp, no)      # teacher delayed by d rows
     W_out_parts = []
     fit_ms = 0.0
-    for g0 in range(0, G, 64):
+    fit_prec = args.fit_precision
+    for g0 in range(0, G, 128):
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        ext = res.harvest(pil_u[g0:g0 + 64], pil_y[g0:g0 + 64], precision="fp64", seed=7 + g0)
-        w, info = res.train_readout(ext, pil_y[g0:g0 + 64], TRANSIENT)
+        ext = res.harvest(pil_u[g0:g0 + 128], pil_y[g0:g0 + 128], precision=fit_prec, seed=7 + g0)
+        w, info = res.train_readout(ext, pil_y[g0:g0 + 128], TRANSIENT)
         f1.record()
         torch.cuda.synchronize()
         fit_ms += f0.elapsed_time(f1)
@@ -389,6 +390,39 @@ def run_gpu(args):
     e2e_ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
 
+    # ---- readout training throughput: a large batch of pilots (one per coherence block), harvest on the
+    # tensor cores (teacher-forced), fp64 dual Gram + Cholesky, UMMA images of the new readouts
+    fit = None
+    if path == "tc" and args.fit_pilots > 0:
+        Gf = args.fit_pilots
+        reps = -(-Gf // G)
+        fu = pil_u.to(torch.float32).repeat(reps, 1, 1)[:Gf].contiguous()
+        fy = pil_y.to(torch.float32).repeat(reps, 1, 1)[:Gf].contiguous()
+        su_fit = res.input_scale_exponent(frames)
+        best = None
+        for rep in range(3):
+            f0, f1, f2 = ev(), ev(), ev()
+            f0.record(stream)
+            ext = res.harvest(fu, fy, precision="tc", seed=3 + rep)
+            f1.record(stream)
+            w, info = res.train_readout(ext, fy, TRANSIENT)
+            res.tc_prepare(w, su_fit, y_absmax=y_absmax)
+            f2.record(stream)
+            torch.cuda.synchronize()
+            t = (f0.elapsed_time(f1), f1.elapsed_time(f2))
+            if best is None or sum(t) < sum(best):
+                best = t
+            assert int(info.abs().max()) == 0
+            del ext, w
+        fit_total = D.max_over_ranks(sum(best), dev)
+        us_fit = fit_total * 1e3 / Gf                          # microseconds per trained readout
+        us_det = (ms / args.steps) * 1e3 / B                   # microseconds per detected frame
+        fit = {"pilots_per_batch": Gf, "ms_per_batch": fit_total, "harvest_ms": best[0], "solve_ms": best[1],
+               "fits_per_s": world * Gf / (fit_total * 1e-3),
+               "what": "teacher-forced harvest on the tensor cores + fp64 dual Gram (512x512) + Cholesky + readout images",
+               "fit_detect_symbols_per_s": world * per_group / ((us_fit + per_group * us_det) * 1e-6),
+               "block": f"1 pilot + {per_group} data frames per coherence block (reference L = 19)"}
+        del fu, fy
     os.sched_setaffinity(0, all_cpus)            # the CPU-baseline leg uses every host core
     counts.zero_()
     step(frames)
@@ -415,7 +449,7 @@ def run_gpu(args):
                    "frames_per_coherence_block": per_group, "readouts_per_gpu": G, "state_noise": "0.001 device counter stream",
                    "link": f"block-fading Rayleigh 8 taps, 16-QAM, Eb/N0 {ebno_db} dB, soft PA clip 3 dB, frames synthesised on the device",
                    "uncoded_ber_esn": bit_errors / total_bits,
-                   "readout_training": f"{G} pilots/GPU, fp64 harvest + Gram + Cholesky on the device, {fit_ms:.1f} ms (untimed setup)",
+                   "readout_training": f"{G} pilots/GPU, {fit_prec} harvest + fp64 Gram + Cholesky on the device, {fit_ms:.1f} ms (untimed setup)",
                    "recurrence_path": ("tcgen05 fp16 hi/lo split x3, fp32 accumulate in TMEM" if path == "tc" else "simt_" + args.precision), "parallelism": f"frames sharded x{world}",
                    "l2": f"inputs {frames.numel() * 4 / 2**20:.0f} MiB + outputs per step exceed the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_in.numel() * 4),
@@ -432,13 +466,32 @@ def run_gpu(args):
                      "peak_source": pk["src"] + " bf16 sustained", "kernel_ms": kms,
                      "algorithmic_flop_per_symbol": algorithmic_flops_per_symbol(),
                      "kernel_share_of_step": kms / (ms / args.steps)},
+        "fit": fit,
         "cpu_baseline": cpu,
         "clocks": clk.summary(),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's original stdout; everything else any library prints
+    (NCCL's version banner, warnings) has been routed to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)                                # C-level and Python prints -> stderr from here on
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -452,6 +505,9 @@ def main():
     ap.add_argument("--ref-frames-per-worker", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ebno", type=float, default=15.0, help="Eb/N0 (dB) of the simulated link")
+    ap.add_argument("--fit-precision", default="fp64", choices=["fp64", "fp32", "tc"],
+                    help="harvest precision of the readouts the timed detection uses")
+    ap.add_argument("--fit-pilots", type=int, default=1184, help="pilots per batch of the fit-throughput leg (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -293,6 +293,8 @@ struct TcParams {
     float *ext_out;                          // [B][T][N+n_in] or null
     float *y_out;                            // [B][T-transient][n_out]
     long long *timeline;                     // [T+1][8] SM-clock stamps of CTA 0 (profiling aid) or null
+    const float *teacher;                    // pair kernel, harvest mode: [B][T][n_out] raw teachers fed back (or null)
+    int steps, row0;                         // recurrence steps and first input row: T, 0 (predict) / T-1, 1 (harvest)
 };
 
 // DBG = host noise tensor and/or extended-state output requested (parity runs)
@@ -774,6 +776,7 @@ __device__ __forceinline__ void tc2_epilogue_blk(const TcParams &p, const uint32
 #pragma unroll
     for (int g8 = 0; g8 < NE / 8; ++g8) {                 // granule of 8 neurons
         uint32_t hi2[4], lo2[4];
+        float ex[8];
 #pragma unroll
         for (int pr = 0; pr < 4; ++pr) {                  // pair of neurons
             const int jj = g8 * 8 + pr * 2, n = n0 + jj;
@@ -794,7 +797,7 @@ __device__ __forceinline__ void tc2_epilogue_blk(const TcParams &p, const uint32
                     float u[2];
 #pragma unroll
                     for (int e = 0; e < 2; ++e)
-                        u[e] = (live && n + e < p.N) ? p.noise[((size_t)b * p.T + it) * p.N + n + e] : 0.5f;
+                        u[e] = (live && n + e < p.N) ? p.noise[((size_t)b * p.steps + it) * p.N + n + e] : 0.5f;
                     nt = pk2(fmaf(u[0], es.ampf, -es.ampoffs), fmaf(u[1], es.ampf, -es.ampoffs));
                 } else {
                     const uint32_t hb = esn_fold32(hkey + (uint32_t)(jj >> 1) * 0xC2B2AE35U);
@@ -812,13 +815,20 @@ __device__ __forceinline__ void tc2_epilogue_blk(const TcParams &p, const uint32
                 if (PAD && n + 1 >= p.N) xb = 0.f;
                 xs = pk2(xa, xb);
             }
-            if (DBG && p.ext_out && live) {
-                float xa, xb;
-                un2(xs, xa, xb);
-                if (n < p.N) p.ext_out[((size_t)b * p.T + it) * P + n] = xa * (1.0f / XS);
-                if (n + 1 < p.N) p.ext_out[((size_t)b * p.T + it) * P + n + 1] = xb * (1.0f / XS);
-            }
+            if (DBG) un2(xs, ex[2 * pr], ex[2 * pr + 1]);
             split_pair(xs, hi2[pr], lo2[pr]);
+        }
+        if (DBG && p.ext_out && live) {                   // this frame's 8 new states: 32 contiguous bytes of E
+            const int n = n0 + g8 * 8;
+            float *dst = p.ext_out + ((size_t)b * p.T + it + p.row0) * P + n;
+            if (!PAD && (P & 3) == 0) {
+                reinterpret_cast<float4 *>(dst)[0] = make_float4(ex[0] * (1.0f / XS), ex[1] * (1.0f / XS), ex[2] * (1.0f / XS), ex[3] * (1.0f / XS));
+                reinterpret_cast<float4 *>(dst)[1] = make_float4(ex[4] * (1.0f / XS), ex[5] * (1.0f / XS), ex[6] * (1.0f / XS), ex[7] * (1.0f / XS));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (n + i < p.N) dst[i] = ex[i] * (1.0f / XS);
+            }
         }
         const uint32_t a = rowaddr + ((uint32_t)((g0 + g8) ^ fx) << 4);
         sts_v4(a, hi2[0], hi2[1], hi2[2], hi2[3]);
@@ -885,6 +895,9 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
     const int g = p.group_ids ? p.group_ids[min(pair0, p.B - 1)] : 0;
     const int P = p.N + p.n_in;
     const bool tl0 = TL && p.timeline && blockIdx.x == 0;
+    const bool harvest = p.teacher != nullptr;               // teacher-forced: y_{t-1} comes from the teacher rows
+    const int nst = p.steps;                                 // recurrence steps
+    const int n_it = harvest ? nst : nst + 1;                // predict: one more pass for the last readout
 
     if (tid == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
@@ -905,7 +918,7 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
     // state tiles and ring start as zeros (the readout rows of CTA 1's slots are never written)
     for (int i = tid; i < (2 * C * STILE + NST * SLOT2) / 16; i += TC2_THREADS)
         reinterpret_cast<uint4 *>(base)[i] = make_uint4(0, 0, 0, 0);
-    {
+    if (!harvest) {
         const float *tab = reinterpret_cast<const float *>(p.readouts + (size_t)g * gm.readout_bytes + gm.readout_tile_bytes);
         for (int i = tid; i < 16 * 24; i += TC2_THREADS) s_wu[i] = tab[i];
     }
@@ -940,7 +953,7 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
         const bool live = b < p.B;
         const uint32_t row = smem_u32(st_hi) + gm.ca * STILE + (f >> 3) * 1024 + (f & 7) * 128;
         const int fx = f & 7, ng = gm.UW >> 3, yg = gm.YO >> 3;
-        const float su = ldexpf(1.0f, p.su), sy = ldexpf(1.0f, p.sy), ys = p.yscale[g];
+        const float su = ldexpf(1.0f, p.su), sy = ldexpf(1.0f, p.sy), ys = harvest ? 0.f : p.yscale[g];
         const uint32_t lane_tm = tmem + ((uint32_t)(warp * 32) << 16) + RC;
         float cur[24], nxt[24], ut[16];   // u_it, u_{it+1} (scaled 2^su), W_out_u u_{it-1} (accumulator units)
 #pragma unroll
@@ -975,6 +988,38 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
 #pragma unroll
             for (int j = 0; j < 24; ++j) cur[j] = nxt[j];
         };
+        if (harvest) {
+            // ---- teacher-forced (ESN.fit, libs/pyESN.py:179-182): step it rewrites x from input row it + 1
+            // and teacher row it; no readout.  ext row 0 = [0, u_0] (its state part is zeroed by the epilogue).
+            float tn[16];
+            auto load_teacher = [&](int r) {
+#pragma unroll
+                for (int o = 0; o < 16; ++o) {
+                    float v = 0.f;
+                    if (o < p.n_out && live && p.feedback)
+                        v = (p.teacher[((size_t)b * p.T + r) * p.n_out + o] * p.t_scale[o] + p.t_shift[o]) * sy;
+                    tn[o] = v;
+                }
+            };
+            auto publish_step = [&]() {
+                write_inputs();
+                store8(yg, tn);
+                if (UO == 16) store8(yg + 1, tn + 8);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) { arrive0(&bar_tB, r_tB); arrive0(&bar_yready, r_yr); }
+            };
+            load_row(0);
+            load_row(1);
+            load_teacher(0);
+            publish_step();
+            for (int it = 0; it < nst; ++it) {
+                const bool more = it + 1 < nst;
+                if (more) { load_row(it + 2); load_teacher(it + 1); }
+                mbar_wait<true>(&bar_d, it & 1);
+                if (more) publish_step();
+            }
+        } else {
         load_row(0);
         write_inputs();
         fence_async_smem();
@@ -1038,6 +1083,7 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
             __syncwarp();
             if (lane == 0) arrive0(&bar_tB, r_tB);
         }
+        }
     } else if (warp == 2) {
         // ============ producer: this CTA's half of every tile, every step ============
         // Tensor-map bulk copies (rows of 512 bytes of the pre-swizzled images) that complete on CTA 0's
@@ -1055,6 +1101,7 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
                 const int slot = item % NST;
                 mbar_wait<false>(&bar_empty[slot], ((item / NST) & 1) ^ 1);
                 const uint32_t dst = ring_s + (uint32_t)slot * SLOT2;
+                y = y && !harvest;
                 if (rank == 0) mbar_expect_tx(&bar_full[slot], 2u * SLOT + (y ? ybytes : 0u));
                 tma2_g2s(dst, &map_w, 0, ((s * C + c) * 2 + h) * (SLOT / 512), r_full[slot]);
                 if (y && rank == 0) tma2_g2s(dst + SLOT, &map_y, 0, yrow0 + (c * 2 + h) * (YTILE / 512), r_full[slot]);
@@ -1063,8 +1110,8 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
             auto chunk = [&](int j, int c) {          // the two items (hi, lo) of slab 2j + r, chunk c
                 for (int h = 0; h < 2; ++h) fetch(2 * j + (int)rank, c, h, j == J - 1 && c < C - 1);
             };
-            for (int it = 0; it <= p.T; ++it) {
-                const bool last = it == p.T;
+            for (int it = 0; it < n_it; ++it) {
+                const bool last = it == nst;
                 if (two && !last) { chunk(0, 0); chunk(0, 2); chunk(0, 1); chunk(0, 3); }
                 for (int c = 0; c < C - 1; ++c) chunk(J - 1, c);
                 if (last) break;
@@ -1123,8 +1170,8 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
                     ++item;
                 }
             };
-            for (int it = 0; it <= p.T; ++it) {
-                const bool last = it == p.T;
+            for (int it = 0; it < n_it; ++it) {
+                const bool last = it == nst;
                 if (TL) tr_i = (it == 200) ? 0 : -1;
                 if (tl0) p.timeline[it * 8 + 0] = clock64();
                 if (two && !last) {
@@ -1224,7 +1271,15 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
             if (two) { arrive0(&bar_tA0, r_tA0); arrive0(&bar_tA1, r_tA1); arrive0(&bar_tD1, r_tD1); }
             arrive0(&bar_tB, r_tB);
         }
-        for (int it = 0; it < p.T; ++it) {
+        if (harvest && DBG && p.ext_out && live) {         // ext row 0: the state before the first step is zero
+            float *row = p.ext_out + (size_t)b * p.T * P;
+            for (int i = 0; i < 32; ++i) {
+                const int n = 128 * hl + 32 * cq + i;
+                if (n < p.N) row[n] = 0.f;
+                if (two && 256 + n < p.N) row[256 + n] = 0.f;
+            }
+        }
+        for (int it = 0; it < nst; ++it) {
             es.key = esn_noise_key(p.seed, (uint32_t)b, (uint32_t)it);
             mbar_wait<true>(&bar_d, it & 1);
             tc_fence_after();
@@ -1285,9 +1340,9 @@ extern "C" int esn_tc_predict(const esn_tc_predict_args *a, void *stream) {
     if (!a) return ESN_E_BADARG;
     if (a->B <= 0 || a->T <= 0 || a->transient < 0 || a->transient >= a->T) return ESN_E_BADARG;
     if (!esn_tc_supported(a->N, a->n_in, a->n_out)) return ESN_E_UNSUPPORTED;
-    if (!a->weights || !a->readouts || !a->yscale || !a->in || !a->in_scale || !a->in_shift || !a->t_scale ||
-        !a->t_shift || !a->y_out)
-        return ESN_E_BADARG;
+    const bool harvest = a->teacher != nullptr;
+    if (!a->weights || !a->in || !a->in_scale || !a->in_shift || !a->t_scale || !a->t_shift) return ESN_E_BADARG;
+    if (harvest ? (!a->ext_out || a->T < 2) : (!a->readouts || !a->yscale || !a->y_out)) return ESN_E_BADARG;
     TcParams p;
     p.B = a->B; p.T = a->T; p.N = a->N; p.n_in = a->n_in; p.n_out = a->n_out; p.transient = a->transient;
     p.feedback = a->feedback; p.su = a->su_exp; p.sy = a->sy_exp;
@@ -1297,6 +1352,9 @@ extern "C" int esn_tc_predict(const esn_tc_predict_args *a, void *stream) {
     p.in = a->in; p.in_scale = a->in_scale; p.in_shift = a->in_shift; p.t_scale = a->t_scale; p.t_shift = a->t_shift;
     p.group_ids = a->group_ids; p.x0 = a->x0; p.y0 = a->y0; p.noise = a->noise_uniforms;
     p.ext_out = a->ext_out; p.y_out = a->y_out; p.timeline = (long long *)a->timeline;
+    p.teacher = a->teacher;
+    p.steps = harvest ? a->T - 1 : a->T;
+    p.row0 = harvest ? 1 : 0;
     const TcGeom gm = tc_geom(a->N, a->n_in);
     const size_t smem = (size_t)2 * gm.C * STILE + (size_t)NST * SLOT + 1024;
     if (smem > 227 * 1024 - 1024) return ESN_E_TOOLARGE;
@@ -1325,10 +1383,11 @@ extern "C" int esn_tc_predict(const esn_tc_predict_args *a, void *stream) {
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
         };
-        if (a->n_groups <= 0) return ESN_E_BADARG;
+        if (!harvest && a->n_groups <= 0) return ESN_E_BADARG;
         CUtensorMap map_w, map_y;
-        if (!make_map(&map_w, a->weights, gm.weight_bytes, SLOT / 512) ||
-            !make_map(&map_y, a->readouts, (size_t)a->n_groups * gm.readout_bytes, (a->n_out <= 8 ? 8u : 16u) * 128u / 512u))
+        if (!make_map(&map_w, a->weights, gm.weight_bytes, SLOT / 512)) return ESN_E_BADARG;
+        if (harvest) map_y = map_w;                          // never dereferenced in harvest mode
+        else if (!make_map(&map_y, a->readouts, (size_t)a->n_groups * gm.readout_bytes, (a->n_out <= 8 ? 8u : 16u) * 128u / 512u))
             return ESN_E_BADARG;
         auto launch = [&](auto kern) -> int {
             ESN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1341,6 +1400,7 @@ extern "C" int esn_tc_predict(const esn_tc_predict_args *a, void *stream) {
         if (rc) return rc;
         return esn_launch_status();
     }
+    if (harvest) return ESN_E_UNSUPPORTED;                   // teacher-forced mode exists in the pair kernel only
     const int grid = (a->B + FT - 1) / FT;
     if (dbg) {
         ESN_CUDA_TRY(cudaFuncSetAttribute(esn_predict_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -285,9 +285,46 @@ class Reservoir:
         check(self.lib.esn_tc_predict(C.byref(a), _stream()), "esn_tc_predict")
         return (y, ext) if return_ext else y
 
+    def harvest_tc(self, inputs, teachers, noise_uniforms=None, seed=0):
+        """Teacher-forced harvesting on the tensor cores (CTA-pair kernel, N padded to
+        256 or 512).  Throughput mode: states carry the tensor-core path's ~1e-5
+        relative error, so W_out trained on them differs from the fp64 fit by more than
+        the 1e-4 parity bar (the noise regulariser itself moves states by ~1e-2); use
+        precision='fp64' where W_out parity is asserted."""
+        if not self.tc_supported() or self.tc_tile_frames() != 128:
+            raise EsnB200Error("tensor-core harvest needs the CTA-pair kernel (N padded to 256 or 512)")
+        inputs = self._as(inputs, torch.float32, 3)
+        teachers = self._as(teachers, torch.float32, 3)
+        B, T, n_in = inputs.shape
+        if n_in != self.n_in or tuple(teachers.shape) != (B, T, self.n_out):
+            raise ValueError(f"inputs [B,T,{self.n_in}] and teachers [B,T,{self.n_out}] expected")
+        aff = self._aff[ESN_F32]
+        y_absmax = float((teachers * aff["t_scale"] + aff["t_shift"]).abs().max().item())
+        su_exp, sy_exp = self.input_scale_exponent(inputs), self.output_scale_exponent(y_absmax)
+        a = _lib.TcPredictArgs()
+        a.B, a.T, a.N, a.n_in, a.n_out = B, T, self.N, self.n_in, self.n_out
+        a.transient, a.feedback = 0, int(self.teacher_forcing)
+        a.su_exp, a.sy_exp, a.n_groups = su_exp, sy_exp, 0
+        a.noise_amp, a.seed = self.noise, int(seed) & 0xFFFFFFFFFFFFFFFF
+        weights = self._tc_weights(su_exp, sy_exp)
+        a.weights, a.inp, a.teacher = ptr(weights), ptr(inputs), ptr(teachers)
+        a.in_scale, a.in_shift = ptr(aff["in_scale"]), ptr(aff["in_shift"])
+        a.t_scale, a.t_shift = ptr(aff["t_scale"]), ptr(aff["t_shift"])
+        if noise_uniforms is not None:
+            noise_uniforms = self._as(noise_uniforms, torch.float32, 3)
+            if tuple(noise_uniforms.shape) != (B, T - 1, self.N):
+                raise ValueError(f"noise_uniforms must be [{B},{T - 1},{self.N}]")
+            a.noise_uniforms = ptr(noise_uniforms)
+        ext = torch.empty((B, T, self.P), dtype=torch.float32, device=self.device)
+        a.ext_out = ptr(ext)
+        check(self.lib.esn_tc_predict(C.byref(a), _stream()), "esn_tc_predict(harvest)")
+        return ext
+
     def harvest(self, inputs, teachers, precision="fp64", noise_uniforms=None, seed=0):
         """Teacher-forced harvesting (libs/pyESN.py:179-182).  Returns the
         extended states E [B, T, N+n_in] = [x_n, u_n] (libs/pyESN.py:189)."""
+        if precision == "tc":
+            return self.harvest_tc(inputs, teachers, noise_uniforms=noise_uniforms, seed=seed)
         ext, _ = self._run(MODE_HARVEST, dtype_code(precision), inputs, teachers=teachers,
                            noise_uniforms=noise_uniforms, seed=seed)
         return ext

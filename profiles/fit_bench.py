@@ -1,6 +1,8 @@
+"""Readout-training throughput at cfg3 (4x8, N=512, T=522): harvest (fp64 / fp32 SIMT, tensor cores) and
+Gram + Cholesky + readout, per batch of G pilots.  python profiles/fit_bench.py [G ...]"""
 import os, sys, time
 import numpy as np, torch
-ROOT="/root/repo"
+ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "esn-ofdm-mimo_b200"))
 from esn_b200 import Reservoir
 N, ni, no, T = 512, 16, 8, 522
@@ -11,7 +13,7 @@ def ev(): return torch.cuda.Event(enable_timing=True)
 for G in (int(a) for a in (sys.argv[1:] or (74, 592, 1184))):
     u = torch.randn(G, T, ni, device="cuda", dtype=torch.float64)
     y = torch.randn(G, T, no, device="cuda", dtype=torch.float64)*1e-2
-    for prec in ("fp64", "fp32"):
+    for prec in ("fp64", "fp32", "tc"):
         for rep in range(2):
             e=[ev() for _ in range(4)]
             e[0].record(); ext = res.harvest(u, y, precision=prec, seed=1); e[1].record()

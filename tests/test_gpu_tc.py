@@ -152,3 +152,58 @@ def test_tc_rejects_what_it_cannot_do():
     rng, Ws, aff, big = _setup(640, 4, 4, seed=2)
     with pytest.raises(EsnB200Error):
         big.predict(_cuda(rng.randn(4, 6, 4)), _cuda(rng.randn(1, 4, 644)), precision="tc")
+
+
+def test_tc_harvest_states_match_oracle():
+    """Teacher-forced harvest on the tensor cores (cfg3 shape): states within the 1e-5 bar of the
+    oracle's fit() states on host-supplied noise, ext row 0 = [0, u_0], input block exact."""
+    c = cases.ESN_CASES["cfg3_4x8_n512"]
+    kw = cases.esn_kwargs(c)
+    o = orc.OracleESN(**kw)
+    from esn_b200 import Reservoir
+    eng = Reservoir(o.W, o.W_in, o.W_feedb, kw["input_scaling"], kw["input_shift"],
+                    kw["teacher_scaling"], kw["teacher_shift"], c["noise"], c["teacher_forcing"])
+    B, T, N = 130, c["T"], c["n_res"]                       # one full pair tile + a ragged one
+    us = np.stack([cases.esn_io(c, i % 5)[0] for i in range(B)])
+    ys = np.stack([cases.esn_io(c, i % 5)[1] for i in range(B)])
+    uni = np.random.RandomState(78).rand(B, T - 1, N)
+    ext = eng.harvest(_cuda(us), _cuda(ys), precision="tc", noise_uniforms=_cuda(uni)).double().cpu().numpy()
+    worst = 0.0
+    for b in (0, 63, 64, 127, 128, 129):
+        r = orc.fit(o.W, o.W_in, o.W_feedb, us[b], ys[b], c["transient"], c["noise"], uni[b],
+                    input_scaling=kw["input_scaling"], input_shift=kw["input_shift"],
+                    teacher_scaling=kw["teacher_scaling"], teacher_shift=kw["teacher_shift"],
+                    teacher_forcing=c["teacher_forcing"])
+        worst = max(worst, rel_err(ext[b, :, :N], r["states"]))
+        assert rel_err(ext[b, :, N:], r["in_s"]) < 1e-6
+        assert np.all(ext[b, 0, :N] == 0)
+    assert worst < 1e-5, worst
+    print("tc harvest worst state err %.2e" % worst)
+
+
+def test_tc_harvest_fit_detects_like_fp64_fit():
+    """Throughput-mode training: W_out from tensor-core states (device noise) drives a detector whose
+    outputs on fresh frames stay within 2e-3 of those of the fp64-trained readout -- the difference the
+    1e-3 state-noise regulariser itself produces between two reference fits is larger."""
+    c = cases.ESN_CASES["cfg3_4x8_n512"]
+    kw = cases.esn_kwargs(c)
+    o = orc.OracleESN(**kw)
+    from esn_b200 import Reservoir
+    eng = Reservoir(o.W, o.W_in, o.W_feedb, kw["input_scaling"], kw["input_shift"],
+                    kw["teacher_scaling"], kw["teacher_shift"], c["noise"], c["teacher_forcing"])
+    G = 4
+    us = _cuda(np.stack([cases.esn_io(c, i)[0] for i in range(G)]))
+    ys = _cuda(np.stack([cases.esn_io(c, i)[1] for i in range(G)]))
+    ext64 = eng.harvest(us, ys, precision="fp64", seed=5)
+    exttc = eng.harvest(us, ys, precision="tc", seed=5)
+    assert rel_err(exttc.double().cpu().numpy(), ext64.cpu().numpy()) < 1e-5
+    W64, i64 = eng.train_readout(ext64, ys, c["transient"])
+    Wtc, itc = eng.train_readout(exttc, ys, c["transient"])
+    assert int(i64.abs().max()) == 0 and int(itc.abs().max()) == 0
+    fresh = _cuda(np.stack([cases.esn_io(c, 10 + i)[0] for i in range(G)]))
+    gid = torch.arange(G, dtype=torch.int32, device="cuda")
+    y64 = eng.predict(fresh, W64, transient=c["transient"], group_ids=gid, precision="fp64", seed=9).cpu().numpy()
+    ytc = eng.predict(fresh, Wtc, transient=c["transient"], group_ids=gid, precision="fp64", seed=9).cpu().numpy()
+    d = rel_err(ytc, y64)
+    print("detector outputs, tc-trained vs fp64-trained readout: %.2e" % d)
+    assert d < 2e-3
