@@ -57,12 +57,18 @@ class HelpFunc():
 
         scores = np.zeros(table.shape[0])
         ref = x_CP[IsiDuration - 1:, :]
+        io = [build(row) for row in range(table.shape[0])]
+        if hasattr(esn, "fit_predict_many"):
+            # all table rows in one batched harvest / solve / predict (same noise order, same results)
+            outs = esn.fit_predict_many([(ein, eout, lo[row] + CyclicPrefixLen) for row, (ein, eout) in enumerate(io)])
+        else:
+            outs = []
+            for row, (ein, eout) in enumerate(io):
+                esn.fit(ein, eout, lo[row] + CyclicPrefixLen)
+                outs.append(esn.predict(ein, lo[row] + CyclicPrefixLen, continuation=False))
         for row in range(table.shape[0]):
             dl = table[row]
-            ein, eout = build(row)
-            forget = lo[row] + CyclicPrefixLen
-            esn.fit(ein, eout, forget)
-            out = esn.predict(ein, forget, continuation=False)
+            out = outs[row]
             for s in range(2):
                 a, b = dl[2 * s] - lo[row], dl[2 * s + 1] - lo[row]
                 est = out[a:a + N + 1, 2 * s] + 1j * out[b:b + N + 1, 2 * s + 1]

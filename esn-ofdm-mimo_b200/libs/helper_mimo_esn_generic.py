@@ -20,13 +20,9 @@ def _pack(y_CP, x_CP, d, T, N_t, N_r):
     return X_in, X_out
 
 
-def _score(esn, d, CyclicPrefixLen, N, N_t, N_r, IsiDuration, y_CP, x_CP):
-    """fit + predict at delay d and the reference's NMSE (reference :40-56,
-    including its habit of slicing the already-trimmed prediction at [d:d+N+1])."""
-    X_in, X_out = _pack(y_CP, x_CP, d, N + CyclicPrefixLen, N_t, N_r)
-    nForget = d + CyclicPrefixLen
-    esn.fit(X_in, X_out, nForget)
-    pred = esn.predict(X_in, nForget, continuation=False)
+def _nmse(pred, d, N, N_t, IsiDuration, x_CP):
+    """The reference's NMSE of a prediction at delay d (reference :47-56, including its
+    habit of slicing the already-trimmed prediction at [d:d+N+1])."""
     x_true = x_CP[IsiDuration - 1:, :N_t]
     seg = pred[d:d + N + 1]
     M = min(seg.shape[0], x_true.shape[0])
@@ -36,7 +32,16 @@ def _score(esn, d, CyclicPrefixLen, N, N_t, N_r, IsiDuration, y_CP, x_CP):
         for tx in range(N_t):
             num = np.linalg.norm(x_hat[:, tx] - x_true[:M, tx]) ** 2
             nmse += num / (np.linalg.norm(x_true[:M, tx]) ** 2 + 1e-12)
-    return nmse, X_in, X_out, nForget
+    return nmse
+
+
+def _score(esn, d, CyclicPrefixLen, N, N_t, N_r, IsiDuration, y_CP, x_CP):
+    """fit + predict at delay d and its NMSE (reference :40-56)."""
+    X_in, X_out = _pack(y_CP, x_CP, d, N + CyclicPrefixLen, N_t, N_r)
+    nForget = d + CyclicPrefixLen
+    esn.fit(X_in, X_out, nForget)
+    pred = esn.predict(X_in, nForget, continuation=False)
+    return _nmse(pred, d, N, N_t, IsiDuration, x_CP), X_in, X_out, nForget
 
 
 def trainMIMOESN_generic(esn, DelayFlag, Min_Delay, Max_Delay,
@@ -54,8 +59,16 @@ def trainMIMOESN_generic(esn, DelayFlag, Min_Delay, Max_Delay,
         nmse, ESN_input, ESN_output, nForgetPoints = _score(esn, d, *args)
     else:
         nmse, chosen = 1e9, None
-        for cand in range(Min_Delay, Max_Delay + 1):
-            s, xi, xo, nf = _score(esn, cand, *args)
+        cands = list(range(Min_Delay, Max_Delay + 1))
+        if hasattr(esn, "fit_predict_many"):
+            # every candidate delay in one batched harvest / solve / predict (same noise order, same results)
+            io = [_pack(y_CP, x_CP, c, N + CyclicPrefixLen, N_t, N_r) for c in cands]
+            preds = esn.fit_predict_many([(xi, xo, c + CyclicPrefixLen) for (xi, xo), c in zip(io, cands)])
+            scored = [(_nmse(p, c, N, N_t, IsiDuration, x_CP), xi, xo, c + CyclicPrefixLen)
+                      for p, (xi, xo), c in zip(preds, io, cands)]
+        else:
+            scored = [_score(esn, c, *args) for c in cands]
+        for cand, (s, xi, xo, nf) in zip(cands, scored):
             if s < nmse:
                 nmse, chosen = s, (xi, xo, nf, cand)
         ESN_input, ESN_output, nForgetPoints, d = chosen

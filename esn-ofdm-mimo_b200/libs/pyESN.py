@@ -186,6 +186,61 @@ class ESN():
         import torch
         return y[0].to(torch.float64).cpu().numpy()
 
+    def fit_predict_many(self, cases):
+        """Batched form of the trainers' delay scan (reference
+        libs/helper_mimo_esn_generic.py:67-81, libs/HelpFunc.py:109-154): for every
+        (inputs, outputs, transient) in `cases`, in order, the reference calls
+        fit(inputs, outputs, transient) and then predict(inputs, transient,
+        continuation=False).  Here all candidates go through ONE batched harvest, ONE
+        batched Gram + Cholesky and ONE batched predict launch.  The state noise is drawn
+        from `random_state_` in exactly the reference's order (fit rows, then predict rows,
+        candidate after candidate), so results equal the sequential calls.  Returns the list
+        of predictions; W_out / laststate / lastoutput end up as after the last fit."""
+        import torch
+        cases = [(_as_2d(i), _as_2d(o), int(t)) for i, o, t in cases]
+        n, N = len(cases), self.n_reservoir
+        Ts = [c[0].shape[0] for c in cases]
+        ms = {T - c[2] for T, c in zip(Ts, cases)}
+        if n == 0:
+            return []
+        if len(ms) != 1 or min(Ts) < 2:                # ragged row windows: plain sequential calls
+            out = []
+            for i, o, t in cases:
+                self.fit(i, o, t)
+                out.append(self.predict(i, t, continuation=False))
+            return out
+        m, Tp = ms.pop(), max(Ts)
+        X_in = np.zeros((n, Tp, self.n_inputs))
+        X_out = np.zeros((n, Tp, self.n_outputs))
+        uni_fit = np.full((n, Tp - 1, N), 0.5)         # 0.5 = no noise on the zero-padded tail
+        uni_pred = np.full((n, Tp, N), 0.5)
+        for k, (i, o, t) in enumerate(cases):
+            T = Ts[k]
+            X_in[k, :T], X_out[k, :T] = i, o
+            uni_fit[k, :T - 1] = self.random_state_.rand(T - 1, N)
+            uni_pred[k, :T] = self.random_state_.rand(T, N)
+        eng = self._engine()
+        noisy = self.noise != 0
+        ext = eng.harvest(X_in, X_out, precision=self.precision, noise_uniforms=uni_fit if noisy else None)
+        dev = ext.device
+        rows = torch.tensor([[c[2] + r for r in range(m)] for c in cases], device=dev)       # [n, m]
+        sel = torch.arange(n, device=dev)[:, None]
+        teach = torch.from_numpy(X_out).to(dev)
+        W_out, info = eng.train_readout(ext[sel, rows].contiguous(), teach[sel, rows].contiguous(), 0)
+        if int(info.abs().max()) != 0:
+            bad = int(torch.nonzero(info)[0])
+            raise np.linalg.LinAlgError(
+                f"readout Gram matrix of candidate {bad} is not positive definite (pivot {int(info[bad])})")
+        y = eng.predict(X_in, W_out, transient=0, group_ids=torch.arange(n, dtype=torch.int32, device=dev),
+                        precision=self.precision, noise_uniforms=uni_pred if noisy else None)
+        y = y.to(torch.float64).cpu().numpy()
+        last = n - 1
+        self.W_out = W_out[last].cpu().numpy()
+        self.laststate = ext[last, Ts[last] - 1, :N].to(torch.float64).cpu().numpy()
+        self.lastinput = cases[last][0][-1, :]
+        self.lastoutput = self._scale_teacher(cases[last][1])[-1, :]
+        return [y[k, cases[k][2]:Ts[k]] for k in range(n)]
+
     # ---- additive batched API (torch CUDA tensors) ------------------------
     def fit_batched(self, inputs, outputs, transient=0, precision="fp64", noise_uniforms=None,
                     seed=0, shared=False):

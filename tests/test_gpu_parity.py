@@ -85,6 +85,30 @@ def test_generic_trainer_matches_reference_golden(golden, name, flag):
     assert rel_err(det, golden[key + "/detect"]) < 1e-4
 
 
+def test_batched_delay_scan_equals_sequential_calls():
+    """ESN.fit_predict_many (one batched harvest / solve / predict for all candidate delays) returns what
+    the reference's sequential fit + predict loop returns on the same seed, and leaves the same state."""
+    from pyESN import ESN
+    from helper_mimo_esn_generic import _pack
+    c = cases.TRAINER_CASES["gen_2x2"]
+    blk = orc.synth_block(c["seed"], c["N"], c["N_t"], c["N_r"], c["m"], c["ebno"], 2, isi_duration=c["isi"])
+    cp = c["isi"] - 1
+    y_CP, x_CP = blk["pilot"]["y_CP"], blk["pilot"]["x_CP"]
+    cand = [0, 1, 2, 3, 5]
+    io = [_pack(y_CP, x_CP, d, c["N"] + cp, c["N_t"], c["N_r"]) for d in cand]
+    a = ESN(**cases.trainer_esn_kwargs(c, blk["var_x"]))
+    b = ESN(**cases.trainer_esn_kwargs(c, blk["var_x"]))
+    seq = []
+    for (xi, xo), d in zip(io, cand):
+        a.fit(xi, xo, d + cp)
+        seq.append(a.predict(xi, d + cp, continuation=False))
+    bat = b.fit_predict_many([(xi, xo, d + cp) for (xi, xo), d in zip(io, cand)])
+    for s_, b_ in zip(seq, bat):
+        assert s_.shape == b_.shape and rel_err(b_, s_) < 1e-9
+    assert rel_err(b.W_out, a.W_out) < 1e-9 and rel_err(b.laststate, a.laststate) < 1e-12
+    assert np.array_equal(a.random_state_.rand(3), b.random_state_.rand(3))      # generators stayed in step
+
+
 def test_legacy_trainer_matches_reference_golden(golden, capsys):
     from pyESN import ESN
     from HelpFunc import HelpFunc
