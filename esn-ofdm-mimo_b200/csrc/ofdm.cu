@@ -479,6 +479,127 @@ extern "C" int ofdm_equalize(int dtype, const void *Y, const void *H, const int3
     return esn_launch_status();
 }
 
+// ---- soft outputs: sigma2 estimate + max-log LLRs (+ logistic calibration) ----------------
+// One CTA per frame.  Pass 1: sigma2 = mean |X - nearest point|^2 + 1e-12 over the frame (the mean of
+// the reference's per-Tx means).  Pass 2: for the square constellation with index L i_re + i_im and
+// LSB-first binary labels the max-log LLR of a bit separates per axis: bits [0, m/2) belong to the
+// imaginary level, bits [m/2, m) to the real level, and the other axis cancels in d1 - d0.
+template <typename T>
+__global__ void __launch_bounds__(256)
+soft_demap_kernel(const T *__restrict__ X, int N, int N_t, int qam_bits, const double *__restrict__ cal_a,
+                  const double *__restrict__ cal_b, T clip, T *__restrict__ sigma2, T *__restrict__ llr) {
+    const Slicer<T> sl(qam_bits);
+    const int b = blockIdx.x, n_sym = N * N_t, hb = qam_bits / 2;
+    const T *Xf = X + (size_t)b * n_sym * 2;
+    __shared__ double s_red[8];
+    __shared__ double s_sigma;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n_sym; i += blockDim.x) {
+        const T re = Xf[2 * i], im = Xf[2 * i + 1];
+        const T dr = re - (T)(2 * sl.level(re) - (sl.L - 1)) / sl.s, di = im - (T)(2 * sl.level(im) - (sl.L - 1)) / sl.s;
+        acc += (double)(dr * dr + di * di);
+    }
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+        s_sigma = t / n_sym + 1e-12;
+        if (sigma2) sigma2[b] = (T)s_sigma;
+    }
+    __syncthreads();
+    if (!llr) return;
+    const T inv = (T)(1.0 / fmax(s_sigma, 1e-12));
+    T *Lf = llr + (size_t)b * n_sym * qam_bits;
+    for (int i = threadIdx.x; i < n_sym; i += blockDim.x) {
+        const int n = i / N_t, tx = i - n * N_t;
+        const T v[2] = {Xf[2 * i + 1], Xf[2 * i]};          // axis 0 = imaginary (low bits), axis 1 = real
+#pragma unroll
+        for (int ax = 0; ax < 2; ++ax) {
+            for (int k = 0; k < hb; ++k) {
+                T d0 = (T)1e30, d1 = (T)1e30;
+                for (int j = 0; j < sl.L; ++j) {
+                    const T e = v[ax] - (T)(2 * j - (sl.L - 1)) / sl.s, e2 = e * e;
+                    if ((j >> k) & 1) d1 = fmin(d1, e2); else d0 = fmin(d0, e2);
+                }
+                const int bit = ax * hb + k;
+                T l = (d1 - d0) * inv;
+                if (cal_a) l = fmin(fmax(-((T)cal_a[bit] * l + (T)cal_b[bit]), -clip), clip);
+                Lf[((size_t)n * qam_bits + bit) * N_t + tx] = l;
+            }
+        }
+    }
+}
+
+// LLR calibration: per bit position, maxiter steps of full-batch gradient descent on the 1-D logistic
+// regression p(y = 1 | x) = sigmoid(a x + b), x = llr[.., bit, ..], y = transmitted bit.  One CTA per
+// bit position, fp64 throughout.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+llr_calibrate_kernel(const T *__restrict__ llr, const uint8_t *__restrict__ tx_idx, long long n_sym_total, int N_t,
+                     int qam_bits, int maxiter, double lr, double l2, double *__restrict__ ab) {
+    const int bit = blockIdx.x;
+    __shared__ double s_ga[32], s_gb[32], s_a, s_b;
+    if (threadIdx.x == 0) { s_a = 1.0; s_b = 0.0; }
+    __syncthreads();
+    for (int it = 0; it < maxiter; ++it) {
+        const double a = s_a, bb = s_b;
+        double ga = 0.0, gb = 0.0;
+        for (long long i = threadIdx.x; i < n_sym_total; i += blockDim.x) {
+            const long long n = i / N_t;                   // (frame, subcarrier) index
+            const int tx = (int)(i - n * N_t);
+            const double x = (double)llr[(n * qam_bits + bit) * N_t + tx];
+            const double y = (double)((tx_idx[i] >> bit) & 1);
+            const double p = 1.0 / (1.0 + exp(-(a * x + bb)));
+            ga += (p - y) * x;
+            gb += (p - y);
+        }
+        for (int s = 16; s > 0; s >>= 1) {
+            ga += __shfl_xor_sync(0xffffffffu, ga, s);
+            gb += __shfl_xor_sync(0xffffffffu, gb, s);
+        }
+        if ((threadIdx.x & 31) == 0) { s_ga[threadIdx.x >> 5] = ga; s_gb[threadIdx.x >> 5] = gb; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double ta = 0.0, tb = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ta += s_ga[w]; tb += s_gb[w]; }
+            s_a = a - lr * (ta / (double)n_sym_total + l2 * a);
+            s_b = bb - lr * (tb / (double)n_sym_total);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { ab[2 * bit] = s_a; ab[2 * bit + 1] = s_b; }
+}
+
+extern "C" int ofdm_soft_demap(int dtype, const void *X_hat, int B, int N, int N_t, int qam_bits, const double *cal_a,
+                               const double *cal_b, double clip, void *sigma2, void *llr, void *stream) {
+    if (!X_hat || B <= 0 || N <= 0 || N_t <= 0 || (!sigma2 && !llr) || ((cal_a == nullptr) != (cal_b == nullptr)))
+        return ESN_E_BADARG;
+    if (qam_bits != 2 && qam_bits != 4 && qam_bits != 6) return ESN_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == ESN_F32)
+        soft_demap_kernel<float><<<B, 256, 0, st>>>((const float *)X_hat, N, N_t, qam_bits, cal_a, cal_b, (float)clip, (float *)sigma2, (float *)llr);
+    else if (dtype == ESN_F64)
+        soft_demap_kernel<double><<<B, 256, 0, st>>>((const double *)X_hat, N, N_t, qam_bits, cal_a, cal_b, clip, (double *)sigma2, (double *)llr);
+    else return ESN_E_BADARG;
+    return esn_launch_status();
+}
+
+extern "C" int ofdm_llr_calibrate(int dtype, const void *llr, const uint8_t *tx_idx, int B, int N, int N_t, int qam_bits,
+                                  int maxiter, double lr, double l2, double *ab, void *stream) {
+    if (!llr || !tx_idx || !ab || B <= 0 || N <= 0 || N_t <= 0 || maxiter < 0) return ESN_E_BADARG;
+    if (qam_bits != 2 && qam_bits != 4 && qam_bits != 6) return ESN_E_BADARG;
+    const long long n = (long long)B * N * N_t;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == ESN_F32)
+        llr_calibrate_kernel<float><<<qam_bits, 1024, 0, st>>>((const float *)llr, tx_idx, n, N_t, qam_bits, maxiter, lr, l2, ab);
+    else if (dtype == ESN_F64)
+        llr_calibrate_kernel<double><<<qam_bits, 1024, 0, st>>>((const double *)llr, tx_idx, n, N_t, qam_bits, maxiter, lr, l2, ab);
+    else return ESN_E_BADARG;
+    return esn_launch_status();
+}
+
 extern "C" int ofdm_demap_count(int dtype, const void *X_hat, int B, int N, int N_t, int qam_bits, uint8_t *idx,
                                 const uint8_t *tx_idx, double boundary_eps, unsigned long long *counts,
                                 void *stream) {

@@ -79,6 +79,8 @@ SIGNATURES = {
     "ofdm_synth_frames": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _d, C.c_uint64, _i, _i, _i, _i, _i, _i, _i, _i,
                                _vp, _vp, _vp, _vp]),
     "ofdm_demap_count": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp, _d, _vp, _vp]),
+    "ofdm_soft_demap": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp, _d, _vp, _vp, _vp]),
+    "ofdm_llr_calibrate": (_i, [_i, _vp, _vp, _i, _i, _i, _i, _i, _d, _d, _vp, _vp]),
 }
 
 _lib = None

@@ -114,6 +114,37 @@ def demap_count(X_hat, qam_bits, tx_idx=None, boundary_eps=0.0, counts=None, wan
     return idx, counts
 
 
+def soft_demap(X_hat, qam_bits, cal=None, clip=20.0, want_llr=True):
+    """X_hat [B,N,N_t] complex -> (sigma2 [B], llr [B,N,qam_bits,N_t]): the frame's noise-variance
+    estimate and max-log LLRs (positive = bit 0).  `cal` = ab [qam_bits,2] from `llr_calibrate`
+    applies the decoder-side map clip(-(a llr + b), +-clip)."""
+    lib = _lib.load()
+    B, N, N_t = X_hat.shape
+    rd = _real_dtype(X_hat)
+    sigma2 = torch.empty((B,), dtype=rd, device=X_hat.device)
+    llr = torch.empty((B, N, qam_bits, N_t), dtype=rd, device=X_hat.device) if want_llr else None
+    a = b = None
+    if cal is not None:
+        cal = cal.to(device=X_hat.device, dtype=torch.float64)
+        a, b = cal[:, 0].contiguous(), cal[:, 1].contiguous()
+    check(lib.ofdm_soft_demap(_CODE[rd], ptr(_cplx_view(X_hat)), B, N, N_t, qam_bits, ptr(a), ptr(b), float(clip),
+                              ptr(sigma2), ptr(llr), _stream()), "ofdm_soft_demap")
+    return sigma2, llr
+
+
+def llr_calibrate(llr, tx_idx, qam_bits, maxiter=400, lr=0.1, l2=1e-3):
+    """Per-bit logistic calibration of LLRs [B,N,qam_bits,N_t] against the transmitted symbol
+    indices [B,N,N_t]; returns ab [qam_bits,2] fp64 on the device."""
+    lib = _lib.load()
+    llr = llr.contiguous()
+    B, N, m, N_t = llr.shape
+    tx_idx = tx_idx.to(device=llr.device, dtype=torch.uint8).contiguous()
+    ab = torch.empty((qam_bits, 2), dtype=torch.float64, device=llr.device)
+    check(lib.ofdm_llr_calibrate(_CODE[llr.dtype], ptr(llr), ptr(tx_idx), B, N, N_t, qam_bits, int(maxiter),
+                                 float(lr), float(l2), ptr(ab), _stream()), "ofdm_llr_calibrate")
+    return ab
+
+
 def synth_frames(tx_idx, taps, Pi, A_clip, N, cp, qam_bits, noise_std, delay=0, chan_index=None, noise=None,
                  seed=0, dtype=torch.float32, want_x_cp=False, want_y_cp=True, want_esn_in=True):
     """Workload generation on the device (bits/indices -> received frames).  tx_idx [B,N,N_t]

@@ -244,6 +244,21 @@ int ofdm_synth_frames(int dtype, const uint8_t *tx_idx, const void *taps, const 
 int ofdm_demap_count(int dtype, const void *X_hat, int B, int N, int N_t, int qam_bits,
                      uint8_t *idx, const uint8_t *tx_idx, double boundary_eps,
                      unsigned long long *err_count, void *stream);
+/* Soft outputs, replacing system_model_2/Demo_MIMO_4x8_Sionna_CDL_ESN_v2.py:
+ * ofdm_soft_demap: per frame sigma2 = mean over Tx of (mean |X_hat - nearest point|^2 + 1e-12)
+ *   (est_sigma2_from_decision :84-88, :459), then max-log LLRs (d1 - d0) / max(sigma2, 1e-12) per bit,
+ *   bit b of the point index LSB first (qam_llrs_maxlog :66-82, bits_to_grayvec :30-32); positive =
+ *   bit 0.  With cal_a / cal_b [qam_bits] (fp64, device) the decoder-side map clip(-(a_b llr + b_b),
+ *   +-clip) is applied (:489-492).  X_hat [B][N][N_t] complex, sigma2 [B] or null, llr
+ *   [B][N][qam_bits][N_t] (the reference's (N, m, N_t) per frame) or null.
+ * ofdm_llr_calibrate: fit_logreg_1d (:108-119) per bit position over every symbol of the B frames:
+ *   maxiter steps of full-batch gradient descent (rate lr, ridge l2 on a) from a = 1, b = 0; y = bit of
+ *   tx_idx [B][N][N_t].  ab [qam_bits][2] fp64 (device). */
+int ofdm_soft_demap(int dtype, const void *X_hat, int B, int N, int N_t, int qam_bits,
+                    const double *cal_a, const double *cal_b, double clip, void *sigma2, void *llr,
+                    void *stream);
+int ofdm_llr_calibrate(int dtype, const void *llr, const uint8_t *tx_idx, int B, int N, int N_t,
+                       int qam_bits, int maxiter, double lr, double l2, double *ab, void *stream);
 
 #ifdef __cplusplus
 }

@@ -410,6 +410,72 @@ def boundary_distance(X_hat, m):
 
 
 # ----------------------------------------------------------------------------
+# §8f row 3: soft outputs -- noise-variance estimate, max-log LLRs, logistic calibration
+# ----------------------------------------------------------------------------
+
+def qam_bit_labels(m):
+    """`qam_bit_labels` (system_model_2/Demo_MIMO_4x8_Sionna_CDL_ESN_v2.py:60-64):
+    labels[idx, b] = bit b of idx, LSB first (`bits_to_grayvec`, :30-32)."""
+    idx = np.arange(2 ** m)
+    return ((idx[:, None] >> np.arange(m)[None, :]) & 1).astype(int)
+
+
+def sigma2_from_decision(X_hat_col, const):
+    """`est_sigma2_from_decision` (Demo_MIMO_4x8_Sionna_CDL_ESN_v2.py:84-88): mean
+    squared distance to the nearest constellation point, + 1e-12."""
+    z = np.asarray(X_hat_col).reshape(-1, 1)
+    idx = np.argmin(np.abs(z - const.reshape(1, -1)) ** 2, axis=1)
+    return float(np.mean(np.abs(z[:, 0] - const[idx]) ** 2) + 1e-12)
+
+
+def frame_sigma2(X_hat, const):
+    """Per-frame noise variance: mean of the per-Tx estimates (:459)."""
+    return float(np.mean([sigma2_from_decision(X_hat[:, tx], const) for tx in range(X_hat.shape[1])]))
+
+
+def llrs_maxlog(z, const, labels, sigma2):
+    """`qam_llrs_maxlog` (Demo_MIMO_4x8_Sionna_CDL_ESN_v2.py:66-82):
+    LLR_b = (min_{c: bit b = 1} |z-c|^2 - min_{c: bit b = 0} |z-c|^2) / max(sigma2, 1e-12);
+    positive = bit 0 more likely.  z [N] -> [N, m]."""
+    d = np.abs(np.asarray(z).reshape(-1, 1) - const.reshape(1, -1)) ** 2
+    m = labels.shape[1]
+    out = np.zeros((d.shape[0], m))
+    for b in range(m):
+        out[:, b] = (d[:, labels[:, b] == 1].min(axis=1) - d[:, labels[:, b] == 0].min(axis=1)) / max(sigma2, 1e-12)
+    return out
+
+
+def frame_llrs(X_hat, m):
+    """LLRs of one frame in the reference's layout (N, m, N_t) (:460-463) and its sigma2."""
+    const, labels = unit_qam_constellation(m), qam_bit_labels(m)
+    s2 = frame_sigma2(X_hat, const)
+    return np.stack([llrs_maxlog(X_hat[:, tx], const, labels, s2) for tx in range(X_hat.shape[1])], axis=2), s2
+
+
+def fit_logreg_1d(x, y, maxiter=400, lr=0.15, l2=1e-3):
+    """`fit_logreg_1d` (Demo_MIMO_4x8_Sionna_CDL_ESN_v2.py:108-119): full-batch gradient
+    descent on p(y=1|x) = sigmoid(a x + b), a0 = 1, b0 = 0."""
+    a, b = 1.0, 0.0
+    n = len(x)
+    for _ in range(maxiter):
+        with np.errstate(over="ignore"):
+            p = 1.0 / (1.0 + np.exp(-(a * x + b)))
+        ga = np.dot(p - y, x) / n + l2 * a
+        gb = np.sum(p - y) / n
+        a -= lr * ga
+        b -= lr * gb
+    return float(a), float(b)
+
+
+def calibrate_llrs(llr, a, b, clip=20.0):
+    """Calibrated, sign-flipped and clipped LLRs fed to the decoder (:489-492):
+    clip(-(a_b llr + b_b), -clip, clip); llr [..., m, N_t]."""
+    a = np.asarray(a).reshape(-1, 1)
+    b = np.asarray(b).reshape(-1, 1)
+    return np.clip(-(a * llr + b), -clip, clip)
+
+
+# ----------------------------------------------------------------------------
 # a11: ESN output unpack + FFT
 # ----------------------------------------------------------------------------
 

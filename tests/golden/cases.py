@@ -81,3 +81,16 @@ def trainer_esn_kwargs(c, var_x):
                 teacher_scaling=5e-7 * np.ones(2 * c["N_t"]),
                 teacher_shift=np.zeros(2 * c["N_t"]),
                 feedback_scaling=np.zeros(2 * c["N_t"]), random_state=c["seed"])
+
+
+# soft-output cases: qam_bits -> (N, N_t, SNR of the synthetic equaliser output in dB, frames)
+SOFT_CASES = {2: (64, 2, 6.0, 6), 4: (64, 4, 14.0, 6), 6: (32, 2, 20.0, 4)}
+
+
+def soft_frames(m, N, N_t, snr_db, frames, const):
+    """Seeded equaliser outputs X_hat [frames, N, N_t] = const[idx] + CN(0, 10^(-snr/10)) and idx."""
+    rng = np.random.RandomState(900 + m)
+    idx = rng.randint(0, 2 ** m, size=(frames, N, N_t))
+    s = 10 ** (-snr_db / 20) / np.sqrt(2)
+    X = const[idx] + s * (rng.randn(frames, N, N_t) + 1j * rng.randn(frames, N, N_t))
+    return X, idx

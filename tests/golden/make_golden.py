@@ -183,14 +183,52 @@ def gen_chain_cases(out):
         print("chain", name, "ok")
 
 
+def gen_soft_cases(out):
+    """Soft-output helpers of the CDL demo (LLRs, noise-variance estimate, logistic calibration)."""
+    script = os.path.join(REF, "system_model_2", "Demo_MIMO_4x8_Sionna_CDL_ESN_v2.py")
+    fns = ref_script_functions(script, {
+        "unit_qam_constellation", "bits_to_grayvec", "qam_bit_labels", "qam_llrs_maxlog",
+        "est_sigma2_from_decision", "sigmoid", "fit_logreg_1d"})
+    for m, (N, N_t, snr_db, frames) in cases.SOFT_CASES.items():
+        const = fns["unit_qam_constellation"](m)
+        labels = fns["qam_bit_labels"](2 ** m, m)
+        X, idx = cases.soft_frames(m, N, N_t, snr_db, frames, const)
+        out[f"soft/{m}/X_hat"] = X
+        out[f"soft/{m}/tx_idx"] = idx
+        llr_all, s2_all = [], []
+        for f in range(frames):
+            s2 = np.mean([fns["est_sigma2_from_decision"](X[f, :, tx], const) for tx in range(N_t)])
+            ll = np.stack([fns["qam_llrs_maxlog"](X[f, :, tx], const, labels, s2) for tx in range(N_t)], axis=2)
+            llr_all.append(ll)
+            s2_all.append(s2)
+        llr_all = np.stack(llr_all)                       # [frames, N, m, N_t]
+        out[f"soft/{m}/llr"] = llr_all
+        out[f"soft/{m}/sigma2"] = np.array(s2_all)
+        ab = np.zeros((m, 2))
+        for b in range(m):
+            x = llr_all[:, :, b, :].reshape(-1)
+            y = ((idx >> b) & 1).reshape(-1).astype(float)
+            ab[b] = fns["fit_logreg_1d"](x, y, maxiter=400, lr=0.1, l2=1e-3)
+        out[f"soft/{m}/ab"] = ab
+        print("soft", m, "sigma2", s2_all[0], "ab", ab[0])
+
+
 def main():
-    out = {}
-    gen_esn_cases(out)
-    gen_trainer_cases(out)
-    gen_chain_cases(out)
-    path = os.path.join(HERE, "reference_golden.npz")
-    np.savez_compressed(path, **out)
-    print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(out), "arrays")
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "core"):
+        out = {}
+        gen_esn_cases(out)
+        gen_trainer_cases(out)
+        gen_chain_cases(out)
+        path = os.path.join(HERE, "reference_golden.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(out), "arrays")
+    if which in ("all", "soft"):
+        out = {}
+        gen_soft_cases(out)
+        path = os.path.join(HERE, "soft_golden.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(out), "arrays")
 
 
 if __name__ == "__main__":

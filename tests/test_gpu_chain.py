@@ -139,3 +139,30 @@ def test_ber_curve_matches_oracle():
         assert abs(err_gpu - err_cpu) <= 4 * near_total, (ebno, err_gpu, err_cpu, near_total)
         ber = err_gpu / (3 * n_data * N * N_t * m)
         assert 0.0 <= ber <= 0.6
+
+
+# --------------------------------------------------------------------------
+# soft outputs against the reference's golden vectors
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("m", [2, 4, 6])
+@pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
+def test_soft_demap_and_calibration_match_reference_golden(m, dt):
+    import os
+    from esn_b200 import ofdm
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "soft_golden.npz"))
+    X = _cuda(g[f"soft/{m}/X_hat"], dt)
+    idx = _cuda(g[f"soft/{m}/tx_idx"].astype(np.uint8))
+    s2, llr = ofdm.soft_demap(X, m)
+    tol = 1e-10 if dt == torch.complex128 else 2e-4
+    assert rel_err(s2.double().cpu().numpy(), g[f"soft/{m}/sigma2"]) < (1e-12 if dt == torch.complex128 else 1e-5)
+    assert rel_err(llr.double().cpu().numpy(), g[f"soft/{m}/llr"]) < tol
+    ab = ofdm.llr_calibrate(llr, idx, m, maxiter=400, lr=0.1, l2=1e-3).cpu().numpy()
+    assert np.allclose(ab, g[f"soft/{m}/ab"], rtol=1e-8 if dt == torch.complex128 else 1e-3, atol=1e-9 if dt == torch.complex128 else 1e-4)
+    # decoder-side map: clip(-(a llr + b), +-20), as one fused launch
+    _, cal = ofdm.soft_demap(X, m, cal=_cuda(g[f"soft/{m}/ab"]), clip=20.0)
+    ref = orc.calibrate_llrs(g[f"soft/{m}/llr"], g[f"soft/{m}/ab"][:, 0], g[f"soft/{m}/ab"][:, 1], 20.0)
+    assert np.max(np.abs(cal.double().cpu().numpy() - ref)) < (1e-9 if dt == torch.complex128 else 5e-3)
+    # sign of the LLR = hard decision of the slicer kernel
+    hard, _ = ofdm.demap_count(X, m)
+    bits = ((hard.cpu().numpy()[:, :, None, :] >> np.arange(m)[None, None, :, None]) & 1)
+    assert np.array_equal((llr.cpu().numpy() < 0).astype(int), bits)

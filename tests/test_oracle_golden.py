@@ -134,3 +134,34 @@ def test_bits_roundtrip():
         const = orc.unit_qam_constellation(m)
         assert np.array_equal(orc.slicer_indices(const[idx], m), idx)
         assert np.array_equal(orc.hard_demap_indices(const[idx], const), idx)
+
+
+# --------------------------------------------------------------------------
+# soft outputs: sigma2 estimate, max-log LLRs, logistic calibration
+# --------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def soft_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "soft_golden.npz"))
+
+
+@pytest.mark.parametrize("m", [2, 4, 6])
+def test_oracle_soft_outputs_match_reference(soft_golden, m):
+    g = soft_golden
+    X, idx = g[f"soft/{m}/X_hat"], g[f"soft/{m}/tx_idx"]
+    const = orc.unit_qam_constellation(m)
+    X2, idx2 = cases.soft_frames(m, *cases.SOFT_CASES[m], const)
+    assert np.array_equal(idx, idx2) and np.allclose(X, X2, rtol=0, atol=1e-15)
+    llr = np.stack([orc.frame_llrs(X[f], m)[0] for f in range(X.shape[0])])
+    s2 = np.array([orc.frame_llrs(X[f], m)[1] for f in range(X.shape[0])])
+    assert np.allclose(s2, g[f"soft/{m}/sigma2"], rtol=1e-13, atol=0)
+    assert np.allclose(llr, g[f"soft/{m}/llr"], rtol=1e-12, atol=1e-12)
+    ab = np.array([orc.fit_logreg_1d(llr[:, :, b, :].reshape(-1), ((idx >> b) & 1).reshape(-1).astype(float),
+                                     maxiter=400, lr=0.1, l2=1e-3) for b in range(m)])
+    assert np.allclose(ab, g[f"soft/{m}/ab"], rtol=1e-12, atol=1e-14)
+    # the labels are the LSB-first binary of the point index, and hard decisions = sign of the LLR
+    hard = (llr < 0).astype(int)
+    idx_hat = orc.hard_demap_indices(X[0], const)
+    assert np.array_equal(hard[0], np.moveaxis(((idx_hat[:, :, None] >> np.arange(m)) & 1), 2, 1))
+    cal = orc.calibrate_llrs(llr, ab[:, 0], ab[:, 1], 20.0)
+    assert cal.shape == llr.shape and np.all(np.abs(cal) <= 20.0)
