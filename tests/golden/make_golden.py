@@ -213,6 +213,41 @@ def gen_soft_cases(out):
         print("soft", m, "sigma2", s2_all[0], "ab", ab[0])
 
 
+def gen_writer_cases(out):
+    """Text the reference's own writer lines produce (CSV :636-641, calibration txt :532-535) and the
+    dict it pickles (:620-633), on synthetic curves."""
+    import csv, pickle, tempfile
+    script = os.path.join(REF, "system_model_2", "Demo_MIMO_4x8_Sionna_CDL_ESN_v2.py")
+    lines = open(script).read().split("\n")
+    EbNoDB = np.arange(0, 30 + 1, 3).astype(np.int32)
+    rng = np.random.RandomState(31)
+    curves = {k: 0.5 * np.exp(-rng.rand() * EbNoDB / 6.0) for k in ("ue", "um", "ce", "cm")}
+    tmp = tempfile.mkdtemp()
+    ns = dict(os=os, csv=csv, pickle=pickle, np=np, OUT_DIR=tmp, outdir=tmp, EbNoDB=EbNoDB,
+              BER_uncoded_ESN=curves["ue"], BER_uncoded_MMSE=curves["um"],
+              BER_coded_ESN=curves["ce"], BER_coded_MMSE=curves["cm"],
+              m=4, ebno_db=12, a_esn=rng.randn(4), b_esn=rng.randn(4) * 0.01,
+              a_mmse=rng.randn(4), b_mmse=rng.randn(4) * 0.01)
+    blk = lines[635:641]                                  # file lines 636..641
+    assert blk[0].startswith("csv_path = ") and "w.writerow([int(snr)" in blk[-1], "reference layout changed"
+    exec(compile("\n".join(blk), script + ":636-641", "exec"), ns)
+    blk = lines[531:535]                                  # file lines 532..535
+    assert "LLR_calibration_params_EbNo" in blk[0] and "a_mmse[b]" in blk[-1], "reference layout changed"
+    exec(compile(textwrap.dedent("\n".join(blk)), script + ":532-535", "exec"), ns)
+    blk = lines[619:633]                                  # file lines 620..633: the compact bundle
+    assert blk[0].startswith("results_ber = {") and blk[-1].strip() == "pickle.dump(results_ber, f)", "reference layout changed"
+    exec(compile("\n".join(blk), script + ":620-633", "exec"), ns)
+    out["writers/EbNoDB"] = EbNoDB
+    for k, v in curves.items():
+        out["writers/" + k] = v
+    for k in ("a_esn", "b_esn", "a_mmse", "b_mmse"):
+        out["writers/" + k] = ns[k]
+    out["writers/csv_bytes"] = np.frombuffer(open(os.path.join(tmp, "results_ber.csv"), "rb").read(), dtype=np.uint8)
+    out["writers/txt_bytes"] = np.frombuffer(open(os.path.join(tmp, "LLR_calibration_params_EbNo12dB.txt"), "rb").read(), dtype=np.uint8)
+    out["writers/pkl_bytes"] = np.frombuffer(open(os.path.join(tmp, "results_ber.pkl"), "rb").read(), dtype=np.uint8)
+    print("writers: csv", len(out["writers/csv_bytes"]), "bytes")
+
+
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "core"):
@@ -226,6 +261,7 @@ def main():
     if which in ("all", "soft"):
         out = {}
         gen_soft_cases(out)
+        gen_writer_cases(out)
         path = os.path.join(HERE, "soft_golden.npz")
         np.savez_compressed(path, **out)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB,", len(out), "arrays")

@@ -174,3 +174,27 @@ def test_two_rank_gloo_allreduce(tmp_path):
     s.close()
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_result_writers_reproduce_reference_files(tmp_path):
+    """results_ber.csv, the calibration txt and the pickled bundle byte-for-byte / key-for-key as the
+    reference's own writer lines produce them (golden made by executing those lines)."""
+    import os
+    import pickle
+    from esn_b200 import results as R
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "soft_golden.npz"))
+    eb = g["writers/EbNoDB"]
+    p = R.write_results_csv(str(tmp_path / "out" / "results_ber.csv"), eb, g["writers/ue"], g["writers/um"],
+                            g["writers/ce"], g["writers/cm"])
+    assert open(p, "rb").read() == g["writers/csv_bytes"].tobytes()
+    back = R.read_results_csv(p)
+    assert back["EBN0"] == [int(x) for x in eb] and back["BER_uncoded"]["ESN"] == [float(x) for x in g["writers/ue"]]
+    t = R.write_llr_calibration(str(tmp_path / "LLR_calibration_params_EbNo12dB.txt"),
+                                np.stack([g["writers/a_esn"], g["writers/b_esn"]], 1),
+                                np.stack([g["writers/a_mmse"], g["writers/b_mmse"]], 1))
+    assert open(t, "rb").read() == g["writers/txt_bytes"].tobytes()
+    ref = pickle.loads(g["writers/pkl_bytes"].tobytes())
+    mine = R.results_bundle(eb, g["writers/ue"], g["writers/um"], g["writers/ce"], g["writers/cm"])
+    assert mine == ref and list(mine) == list(ref)
+    # uncoded-only run: coded columns are zeros, like the reference's zero-initialised arrays
+    assert R.results_bundle(eb, g["writers/ue"], g["writers/um"])["BER_coded"]["ESN_calLLR"] == [0.0] * len(eb)
