@@ -89,7 +89,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark(self, which):
+        """Host time stamps of the timed region: samples inside it are the ones reported."""
+        setattr(self, "t_" + which, time.time())
 
     def __exit__(self, *a):
         if self.proc:
@@ -102,7 +106,11 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0, t1 = getattr(self, "t_start", None), getattr(self, "t_end", None)
+        rows = [r for t, r in self.rows if t0 is None or t1 is None or (t0 <= t <= t1 + 0.15)]
+        if not rows and t1 is not None:              # short timed region: the last samples taken under load
+            rows = [r for t, r in self.rows if t <= t1 + 0.15][-3:]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -336,18 +344,20 @@ def run_gpu(args):
             D.allreduce_sum_(counts)
         return idx
 
-    for _ in range(args.warmup):
-        step(frames)
-    torch.cuda.synchronize()
-    D.barrier()
-    torch.cuda.synchronize()
-    t0, t1 = ev(), ev()
-    with ClockSampler(local) as clk:
+    with ClockSampler(local) as clk:                 # started before the warm-up: nvidia-smi needs a moment
+        for _ in range(args.warmup):
+            step(frames)
+        torch.cuda.synchronize()
+        D.barrier()
+        torch.cuda.synchronize()
+        t0, t1 = ev(), ev()
+        clk.mark("start")
         t0.record(stream)
         for _ in range(args.steps):
             step(frames, time_kernel=True)
         t1.record(stream)
         torch.cuda.synchronize()
+        clk.mark("end")
     D.barrier()
     ms = t0.elapsed_time(t1)
     ms = D.max_over_ranks(ms, dev)

@@ -1,34 +1,19 @@
-// Reservoir recurrence on the 5th-generation tensor cores (tcgen05 + TMEM).
+// Reservoir recurrence on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
 //
-// Free-running ESN.predict (reference libs/pyESN.py:243-255) for reservoirs of
-// up to 512 neurons (S = ceil(N/128) slabs), batched over frames: one CTA owns 64
-// frames and steps them through all T time steps.
-//
-// Per step the pre-activation of all neurons is D[neuron, frame] =
-// [W | W_in | 0 | W_fb][neuron, :] . [x_{t-1} | u_t | u_{t-1} | y_{t-1}][frame, :],
-// an M=128 x N=64 x K UMMA chain per 128-neuron slab:
-//   A (M side) = weight tiles, ONE image shared by every CTA and every readout (it
-//                stays L2-resident), streamed each step through a ring of 16 KB
-//                slots with cp.async.bulk (UBLKCP) + mbarrier tx counts; the image
-//                is pre-swizzled (SWIZZLE_128B, K-major) so a plain bulk copy lands
-//                a UMMA-ready tile.
-//   B (N side) = the state tile [64 frames x K] that lives in shared memory for the
-//                whole kernel and is rewritten in place every step.
-//   D          = fp32 accumulators in TMEM (S x 64 columns), read with tcgen05.ld.
-// The readout y_{t-1} = W_out[g] [x_{t-1}; u_{t-1}] is one more small UMMA chain
-// over the same state tile (M = frames, N = 16) issued FIRST in the step; two
-// "frame" warps pull it out of TMEM while the big chain runs, emit it, and write
-// it back into the y columns of the state tile, where the last K chunk of the
-// big chain (W_in, W_fb) picks it up -- the output feedback of the reference
-// without serialising the tensor pipe.
-// fp32-grade accuracy from fp16 operands: every operand v is split v = hi + lo
-// (two fp16, ~22 mantissa bits, power-of-two pre-scaling keeps lo out of the
-// subnormals) and each product is issued as hi*hi + lo*hi + hi*lo with fp32
-// accumulation -- three kind::f16 MMAs, half the tensor time of 3xTF32.
-//
-// Warp roles (640 threads): 0-1 frame warps (inputs, readout, noise keys),
-// 2 weight-ring producer, 3 MMA issuer + TMEM owner, 4-19 epilogue
-// (TMEM -> tanh -> noise -> fp16 hi/lo -> swizzled state tile).
+// Free-running ESN.predict (reference libs/pyESN.py:243-255) and the teacher-forced harvest of ESN.fit
+// (:179-182) for reservoirs of up to 512 neurons, batched over frames: a pair of CTAs (one cluster,
+// tcgen05 cta_group::2) owns 128 frames and steps them through all T time steps.  The reservoir is
+// padded to an even number of 128-neuron slabs (256 or 512 neurons).  See the comment above
+// esn_predict_tc2 for the layout; in short:
+//   D[frame, neuron] = [x_{t-1} | u_t | y_{t-1}] . [W | W_in | W_fb]^T   per step,
+//   A = the CTA's state tile (shared memory, rewritten in place by the epilogue),
+//   B = weight tiles of ONE image shared by every CTA and every readout (L2-resident), streamed through a
+//       ring of 16 KB slots by tensor-map bulk copies; the image is pre-swizzled (SWIZZLE_128B, K-major)
+//       so a plain copy lands a UMMA-ready tile,
+//   D = fp32 accumulators in TMEM, read with tcgen05.ld.
+// fp32-grade accuracy from fp16 operands: every operand v is split v = hi + lo (two fp16, ~22 mantissa
+// bits, power-of-two pre-scaling keeps lo out of the subnormals) and each product is issued as
+// hi*hi + lo*hi + hi*lo with fp32 accumulation -- three kind::f16 MMAs, half the tensor time of 3xTF32.
 #include <algorithm>
 #include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through the runtime)
 #include "common.cuh"
@@ -42,9 +27,7 @@ constexpr int SLOT = 16384;            // bytes per ring slot: [128 rows x 64 k]
 constexpr int STILE = 8192;            // bytes per state tile: [64 rows x 64 k] fp16
 constexpr int YTILE = 2048;            // bytes per readout tile: [16 rows x 64 k] fp16
 constexpr int SX = 8, SW = 8;          // power-of-two pre-scales of state and weights
-constexpr int TC_THREADS = 640;
 constexpr int TMEM_COLS = 512;
-constexpr int YCOL = 256;              // TMEM column of the readout accumulator
 
 struct TcGeom {
     int S, C, UW, YO, ca, kaug;        // slabs, 64-wide K chunks, input block width, y column offset, aug chunk, k-steps in aug chunk
@@ -53,7 +36,7 @@ struct TcGeom {
 
 __host__ __device__ inline TcGeom tc_geom(int N, int n_in) {
     TcGeom g;
-    g.S = (N + 127) / 128;
+    g.S = ((N + 255) / 256) * 2;       // 128-neuron slabs, an even number: each CTA of the pair streams every other one
     g.UW = (n_in + 7) / 8 * 8;
     g.YO = (2 * g.UW + 15) / 16 * 16;
     g.C = 2 * g.S + 1;
@@ -181,10 +164,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         }
     }
 }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -197,19 +176,6 @@ __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 
 __device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
     // D = F32, A = B = F16, both K-major
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "mov.b64 da, {%1, %5};\n\t"
-        "mov.b64 db, {%2, %5};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(DESC_HI) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                 ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -243,35 +209,7 @@ __device__ __forceinline__ void split_sts(uint32_t addr, uint32_t lo_delta, floa
     sts_u16(addr + lo_delta, __half_as_ushort(l));
 }
 
-// tanh to ~1e-7: odd Taylor series below 0.35 (truncation < 5e-9), 1 - 2/(e^{2|z|}+1) above
-__device__ __forceinline__ float tanh_f32(float z) {
-    const float az = fabsf(z);
-    if (az < 0.35f) {
-        const float z2 = z * z;
-        float p = -0.008863235f;                 // -1382/155925
-        p = fmaf(p, z2, 0.021869488f);           //  62/2835
-        p = fmaf(p, z2, -0.053968254f);          // -17/315
-        p = fmaf(p, z2, 0.133333333f);           //  2/15
-        p = fmaf(p, z2, -0.333333333f);          // -1/3
-        return fmaf(z * z2, p, z);
-    }
-    const float e = __expf(2.0f * az);
-    return copysignf(1.0f - __fdividef(2.0f, e + 1.0f), z);
-}
 
-// Branch-free tanh for |z| <= 3: [7/6] Pade approximant, error < 2.4e-7 relative up to
-// |z| = 2 and < 1e-6 up to 3 (checked against float64 tanh).  Larger arguments are rare
-// in an echo-state reservoir and are patched afterwards with tanh_large().
-__device__ __forceinline__ float tanh_pade(float z) {
-    const float z2 = z * z;
-    float num = z2 + 378.0f;
-    num = fmaf(num, z2, 17325.0f);
-    num = fmaf(num, z2, 135135.0f);
-    float den = fmaf(28.0f, z2, 3150.0f);
-    den = fmaf(den, z2, 62370.0f);
-    den = fmaf(den, z2, 135135.0f);
-    return __fdividef(num * z, den);
-}
 __device__ __forceinline__ float tanh_large(float z) {      // |z| > 3
     const float e = __expf(2.0f * fabsf(z));
     return copysignf(1.0f - __fdividef(2.0f, e + 1.0f), z);
@@ -287,7 +225,7 @@ struct TcParams {
     const unsigned char *readouts;           // [G][readout_bytes]
     const float *yscale;                     // [G]
     const float *in, *in_scale, *in_shift, *t_scale, *t_shift;
-    const int *group_ids;                    // [B] or null; uniform within each 64-frame tile
+    const int *group_ids;                    // [B] or null; uniform within each 128-frame tile
     const float *x0, *y0;                    // [B][N], [B][n_out] (scaled domain) or null
     const float *noise;                      // [B][T][N] uniforms or null
     float *ext_out;                          // [B][T][N+n_in] or null
@@ -296,300 +234,6 @@ struct TcParams {
     const float *teacher;                    // pair kernel, harvest mode: [B][T][n_out] raw teachers fed back (or null)
     int steps, row0;                         // recurrence steps and first input row: T, 0 (predict) / T-1, 1 (harvest)
 };
-
-// DBG = host noise tensor and/or extended-state output requested (parity runs)
-template <bool DBG>
-__global__ void __launch_bounds__(TC_THREADS, 1) esn_predict_tc(const TcParams p) {
-    extern __shared__ unsigned char smem_dyn[];
-    __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_d, bar_state, bar_y, bar_yready;
-    __shared__ uint32_t s_tmem;
-    __shared__ uint32_t s_key[2][FT];        // noise keys of (frame, step), double-buffered by step parity
-
-    const TcGeom gm = tc_geom(p.N, p.n_in);
-    const int S = gm.S, C = gm.C;
-    unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-    unsigned char *st_hi = base;                            // C state tiles, hi halves
-    unsigned char *st_lo = base + (size_t)C * STILE;        // C state tiles, lo halves
-    unsigned char *ring = base + (size_t)2 * C * STILE;     // NST slots
-    const uint32_t lo_delta = (uint32_t)C * STILE;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile0 = blockIdx.x * FT;
-    const int g = p.group_ids ? p.group_ids[tile0] : 0;
-    const int P = p.N + p.n_in;
-    const bool full_tile = tile0 + FT <= p.B;
-    const int items_per_step = 2 * C + 2 * S * C;
-
-    if (tid == 0) {
-        for (int i = 0; i < NST; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-        mbar_init(&bar_d, 1);
-        mbar_init(&bar_y, 1);
-        mbar_init(&bar_yready, 2);
-        mbar_init(&bar_state, 4 * S + 2);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 3) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(smem_u32(&s_tmem)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    for (int i = tid; i < 2 * C * STILE / 16; i += TC_THREADS)
-        reinterpret_cast<uint4 *>(base)[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    if (p.x0) {                                             // continuation: x_{-1} = x0
-        const float xscale = ldexpf(1.0f, SX);
-        for (int i = tid; i < FT * p.N; i += TC_THREADS) {
-            const int f = i / p.N, n = i - f * p.N, b = tile0 + f;
-            if (b < p.B)
-                split_sts(smem_u32(st_hi) + (n >> 6) * STILE + sw128_off(f, n & 63), lo_delta,
-                          p.x0[(size_t)b * p.N + n] * xscale);
-        }
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = s_tmem;
-
-    if (warp < 2) {
-        // ============ frame warps: thread = frame; inputs, readout, noise keys ============
-        const int f = warp * 32 + lane, b = tile0 + f;
-        const bool live = b < p.B;
-        const uint32_t row = smem_u32(st_hi) + gm.ca * STILE + (f >> 3) * 1024 + (f & 7) * 128;
-        const int fx = f & 7;
-        const int ng = gm.UW >> 3, yg = gm.YO >> 3;
-        const float su = ldexpf(1.0f, p.su), sy = ldexpf(1.0f, p.sy), ys = p.yscale[g];
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        float cur[24], nxt[24];
-#pragma unroll
-        for (int j = 0; j < 24; ++j) { cur[j] = 0.f; nxt[j] = 0.f; }
-        auto load_row = [&](int r) {
-#pragma unroll
-            for (int j = 0; j < 24; ++j) {
-                float v = 0.f;
-                if (j < p.n_in && live && r < p.T) {
-                    v = p.in[((size_t)b * p.T + r) * p.n_in + j] * p.in_scale[j] + p.in_shift[j];
-                    if (DBG && p.ext_out) p.ext_out[((size_t)b * p.T + r) * P + p.N + j] = v;
-                    v *= su;
-                }
-                nxt[j] = v;
-            }
-        };
-        auto write_inputs = [&]() {       // block 0 <- nxt (u_it), block 1 <- cur (u_{it-1})
-#pragma unroll
-            for (int gi = 0; gi < 3; ++gi) {
-                if (gi < ng) {
-#pragma unroll
-                    for (int blk = 0; blk < 2; ++blk) {
-                        const uint32_t a = row + (((gi + blk * ng) ^ fx) << 4);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            split_sts(a + e * 2, lo_delta, blk == 0 ? nxt[gi * 8 + e] : cur[gi * 8 + e]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 24; ++j) cur[j] = nxt[j];
-        };
-        load_row(0);
-        s_key[0][f] = esn_noise_key(p.seed, (uint32_t)b, 0u);
-        write_inputs();
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_state);
-        for (int it = 0; it <= p.T; ++it) {
-            if (it < p.T) load_row(it + 1);
-            // ---- readout y_{it-1}: out of TMEM, emit, feed back into the y columns ----
-            mbar_wait<true>(&bar_y, it & 1);
-            tc_fence_after();
-            // every epilogue warp has finished step it-1 by now, so its key row can be replaced
-            s_key[(it + 1) & 1][f] = esn_noise_key(p.seed, (uint32_t)b, (uint32_t)(it + 1));
-            uint32_t yv[16];
-            tmem_ld16(lane_base + YCOL, yv);
-            tmem_ld_wait();
-            float y[16];
-#pragma unroll
-            for (int o = 0; o < 16; ++o) {
-                y[o] = __uint_as_float(yv[o]) * ys;
-                if (it == 0) y[o] = (p.y0 && live && o < p.n_out) ? p.y0[(size_t)b * p.n_out + o] : 0.f;
-                if (o >= p.n_out) y[o] = 0.f;
-            }
-            if (it >= 1 && it - 1 >= p.transient && live) {
-                float *dst = p.y_out + ((size_t)b * (p.T - p.transient) + (it - 1 - p.transient)) * p.n_out;
-#pragma unroll
-                for (int o = 0; o < 16; ++o)
-                    if (o < p.n_out) dst[o] = (y[o] - p.t_shift[o]) / p.t_scale[o];
-            }
-            if (it == p.T) break;
-#pragma unroll
-            for (int gi = 0; gi < 2; ++gi) {
-                const uint32_t a = row + (((yg + gi) ^ fx) << 4);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) split_sts(a + e * 2, lo_delta, p.feedback ? y[gi * 8 + e] * sy : 0.f);
-            }
-            fence_async_smem();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_yready);
-            // ---- inputs for step it+1 once the big chain of step it is done ----
-            mbar_wait<true>(&bar_d, it & 1);
-            write_inputs();
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_state);
-        }
-    } else if (warp == 2) {
-        // ================= producer: stream the weight image, every step =================
-        if (lane == 0) {
-            const unsigned char *wimg = p.weights;
-            const unsigned char *yimg = p.readouts + (size_t)g * gm.readout_bytes;
-            uint32_t item = 0;
-            for (int it = 0; it <= p.T; ++it) {
-                const int n_items = it == p.T ? 2 * C : items_per_step;
-                for (int i = 0; i < n_items; ++i, ++item) {
-                    const int slot = item % NST;
-                    mbar_wait<false>(&bar_empty[slot], ((item / NST) & 1) ^ 1);
-                    const unsigned char *src;
-                    uint32_t bytes;
-                    if (i < 2 * C) { src = yimg + (size_t)i * YTILE; bytes = YTILE; }
-                    else {
-                        // consumption order: all state chunks of every slab, then the aug chunk of every slab
-                        int m = i - 2 * C, s, c, h;
-                        const int main_items = 2 * S * (C - 1);
-                        if (m < main_items) { s = m / (2 * (C - 1)); m -= s * 2 * (C - 1); c = m >> 1; h = m & 1; }
-                        else { m -= main_items; s = m >> 1; h = m & 1; c = C - 1; }
-                        src = wimg + ((size_t)(s * C + c) * 2 + h) * SLOT;
-                        bytes = SLOT;
-                    }
-                    mbar_expect_tx(&bar_full[slot], bytes);
-                    bulk_g2s(ring + (size_t)slot * SLOT, src, bytes, &bar_full[slot]);
-                }
-            }
-        }
-    } else if (warp == 3) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t id_main = umma_idesc(128, FT), id_y = umma_idesc(128, 16);
-            const uint32_t hi0 = desc_lo(smem_u32(st_hi)), ring0 = smem_u32(ring);
-            const uint32_t lod = lo_delta >> 4;            // hi -> lo state tile, in descriptor units
-            uint32_t item = 0;
-            // one ring item: streamed tile in the slot, state chunk c, hi (h=0) or lo (h=1) half of
-            // the streamed operand; 2 (h=0) or 1 (h=1) MMAs per 16-wide k-step
-            auto chain = [&](bool readout, uint32_t d, int c, int h, int ks, bool first) {
-                const int slot = item % NST;
-                mbar_wait<false>(&bar_full[slot], (item / NST) & 1);
-                tc_fence_after();
-                const uint32_t w = desc_lo(ring0 + slot * SLOT);
-                const uint32_t x = hi0 + c * (STILE >> 4);
-                const uint32_t idesc = readout ? id_y : id_main;
-#pragma unroll 4
-                for (int kk = 0; kk < ks; ++kk) {
-                    const uint32_t wk = w + kk * 2, xk = x + kk * 2;
-                    const uint32_t acc = (first && kk == 0) ? 0u : 1u;
-                    // readout: D_y[frame, out] += state . W_out^T ; else D_s[neuron, frame] += W . state^T
-                    if (h == 0) {
-                        umma_f16(d, readout ? xk : wk, readout ? wk : xk, idesc, acc);
-                        umma_f16(d, readout ? xk + lod : wk, readout ? wk : xk + lod, idesc, 1u);
-                    } else {
-                        umma_f16(d, readout ? xk : wk, readout ? wk : xk, idesc, 1u);
-                    }
-                }
-                umma_commit(&bar_empty[slot]);
-                ++item;
-            };
-            const bool stamp = p.timeline && blockIdx.x == 0;
-            for (int it = 0; it <= p.T; ++it) {
-                if (stamp) p.timeline[it * 8 + 0] = clock64();       // waiting for the state tile
-                mbar_wait<false>(&bar_state, it & 1);
-                tc_fence_after();
-                if (stamp) p.timeline[it * 8 + 1] = clock64();       // state ready, issue starts
-                for (int c = 0; c < C; ++c) {
-                    const int ks = (c == C - 1) ? gm.YO / 16 : 4;
-                    chain(true, tmem + YCOL, c, 0, ks, c == 0);
-                    chain(true, tmem + YCOL, c, 1, ks, false);
-                }
-                umma_commit(&bar_y);
-                if (it == p.T) break;                    // only the last readout is left
-                for (int s = 0; s < S; ++s)
-                    for (int c = 0; c < C - 1; ++c) {
-                        chain(false, tmem + s * FT, c, 0, 4, c == 0);
-                        chain(false, tmem + s * FT, c, 1, 4, false);
-                    }
-                if (stamp) p.timeline[it * 8 + 2] = clock64();       // main chain issued
-                mbar_wait<false>(&bar_yready, it & 1);   // y_{it-1} is in the state tile
-                tc_fence_after();
-                for (int s = 0; s < S; ++s) {
-                    chain(false, tmem + s * FT, C - 1, 0, gm.kaug, false);
-                    chain(false, tmem + s * FT, C - 1, 1, gm.kaug, false);
-                }
-                umma_commit(&bar_d);
-                if (stamp) p.timeline[it * 8 + 3] = clock64();       // everything issued
-            }
-        }
-    } else {
-        // ================= epilogue warps: TMEM -> tanh -> fp16 hi/lo state =================
-        const int e = warp - 4, q = warp & 3, s = e >> 2;
-        if (s < S) {
-            const int n = s * 128 + q * 32 + lane;         // neuron of this thread (TMEM lane)
-            const bool n_ok = n < p.N;
-            const int k = n & 63;
-            const float dscale = ldexpf(1.0f, -(SX + SW)), xscale = ldexpf(1.0f, SX);
-            const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + s * FT;
-            const bool use_noise = p.noise_amp != 0.f;
-            const uint32_t nmul = (uint32_t)(n >> 1) * 0xC2B2AE35U;
-            const uint32_t tile = smem_u32(st_hi) + (n >> 6) * STILE + (k & 7) * 2;
-            uint32_t goff[8];                              // row-in-group + swizzled granule offsets
-#pragma unroll
-            for (int i = 0; i < 8; ++i) goff[i] = i * 128 + ((((k >> 3) & 7) ^ i) << 4);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_state);        // initial state is in place
-            for (int it = 0; it < p.T; ++it) {
-                mbar_wait<true>(&bar_d, it & 1);
-                tc_fence_after();
-                if (p.timeline && blockIdx.x == 0 && warp == 4 && lane == 0) p.timeline[it * 8 + 4] = clock64();
-                const uint32_t *keys = s_key[it & 1];
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t v[32];
-                    tmem_ld32(lane_base + half * 32, v);
-                    tmem_ld_wait();
-                    const uint32_t hbase = tile + half * 4096;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int f = half * 32 + j;
-                        float x = tanh_f32(__uint_as_float(v[j]) * dscale);
-                        if (use_noise) {
-                            float u;
-                            if (DBG && p.noise) {
-                                const int b = tile0 + f;
-                                u = (b < p.B && n_ok) ? p.noise[((size_t)b * p.T + it) * p.N + n] : 0.5f;
-                            } else {
-                                const uint32_t hb = esn_fold32(keys[f] + nmul);
-                                u = (float)((n & 1) ? (hb >> 16) : (hb & 0xFFFFu)) * (1.0f / 65536.0f);
-                            }
-                            x = fmaf(u, p.noise_amp, x - 0.5f * p.noise_amp);
-                        }
-                        if (!n_ok || (!full_tile && tile0 + f >= p.B)) x = 0.f;
-                        if (DBG && p.ext_out && n_ok && tile0 + f < p.B)
-                            p.ext_out[((size_t)(tile0 + f) * p.T + it) * P + n] = x;
-                        split_sts(hbase + (j >> 3) * 1024 + goff[j & 7], lo_delta, x * xscale);
-                    }
-                }
-                fence_async_smem();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_state);
-                if (p.timeline && blockIdx.x == 0 && warp == 4 && lane == 0) p.timeline[it * 8 + 5] = clock64();
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 3) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
-    }
-}
-
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -603,9 +247,6 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // Signal-only remote arrive (no data published by this thread): relaxed, so no
 // MEMBAR.ALL.GPU is emitted (release.cluster costs one per arrive).
@@ -649,39 +290,12 @@ __device__ __forceinline__ void umma2_commit_pair(uint64_t *bar) {     // arrive
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
 }
-__device__ __forceinline__ void sts_cluster_u16(uint32_t cluster_addr, unsigned short v) {
-    asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(cluster_addr), "h"(v) : "memory");
-}
-__device__ __forceinline__ void split_sts_cluster(uint32_t addr, uint32_t lo_delta, float xs) {
-    const __half h = __float2half_rn(xs);
-    const __half l = __float2half_rn(xs - __half2float(h));
-    sts_cluster_u16(addr, __half_as_ushort(h));
-    sts_cluster_u16(addr + lo_delta, __half_as_ushort(l));
-}
 
-// ---- pair-kernel state tile: MN-major (frames contiguous), SWIZZLE_128B -----------------
-// chunk c = 64 k-rows x 128 B (this CTA's 64 frames); 8-row atoms of 1024 B; inside an atom
-// the 16-byte granule (8 frames) g of row k sits at position g ^ (k & 7).  A thread that owns
-// neuron k therefore writes its 64 frames as eight 16-byte stores into one 128-byte row.
-__host__ __device__ inline int mn128_off(int k, int f) {          // k < 64 within the chunk, f < 64
-    return (k >> 3) * 1024 + (k & 7) * 128 + ((((f >> 3) & 7) ^ (k & 7)) << 4) + (f & 7) * 2;
-}
-__device__ __forceinline__ void sts_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d)
-                 : "memory");
-}
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {   // -> {lo half, hi half}
     uint32_t r;
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
-__device__ __forceinline__ uint32_t umma_idesc_major(int M, int N, int a_mn, int b_mn) {
-    return umma_idesc(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
-}
-// MN-major SWIZZLE_128B descriptor, low word: start address, LBO = 0 (a second 64-wide MN block
-// aliases the first: only used by the readout chain, whose rows 64..127 are don't-care)
-__device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr) { return (saddr >> 4) & 0x3FFF; }
-
 constexpr int PF = 2 * FT;             // frames per CTA pair
 constexpr int SLOT2 = SLOT + 2048;     // pair-kernel ring slot: weight tile (128 rows) + up to 16 readout rows
 constexpr int X1ROWS = 72;             // B rows per CTA of the first X MMA (N = 144); the second takes 56 + readout rows
@@ -856,7 +470,7 @@ __device__ __forceinline__ void tc2_epilogue_blk(const TcParams &p, const uint32
 // one N = 256 MMA per k-step), G1 = slabs 2 + r (+ readout rows in CTA 0; neurons 256..511).  The
 // epilogue rewrites the state in the order chunks {0,2}, chunks {1,3}, chunks 4..7, so that the next
 // step's MMAs start as early as possible and overlap the rest of the epilogue:
-//   wait tA0 (chunks 0, 2 rewritten in both CTAs; G0 accumulators drained) -> G0 items of chunks 0, 2
+//   wait tA0 (chunks 0, 2 rewritten in both CTAs; ALL G0 accumulators in registers) -> G0 items of chunks 0, 2
 //   wait tA1 (chunks 1, 3 rewritten)                                       -> G0 items of chunks 1, 3
 //   wait tD1 (G1 accumulators drained)                                     -> G1 items of chunks 0..3
 //   wait tB  (everything rewritten)  -> G1 items of chunks 4..7 -> commit y
@@ -1229,10 +843,8 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
             __syncwarp();
             if (lane == 0) arrive0(local, remote);
         };
-        auto block16 = [&](int it, int col, int n0) {
-            uint32_t v[16];
-            tmem_ld16(lane_tm + (uint32_t)col, v);
-            tmem_ld_wait();
+        // one 16-neuron block whose accumulators v[] are already in registers
+        auto block16 = [&](int it, const uint32_t (&v)[16], int n0) {
             float m = 0.f;
 #pragma unroll
             for (int i = 0; i < 16; i += 2) m = fmaxf(m, fmaxf(fabsf(__uint_as_float(v[i])), fabsf(__uint_as_float(v[i + 1]))));
@@ -1285,10 +897,16 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
             tc_fence_after();
             if (st4) p.timeline[it * 8 + 4] = clock64();
             if (two) {
-                block16(it, 16 * cq, 128 * hl + 16 * cq);
+                // BOTH G0 blocks leave TMEM before the first barrier: the next step's first G0 MMA
+                // overwrites every G0 column, whichever state chunk it reads
+                uint32_t va[16], vb[16];
+                tmem_ld16(lane_tm + (uint32_t)(16 * cq), va);
+                tmem_ld16(lane_tm + (uint32_t)(64 + 16 * cq), vb);
+                tmem_ld_wait();
+                block16(it, va, 128 * hl + 16 * cq);
                 publish(&bar_tA0, r_tA0);
                 if (st4) p.timeline[it * 8 + 5] = clock64();
-                block16(it, 64 + 16 * cq, 128 * hl + 64 + 16 * cq);
+                block16(it, vb, 128 * hl + 64 + 16 * cq);
                 publish(&bar_tA1, r_tA1);
                 block32(it, 128 + 32 * cq, 256 + 128 * hl + 32 * cq);
             } else {
@@ -1356,13 +974,12 @@ extern "C" int esn_tc_predict(const esn_tc_predict_args *a, void *stream) {
     p.steps = harvest ? a->T - 1 : a->T;
     p.row0 = harvest ? 1 : 0;
     const TcGeom gm = tc_geom(a->N, a->n_in);
-    const size_t smem = (size_t)2 * gm.C * STILE + (size_t)NST * SLOT + 1024;
-    if (smem > 227 * 1024 - 1024) return ESN_E_TOOLARGE;
     const bool dbg = a->noise_uniforms || a->ext_out;
-    if (gm.S % 2 == 0 && !a->single_cta) {
+    {
         // CTA-pair kernel (cta_group::2): 128 frames per 2-CTA cluster
         const int grid2 = 2 * ((a->B + PF - 1) / PF);
         const size_t smem = (size_t)2 * gm.C * STILE + (size_t)NST * SLOT2 + 1024;
+        if (smem > 227 * 1024 - 2048) return ESN_E_TOOLARGE;
         // tensor maps over the two images, as rows of 512 bytes (they are pre-swizzled: plain copies)
         typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                       const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -1400,14 +1017,4 @@ extern "C" int esn_tc_predict(const esn_tc_predict_args *a, void *stream) {
         if (rc) return rc;
         return esn_launch_status();
     }
-    if (harvest) return ESN_E_UNSUPPORTED;                   // teacher-forced mode exists in the pair kernel only
-    const int grid = (a->B + FT - 1) / FT;
-    if (dbg) {
-        ESN_CUDA_TRY(cudaFuncSetAttribute(esn_predict_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        esn_predict_tc<true><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
-    } else {
-        ESN_CUDA_TRY(cudaFuncSetAttribute(esn_predict_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        esn_predict_tc<false><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
-    }
-    return esn_launch_status();
 }

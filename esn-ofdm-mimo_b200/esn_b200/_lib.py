@@ -49,7 +49,7 @@ class TcPredictArgs(C.Structure):
         ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("t_scale", C.c_void_p), ("t_shift", C.c_void_p),
         ("group_ids", C.c_void_p), ("x0", C.c_void_p), ("y0", C.c_void_p), ("noise_uniforms", C.c_void_p),
         ("ext_out", C.c_void_p), ("y_out", C.c_void_p), ("timeline", C.c_void_p),
-        ("single_cta", C.c_int32), ("teacher", C.c_void_p),
+        ("reserved", C.c_int32), ("teacher", C.c_void_p),
     ]
 
 

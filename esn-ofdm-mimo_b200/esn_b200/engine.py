@@ -178,9 +178,9 @@ class Reservoir:
         return bool(self.lib.esn_tc_supported(self.N, self.n_in, self.n_out))
 
     def tc_tile_frames(self):
-        """Frames that must share one readout on the tensor-core path: 128 for
-        the CTA-pair kernel (N padded to 256 or 512), else 64."""
-        return 128 if ((self.N + 127) // 128) % 2 == 0 else 64
+        """Frames that must share one readout on the tensor-core path: the 128
+        frames of a CTA pair."""
+        return 128
 
     def input_scale_exponent(self, inputs):
         """su_exp for the tensor-core path: the power of two that brings the
@@ -238,9 +238,9 @@ class Reservoir:
         return TcReadout(weights, image, yscale, int(su_exp), sy_exp, G)
 
     def predict_tc(self, inputs, readout, transient=0, group_ids=None, x0=None, y0=None,
-                   noise_uniforms=None, seed=0, return_ext=False, timeline=None, single_cta=False):
+                   noise_uniforms=None, seed=0, return_ext=False, timeline=None):
         """Free-running prediction on the tensor cores.  `readout` comes from
-        tc_prepare; each 64-frame tile must use a single readout."""
+        tc_prepare; each 128-frame tile must use a single readout."""
         inputs = self._as(inputs, torch.float32, 3)
         B, T, n_in = inputs.shape
         if n_in != self.n_in:
@@ -279,7 +279,6 @@ class Reservoir:
             a.ext_out = ptr(ext)
         y = torch.empty((B, T - int(transient), self.n_out), dtype=torch.float32, device=self.device)
         a.y_out = ptr(y)
-        a.single_cta = int(bool(single_cta))
         if timeline is not None:           # [T+1, 8] int64 device tensor (profiling aid)
             a.timeline = ptr(timeline)
         check(self.lib.esn_tc_predict(C.byref(a), _stream()), "esn_tc_predict")
@@ -291,8 +290,8 @@ class Reservoir:
         relative error, so W_out trained on them differs from the fp64 fit by more than
         the 1e-4 parity bar (the noise regulariser itself moves states by ~1e-2); use
         precision='fp64' where W_out parity is asserted."""
-        if not self.tc_supported() or self.tc_tile_frames() != 128:
-            raise EsnB200Error("tensor-core harvest needs the CTA-pair kernel (N padded to 256 or 512)")
+        if not self.tc_supported():
+            raise EsnB200Error("tensor-core path needs N <= 512, n_inputs <= 24, n_outputs <= 16")
         inputs = self._as(inputs, torch.float32, 3)
         teachers = self._as(teachers, torch.float32, 3)
         B, T, n_in = inputs.shape

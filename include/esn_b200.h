@@ -143,8 +143,8 @@ typedef struct esn_tc_predict_args {
     float *ext_out;             /* [B][T][N+n_in] or null */
     float *y_out;               /* [B][T-transient][n_out] */
     void *timeline;             /* profiling aid: [T+1][8] int64 SM-clock stamps of CTA 0, or null */
-    int32_t single_cta;         /* 1 = force the one-CTA kernel (default 0: CTA-pair kernel when N_pad is 256 or 512) */
-    const float *teacher;       /* harvest mode (CTA-pair kernel only): [B][T][n_out] raw teachers; the recurrence is
+    int32_t reserved;           /* must be 0 */
+    const float *teacher;       /* harvest mode: [B][T][n_out] raw teachers; the recurrence is
                                    teacher-forced as in ESN.fit (libs/pyESN.py:179-182), ext_out [B][T][N+n_in] is
                                    required, readouts / yscale / y_out are ignored.  null = free-running predict */
 } esn_tc_predict_args;

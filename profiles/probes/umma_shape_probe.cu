@@ -10,6 +10,14 @@
 #include <cstdio>
 #include "../../esn-ofdm-mimo_b200/csrc/recurrence_tc.cu"
 
+namespace {
+__device__ __forceinline__ uint32_t umma_idesc_major(int M, int N, int a_mn, int b_mn) {
+    return umma_idesc(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+}
+// MN-major SWIZZLE_128B descriptor, low word: start address, LBO = 0
+__device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr) { return (saddr >> 4) & 0x3FFF; }
+}  // namespace
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe(int mode, int n, long long *out) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bar;

@@ -2,9 +2,9 @@
 """Per-step phase timing of the tensor-core recurrence kernel (CTA 0), from the
 kernel's own SM-clock stamps (esn_tc_predict_args.timeline).  Run on the GPU box:
     python profiles/tc_timeline.py [frames]
-Rows (cycles): the issuer's waits for the two state barriers (sA: chunks 0-3 rewritten,
-sB: everything rewritten), its issue phases (ring-bound when the data is late) and the two
-halves of the epilogue (warp 4)."""
+Rows (cycles): the issuer's waits for the state barriers (tA0: chunks 0, 2 rewritten and every G0
+accumulator read; tB: everything rewritten), its issue phases (ring-bound when the data is late) and
+the epilogue of warp 4 (first 16-neuron block, then the rest)."""
 import os
 import sys
 
@@ -34,13 +34,13 @@ full = tl.cpu().numpy()
 t = full[50:500]
 step = t[1:, 0] - t[:-1, 0]
 rows = (("step", step),
-        ("wait sA (group-0 state)", t[:, 1] - t[:, 0]),
-        ("phase 1 issue (g0 c0-3 + y)", t[:, 2] - t[:, 1]),
-        ("wait sB (all state)", t[:, 3] - t[:, 2]),
-        ("phase 2 issue (g0 c4-7 + y, g1)", t[:, 7] - t[:, 3]),
-        ("wait y + aug -> epilogue start", t[:, 4] - t[:, 7]),
-        ("epilogue group 0 (+arrive)", t[:, 5] - t[:, 4]),
-        ("epilogue group 1 (+arrive)", t[:, 6] - t[:, 5]))
+        ("wait tA0 (chunks 0,2 rewritten)", t[:, 1] - t[:, 0]),
+        ("issue G0 c0-3, G1 c0-3", t[:, 2] - t[:, 1]),
+        ("wait tB (all state rewritten)", t[:, 3] - t[:, 2]),
+        ("issue G1 c4-7 (y), G0 c4-6", t[:, 7] - t[:, 3]),
+        ("wait y, aug, G0 c7 -> D ready", t[:, 4] - t[:, 7]),
+        ("epilogue block a (+publish)", t[:, 5] - t[:, 4]),
+        ("epilogue block b + G1", t[:, 6] - t[:, 5]))
 for name, v in rows:
     print(f"{name:32s} mean {v.mean():9.0f}  p10 {np.percentile(v, 10):9.0f}  p90 {np.percentile(v, 90):9.0f} cycles")
 
