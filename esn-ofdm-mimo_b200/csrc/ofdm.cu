@@ -52,6 +52,52 @@ __device__ void fft_inplace(T *re, T *im, const T *twr, const T *twi, int N, int
     }
 }
 
+// Skewed shared-memory index: one pad word per 32 keeps the power-of-two strides of the FFT (and the
+// bit-reversed scatter of its input) off a single bank.
+__device__ __forceinline__ int skew(int i) { return i + (i >> 5); }
+
+// r radix-2 layers (stages s0+1 .. s0+r of the DIT on bit-reversed data) fused in registers: each work
+// item loads 2^r points at stride 2^s0, runs the r butterfly layers and stores them back, so a 512-point
+// FFT takes 3 passes over shared memory instead of 9.  `nb` arrays of N points side by side (skewed).
+template <typename T, int r>
+__device__ __forceinline__ void fft_pass(T *re, T *im, const T *twr, const T *twi, int N, int logn, int s0, int nb) {
+    constexpr int R = 1 << r;
+    const int h = 1 << s0, per = N >> r, items = per * nb;
+    for (int q = threadIdx.x; q < items; q += blockDim.x) {
+        const int a = q >> (logn - r), j = q & (per - 1);
+        const int pos = j & (h - 1), base = a * N + ((j >> s0) << (s0 + r)) + pos;
+        T xr[R], xi[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) { xr[k] = re[skew(base + k * h)]; xi[k] = im[skew(base + k * h)]; }
+#pragma unroll
+        for (int l = 0; l < r; ++l) {
+            const int d = 1 << l, tstride = N >> (s0 + l + 1);
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                if ((k & d) == 0) {
+                    const int pw = (pos + (k & (d - 1)) * h) * tstride;
+                    const T wr = twr[pw], wi = twi[pw];
+                    const T tr = wr * xr[k + d] - wi * xi[k + d], ti = wr * xi[k + d] + wi * xr[k + d];
+                    xr[k + d] = xr[k] - tr; xi[k + d] = xi[k] - ti;
+                    xr[k] += tr; xi[k] += ti;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) { re[skew(base + k * h)] = xr[k]; im[skew(base + k * h)] = xi[k]; }
+    }
+    __syncthreads();
+}
+// forward FFT of nb arrays already in bit-reversed order (caller has synchronised)
+template <typename T>
+__device__ void fft_batched_radix8(T *re, T *im, const T *twr, const T *twi, int N, int logn, int nb) {
+    int s0 = 0;
+    const int rem = logn % 3;
+    if (rem == 1) { fft_pass<T, 1>(re, im, twr, twi, N, logn, 0, nb); s0 = 1; }
+    if (rem == 2) { fft_pass<T, 2>(re, im, twr, twi, N, logn, 0, nb); s0 = 2; }
+    for (; s0 < logn; s0 += 3) fft_pass<T, 3>(re, im, twr, twi, N, logn, s0, nb);
+}
+
 __device__ __forceinline__ int ilog2(int n) { return 31 - __clz(n); }
 
 template <typename T>
@@ -123,6 +169,57 @@ __global__ void unpack_fft_demap_kernel(const T *__restrict__ y, int rows, int N
     for (int k = threadIdx.x; k < N; k += blockDim.x) {
         const T xr = re[k] * scale, xi = im[k] * scale;
         const size_t o = ((size_t)b * N + k) * N_t + tx;
+        if (X_hat) { X_hat[2 * o] = xr; X_hat[2 * o + 1] = xi; }
+        const int id = sl.index(xr, xi);
+        if (idx) idx[o] = (uint8_t)id;
+        if (tx_idx) errs += __popc((unsigned)(id ^ (int)tx_idx[o]));
+        if (eps > (T)0 && sl.boundary_dist(xr, xi) < eps) near += 1;
+    }
+    block_add_counts(errs, near, counts);
+}
+
+// One CTA per frame, all N_t streams at once: the frame's N x 2 N_t block of ESN outputs is read with
+// fully coalesced loads, the N_t FFTs run side by side in shared memory, and symbol indices / X_hat are
+// written as contiguous rows.  Algorithmic traffic: N (2 N_t) reals in, N N_t bytes (+ N N_t for tx_idx)
+// out -- one pass over HBM.
+template <typename T>
+__global__ void __launch_bounds__(512)
+unpack_fft_demap_frame_kernel(const T *__restrict__ y, int rows, int N, int N_t, const T *__restrict__ Pi,
+                              int pi_stride, int qam_bits, T *__restrict__ X_hat, uint8_t *__restrict__ idx,
+                              const uint8_t *__restrict__ tx_idx, T eps, unsigned long long *__restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int tot = N * N_t, tots = tot + (tot >> 5) + 1;             // skewed array length
+    T *re = reinterpret_cast<T *>(sm), *im = re + tots, *twr = im + tots, *twi = twr + N / 2;
+    const int b = blockIdx.x, logn = ilog2(N), W2 = 2 * N_t;
+    const bool w2pow2 = (W2 & (W2 - 1)) == 0;                         // shifts instead of integer divisions
+    const int lw2 = ilog2(W2);
+    fft_make_twiddles(twr, twi, N);
+    const T *yb = y + (size_t)b * rows * W2;
+    for (int e0 = 0; e0 < N * W2; e0 += 8 * blockDim.x) {             // contiguous, coalesced, 8 loads in flight
+        T v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = e0 + i * blockDim.x + threadIdx.x;
+            v[i] = e < N * W2 ? yb[e] : (T)0;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = e0 + i * blockDim.x + threadIdx.x;
+            if (e < N * W2) {
+                const int t = w2pow2 ? (e >> lw2) : e / W2, c = e - t * W2;
+                ((c & 1) ? im : re)[skew((c >> 1) * N + bitrev(t, logn))] = v[i];
+            }
+        }
+    }
+    __syncthreads();
+    fft_batched_radix8(re, im, twr, twi, N, logn, N_t);              // N_t FFTs side by side, 3 layers per pass
+    const T scale = (T)1 / ((T)N * sqrt_t(Pi[(size_t)b * pi_stride]));
+    const Slicer<T> sl(qam_bits);
+    unsigned long long errs = 0, near = 0;
+    for (int e = threadIdx.x; e < N * N_t; e += blockDim.x) {          // e = k N_t + tx: contiguous outputs
+        const int k = w2pow2 ? (e >> (lw2 - 1)) : e / N_t, tx = e - k * N_t;
+        const T xr = re[skew(tx * N + k)] * scale, xi = im[skew(tx * N + k)] * scale;
+        const size_t o = (size_t)b * N * N_t + e;
         if (X_hat) { X_hat[2 * o] = xr; X_hat[2 * o + 1] = xi; }
         const int id = sl.index(xr, xi);
         if (idx) idx[o] = (uint8_t)id;
@@ -410,6 +507,24 @@ extern "C" int ofdm_unpack_fft_demap(int dtype, const void *y, int B, int rows, 
     if (qam_bits != 2 && qam_bits != 4 && qam_bits != 6) return ESN_E_BADARG;
     dim3 grid(N_t, B);
     cudaStream_t st = (cudaStream_t)stream;
+    // whole-frame kernel when the N_t streams fit in shared memory together (always at the demo sizes)
+    const size_t el = dtype == ESN_F64 ? sizeof(double) : sizeof(float);
+    const size_t frame_smem = ((size_t)2 * ((size_t)N * N_t + (size_t)N * N_t / 32 + 1) + N) * el;
+    if (frame_smem <= 160 * 1024 && (dtype == ESN_F32 || dtype == ESN_F64)) {
+        const int threads = std::min(256, std::max(64, (N / 8) * N_t));
+        if (dtype == ESN_F32) {
+            if (int rc = allow_smem(unpack_fft_demap_frame_kernel<float>, frame_smem)) return rc;
+            unpack_fft_demap_frame_kernel<float><<<B, threads, frame_smem, st>>>(
+                (const float *)y, rows, N, N_t, (const float *)Pi, pi_stride, qam_bits, (float *)X_hat, idx, tx_idx,
+                (float)boundary_eps, counts);
+        } else {
+            if (int rc = allow_smem(unpack_fft_demap_frame_kernel<double>, frame_smem)) return rc;
+            unpack_fft_demap_frame_kernel<double><<<B, threads, frame_smem, st>>>(
+                (const double *)y, rows, N, N_t, (const double *)Pi, pi_stride, qam_bits, (double *)X_hat, idx, tx_idx,
+                boundary_eps, counts);
+        }
+        return esn_launch_status();
+    }
     if (int rc = dtype == ESN_F64 ? allow_smem(unpack_fft_demap_kernel<double>, 3 * (size_t)N * sizeof(double)) : 0) return rc;
     if (dtype == ESN_F32)
         unpack_fft_demap_kernel<float><<<grid, fft_threads(N), 3 * N * sizeof(float), st>>>(
