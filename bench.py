@@ -180,6 +180,35 @@ def cpu_throughput(frames_per_worker, workers, target_seconds=None):
     return frames_per_worker * workers / dt, dt, frames_per_worker
 
 
+def _cpu_fit_worker(args):
+    """`n` readout fits (harvest + pinv, oracle port of ESN.fit) on one core."""
+    seed, n = args
+    from threadpoolctl import threadpool_limits
+    from oracle import esn_oracle as orc
+    with threadpool_limits(limits=1):
+        st = _cpu_state()
+        rng = np.random.RandomState(seed)
+        for _ in range(n):
+            u = rng.randn(T_STEPS, CFG["n_in"])
+            y = rng.randn(T_STEPS, CFG["n_out"])
+            uni = rng.rand(T_STEPS - 1, CFG["n_res"])
+            orc.fit(st["W"], st["W_in"], st["W_fb"], u, y, TRANSIENT, CFG["noise"], uni,
+                    input_scaling=st["in_scale"], input_shift=None, teacher_scaling=CFG["t_scale"], teacher_shift=None)
+    return n
+
+
+def cpu_fit_throughput(workers, fits_per_worker=2):
+    """Readouts trained per second by the oracle port on `workers` host processes (1 BLAS thread each)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        pool.map(_cpu_fit_worker, [(i, 1) for i in range(workers)])
+        t0 = time.perf_counter()
+        pool.map(_cpu_fit_worker, [(200 + i, fits_per_worker) for i in range(workers)])
+        dt = time.perf_counter() - t0
+    return workers * fits_per_worker / dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -431,7 +460,9 @@ def run_gpu(args):
                "fits_per_s": world * Gf / (fit_total * 1e-3),
                "what": "teacher-forced harvest on the tensor cores + fp64 dual Gram (512x512) + Cholesky + readout images",
                "fit_detect_symbols_per_s": world * per_group / ((us_fit + per_group * us_det) * 1e-6),
-               "block": f"1 pilot + {per_group} data frames per coherence block (reference L = 19)"}
+               "block": f"1 pilot + {per_group} data frames per coherence block",
+               # the reference's own coherence block at N = 512: every 19th symbol is a pilot (L = 19)
+               "fit_detect_symbols_per_s_L19": world * 18 / ((us_fit + 18 * us_det) * 1e-6)}
         del fu, fy
     os.sched_setaffinity(0, all_cpus)            # the CPU-baseline leg uses every host core
     counts.zero_()
@@ -451,6 +482,8 @@ def run_gpu(args):
         cpu = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
                "sample": f"{fpw * workers} frames of the same workload "
                          f"({dt:.1f} s; numpy float64 oracle port, one process per core, 1 BLAS thread each)"}
+        if fit is not None:
+            fit["cpu_fits_per_s"] = cpu_fit_throughput(workers)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

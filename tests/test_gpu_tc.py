@@ -116,6 +116,24 @@ def test_tc_padded_reservoir_and_small_io():
         _check(eng, Ws, aff, us, W_outs, None, T, 2, 0.001, uni)
 
 
+def test_tc_widest_io_and_harvest():
+    """n_in = 24 and n_out = 16 (the widest blocks the path accepts: three input granules, sixteen readout
+    rows, N = 144 second MMA) with a feedback strong enough to matter; predict and harvest."""
+    rng, Ws, aff, eng = _setup(200, 24, 16, seed=11, noise=0.001, in_scale=0.02, t_scale=2e-2)
+    B, T, N = 140, 24, 200
+    us = rng.randn(B, T, 24)
+    W_outs = rng.randn(2, 16, N + 24) * 2e-3
+    gid = np.array([0] * 128 + [1] * 12)
+    uni = rng.rand(B, T, N)
+    _check(eng, Ws, aff, us, W_outs, gid, T, 1, 0.001, uni, frames=[0, 70, 127, 128, 139])
+    ts = rng.randn(B, T, 16)
+    ext = eng.harvest(_cuda(us), _cuda(ts), precision="tc", noise_uniforms=_cuda(uni[:, :T - 1])).double().cpu().numpy()
+    for b in (0, 127, 139):
+        r = orc.fit(Ws[0], Ws[1], Ws[2], us[b], ts[b], 1, 0.001, uni[b, :T - 1], **aff)
+        assert rel_err(ext[b, :, :N], r["states"]) < 1e-5
+        assert rel_err(ext[b, :, N:], r["in_s"]) < 1e-6
+
+
 def test_tc_continuation_and_strong_feedback():
     """continuation=True semantics (explicit x0 / y0) and a teacher scale large
     enough that the W_fb y term matters (SISO demo regime)."""
