@@ -428,8 +428,9 @@ __global__ void synth_frames_kernel(const uint8_t *__restrict__ tx_idx, const T 
         for (int k = threadIdx.x; k < N; k += blockDim.x) {
             const int id = tx_idx[((size_t)b * N + k) * N_t + tx];
             const int r = bitrev(k, logn);
-            re[r] = (T)(2 * (id / side) - (side - 1)) * cs;       // index = side*i_re + i_im
-            im[r] = (T)(2 * (id % side) - (side - 1)) * cs;
+            // index = side*i_re + i_im; 255 = empty subcarrier (the comb pilot of the LS estimator)
+            re[r] = id == 255 ? (T)0 : (T)(2 * (id / side) - (side - 1)) * cs;
+            im[r] = id == 255 ? (T)0 : (T)(2 * (id % side) - (side - 1)) * cs;
         }
         fft_inplace(re, im, twr, twi, N, logn, true);             // = N * ifft(X)
         for (int t = threadIdx.x; t < L; t += blockDim.x) {

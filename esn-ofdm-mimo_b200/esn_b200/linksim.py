@@ -1,0 +1,148 @@
+"""Device-resident restatement of the block-fading demo loop (uncoded part) of the reference's System
+Model 2 template (system_model_2/OFDM_MIMO_2-2_NBF_LDPC.py:230-474 with USE_LDPC off): per coherence
+block one pilot OFDM symbol trains an ESN readout and yields the LS / MMSE channel estimates, the data
+symbols of the block are detected by the ESN and by the Perfect-ZF / LS-ZF / MMSE baselines, and bit
+errors are counted per detector.
+
+Where the reference walks symbol by symbol in Python, everything here is batched over all blocks of an
+SNR point: frame synthesis (`ofdm_synth_frames`), comb-pilot channel estimation (`ofdm_chanest`), readout
+training (harvest + Gram + Cholesky), one grouped `predict` over every data frame, equalisation and
+slicing + error counting kernels.  One reservoir (fixed `random_state`) serves all blocks, each block
+gets its own W_out.  Blocks shard over ranks; counters are summed with one allreduce.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import dist as D
+from . import ofdm
+
+DETECTORS = ("ESN", "Perfect_ZF", "LS_ZF", "MMSE")
+
+
+def isi_profile(isi, device):
+    """Exponential power-delay profile of the template (:162-164), normalised to unit sum."""
+    mag = torch.exp(-torch.arange(isi, dtype=torch.float64, device=device) / ((isi - 1) / 9))
+    return mag / mag.sum()
+
+
+def comb_pilot(pil_idx):
+    """LS comb pilot: Tx `tx` keeps the pilot symbols on subcarriers tx::N_t, the rest is empty (:287-289)."""
+    G, N, N_t = pil_idx.shape
+    k = torch.arange(N, device=pil_idx.device)[:, None]
+    tx = torch.arange(N_t, device=pil_idx.device)[None, :]
+    keep = (k % N_t) == tx
+    return torch.where(keep[None], pil_idx, torch.full_like(pil_idx, 255))
+
+
+def const_table(qam_bits, device, dtype=torch.complex128):
+    side = 1 << (qam_bits // 2)
+    pam = torch.arange(-(side - 1), side, 2, dtype=torch.float64, device=device)
+    c = (pam[:, None] + 1j * pam[None, :]).reshape(-1)
+    return (c / math.sqrt(2.0 * (side * side - 1) / 3.0)).to(dtype)
+
+
+def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_bits, isi=8, No=1e-5,
+                  clip_db=3.0, delay=None, fit_precision="fp64", detect_precision="fp32", seed=0,
+                  noise_pilot=None, noise_data=None, state_noise_seed=1):
+    """One SNR point on this rank's blocks.
+
+    res             Reservoir with n_inputs = 2 N_r, n_outputs = 2 N_t (input_scaling as the template:
+                    0.005 / sqrt(var_x), :237-241)
+    pil_idx         [G, N, N_t] uint8 pilot symbol indices (one pilot OFDM symbol per coherence block)
+    data_idx        [B, N, N_t] uint8 data symbol indices, block_of_frame [B] int32 in [0, G)
+    taps            [G, N_r, N_t, isi] complex channel taps
+    noise_*         optional standard-normal complex noise [G or B, N+cp, N_r] (else the device stream)
+    Returns {detector: int64 tensor [bit errors, bits]} and the extras used by the tests.
+    """
+    dev = pil_idx.device
+    G, _, N_t = pil_idx.shape
+    B = data_idx.shape[0]
+    N_r = taps.shape[1]
+    cp = isi - 1
+    Pi = 10 ** (ebno_db / 10) * No
+    var_x = Pi * N
+    A_clip = math.sqrt(var_x) * 10 ** (clip_db / 20)
+    std = math.sqrt((N + cp) * No / 2)
+    if delay is None:                                   # DelayFlag == 0: (Min + Max) // 2, Max = ceil(isi/2) + 2
+        delay = (0 + int(math.ceil(isi / 2) + 2)) // 2
+    transient = delay + cp
+    rd = torch.float64 if fit_precision == "fp64" else torch.float32
+    taps = taps.to(dev)
+    # ---- pilot symbol of every block: ESN training pair and the comb pilot through the same channel/noise
+    pil = ofdm.synth_frames(pil_idx, taps, Pi, A_clip, N, cp, qam_bits, std, delay=delay, noise=noise_pilot,
+                            seed=seed, dtype=torch.float64, want_x_cp=True)
+    ls = ofdm.synth_frames(comb_pilot(pil_idx), taps, Pi, A_clip, N, cp, qam_bits, std, noise=noise_pilot,
+                           seed=seed, dtype=torch.float64, want_esn_in=False)
+    teacher = torch.zeros((G, N + cp + delay, 2 * N_t), dtype=torch.float64, device=dev)
+    teacher[:, delay:, :] = torch.view_as_real(pil["x_cp"]).reshape(G, N + cp, 2 * N_t)
+    ext = res.harvest(pil["esn_in"].to(rd), teacher.to(rd), precision=fit_precision, seed=state_noise_seed)
+    W_out, info = res.train_readout(ext, teacher, transient)
+    if int(info.abs().max()) != 0:
+        raise np.linalg.LinAlgError("readout training failed for block %d" % int(torch.nonzero(info)[0]))
+    del ext
+    # ---- channel estimates from the comb pilot (:316-334) and the true channel
+    const = const_table(qam_bits, dev)
+    X_LS = torch.where(comb_pilot(pil_idx) == 255, torch.zeros((), dtype=const.dtype, device=dev),
+                       const[pil_idx.long()])
+    Y_LS = ofdm.rx_fft(ls["y_cp"], N, cp)
+    H_LS, H_MMSE = ofdm.chanest(Y_LS, X_LS, Pi, isi_profile(isi, dev), isi, No)
+    H_true = torch.fft.fft(taps.to(torch.complex128), n=N, dim=3).permute(0, 3, 1, 2).contiguous()   # [G,N,N_r,N_t]
+    # ---- data symbols
+    dd = torch.float32 if detect_precision in ("fp32", "tc") else torch.float64
+    fr = ofdm.synth_frames(data_idx, taps.to(torch.complex64 if dd == torch.float32 else torch.complex128), Pi, A_clip,
+                           N, cp, qam_bits, std, delay=delay, chan_index=block_of_frame, noise=noise_data,
+                           seed=seed + 1, dtype=dd)
+    y = res.predict(fr["esn_in"], W_out, transient=transient, group_ids=block_of_frame, precision=detect_precision,
+                    seed=state_noise_seed + 1)
+    out = {}
+    total = B * N * N_t * qam_bits
+    _, _, c = ofdm.unpack_fft_demap(y, N, N_t, Pi, qam_bits, tx_idx=data_idx, want_xhat=False, want_idx=False)
+    out["ESN"] = c
+    Y = ofdm.rx_fft(fr["y_cp"], N, cp)
+    cd = Y.dtype
+    for name, H, reg in (("Perfect_ZF", H_true, 1e-12), ("LS_ZF", H_LS, 1e-12), ("MMSE", H_MMSE, No / Pi)):
+        X = ofdm.equalize(Y, H.to(cd), reg, math.sqrt(Pi), h_index=block_of_frame)
+        _, c = ofdm.demap_count(X, qam_bits, tx_idx=data_idx, want_idx=False)
+        out[name] = c
+    res_ = {k: torch.stack([v[0], torch.tensor(total, dtype=v.dtype, device=dev)]) for k, v in out.items()}
+    res_["_W_out"], res_["_delay"], res_["_transient"] = W_out, delay, transient
+    return res_
+
+
+def ber_curve(res_factory, N_t, N_r, N, qam_bits, ebno_db_list, n_blocks, frames_per_block, isi=8, No=1e-5, seed=0,
+              fit_precision="fp64", detect_precision="tc", device=None):
+    """BER-vs-SNR Monte-Carlo: for every Eb/N0, `n_blocks` coherence blocks of `frames_per_block` data
+    symbols (blocks sharded over ranks, counters summed over ranks).  `res_factory(var_x)` returns the
+    Reservoir for an SNR point (the template scales the inputs by 0.005 / sqrt(var_x)).  Returns
+    {detector: [BER per SNR]} plus 'EBN0'."""
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    rank, world = D.rank(), D.world()
+    g0, g1 = D.shard_range(n_blocks, rank, world)
+    G = g1 - g0
+    gen = torch.Generator(device=device)
+    curves = {k: [] for k in DETECTORS}
+    for si, ebno in enumerate(ebno_db_list):
+        gen.manual_seed(seed * 100003 + si * 1009 + rank)
+        counts = torch.zeros((len(DETECTORS), 2), dtype=torch.int64, device=device)
+        if G > 0:
+            mag = isi_profile(isi, device)
+            taps = (torch.randn((G, N_r, N_t, isi), generator=gen, device=device, dtype=torch.float64)
+                    + 1j * torch.randn((G, N_r, N_t, isi), generator=gen, device=device, dtype=torch.float64)) / math.sqrt(2)
+            taps = taps * mag.sqrt()
+            pil_idx = torch.randint(0, 2 ** qam_bits, (G, N, N_t), generator=gen, device=device, dtype=torch.uint8)
+            data_idx = torch.randint(0, 2 ** qam_bits, (G * frames_per_block, N, N_t), generator=gen, device=device,
+                                     dtype=torch.uint8)
+            blk = (torch.arange(G * frames_per_block, device=device) // frames_per_block).to(torch.int32)
+            res = res_factory(10 ** (ebno / 10) * No * N)
+            r = detect_blocks(res, pil_idx, data_idx, blk, taps, ebno, N, qam_bits, isi=isi, No=No,
+                              fit_precision=fit_precision, detect_precision=detect_precision,
+                              seed=seed * 7919 + si * 31 + rank * 3 + 11, state_noise_seed=seed + 17 * si + rank)
+            for di, k in enumerate(DETECTORS):
+                counts[di] = r[k]
+        D.allreduce_sum_(counts)
+        for di, k in enumerate(DETECTORS):
+            curves[k].append(float(counts[di, 0]) / max(1, int(counts[di, 1])))
+    curves["EBN0"] = [int(e) if float(e).is_integer() else float(e) for e in ebno_db_list]
+    return curves

@@ -235,7 +235,8 @@ int ofdm_chanest(int dtype, const void *Y_LS, const void *X_LS, int B, int N, in
  * [B][N+CP][N_r] complex and/or the real ESN input rows esn_in [B][N+CP+delay][2 N_r].
  * Replaces system_model_2/OFDM_MIMO_2-2_NBF_LDPC.py:402-426 (Tx chain, lfilter, AWGN) and
  * :430-433 (ESN input packing).  taps [n_chan][N_r][N_t][ntaps] complex, chan_index[b] or null
- * (= b); noise [B][N+CP][N_r] complex standard normals or null (device counter stream `seed`);
+ * (= b); a tx_idx of 255 is an empty subcarrier (comb pilots, :287-289);
+ * noise [B][N+CP][N_r] complex standard normals or null (device counter stream `seed`);
  * x_cp [B][N+CP][N_t] complex receives the unclipped Tx samples (the ESN teacher) or null. */
 int ofdm_synth_frames(int dtype, const uint8_t *tx_idx, const void *taps, const int32_t *chan_index,
                       const void *Pi, const void *A_clip, const void *noise, double noise_std,

@@ -166,3 +166,101 @@ def test_soft_demap_and_calibration_match_reference_golden(m, dt):
     hard, _ = ofdm.demap_count(X, m)
     bits = ((hard.cpu().numpy()[:, :, None, :] >> np.arange(m)[None, None, :, None]) & 1)
     assert np.array_equal((llr.cpu().numpy() < 0).astype(int), bits)
+
+
+# --------------------------------------------------------------------------
+# the batched demo loop (esn_b200.linksim) against the oracle's symbol-by-symbol loop
+# --------------------------------------------------------------------------
+def test_linksim_block_loop_matches_oracle_loop():
+    """3 coherence blocks x 4 data symbols, 2x2, N = 32: identical bits, channels and AWGN on both sides;
+    the ESN, Perfect-ZF, LS-ZF and MMSE error counts of the batched device loop equal those of the
+    oracle's per-symbol loop (OFDM_MIMO_2-2_NBF_LDPC.py:270-474, uncoded)."""
+    from esn_b200 import Reservoir, linksim
+    N, N_t, N_r, m, isi, ebno, No = 32, 2, 2, 4, 8, 15, 1e-5
+    G, per = 3, 4
+    cp = isi - 1
+    rng = np.random.RandomState(321)
+    Pi = 10 ** (ebno / 10) * No
+    var_x = Pi * N
+    A = math.sqrt(var_x) * 10 ** (3 / 20)
+    std = math.sqrt((N + cp) * No / 2)
+    mag = orc.isi_profile(isi)
+    taps = np.stack([orc.draw_channel(rng, N_r, N_t, mag, isi) for _ in range(G)])
+    pil_idx = rng.randint(0, 16, size=(G, N, N_t))
+    dat_idx = rng.randint(0, 16, size=(G * per, N, N_t))
+    nz_p = rng.randn(G, N + cp, N_r) + 1j * rng.randn(G, N + cp, N_r)
+    nz_d = rng.randn(G * per, N + cp, N_r) + 1j * rng.randn(G * per, N + cp, N_r)
+    blk = np.repeat(np.arange(G), per)
+    kw = dict(n_inputs=2 * N_r, n_outputs=2 * N_t, n_reservoir=40, spectral_radius=0.9, sparsity=0.1,
+              input_shift=np.zeros(2 * N_r), input_scaling=(0.005 / var_x ** 0.5) * np.ones(2 * N_r),
+              teacher_scaling=5e-7 * np.ones(2 * N_t), teacher_shift=np.zeros(2 * N_t), random_state=9, noise=0.0)
+    cpu = orc.OracleESN(**kw)
+    res = Reservoir(cpu.W, cpu.W_in, cpu.W_feedb, kw["input_scaling"], kw["input_shift"], kw["teacher_scaling"],
+                    kw["teacher_shift"], 0.0, True)
+    out = linksim.detect_blocks(res, _cuda(pil_idx.astype(np.uint8)), _cuda(dat_idx.astype(np.uint8)),
+                                _cuda(blk.astype(np.int32)), _cuda(taps), ebno, N, m, isi=isi, No=No,
+                                fit_precision="fp64", detect_precision="fp64", noise_pilot=_cuda(nz_p),
+                                noise_data=_cuda(nz_d))
+    # ---- the oracle's loop
+    const = orc.unit_qam_constellation(m)
+    maxd = int(math.ceil(isi / 2) + 2)
+
+    def rx(X, c, nz):
+        x_cp, x_nld = orc.tx_frame(X, N, cp, Pi, A)
+        y = np.zeros((N + cp, N_r), dtype=complex)
+        for nr in range(N_r):
+            for tx in range(N_t):
+                y[:, nr] += orc.fir_causal(c[nr, tx], x_nld[:, tx])
+        return x_cp, y + std * nz
+    errs = dict(ESN=0, Perfect_ZF=0, LS_ZF=0, MMSE=0)
+    for g in range(G):
+        Xp = const[pil_idx[g]]
+        x_cp_p, y_p = rx(Xp, taps[g], nz_p[g])
+        X_LS = np.zeros_like(Xp)
+        for tx in range(N_t):
+            X_LS[tx::N_t, tx] = Xp[tx::N_t, tx]
+        _, y_ls = rx(X_LS, taps[g], nz_p[g])
+        H_LS, H_MM = orc.channel_estimate(orc.rx_fft(y_ls, cp, N), X_LS, Pi, No, N, N_t, N_r, mag, isi)
+        H_true = np.fft.fft(np.concatenate([taps[g], np.zeros((N_r, N_t, N - isi))], axis=2), axis=2).transpose(2, 0, 1)
+        esn = orc.OracleESN(**kw)
+        r = orc.train_generic(esn, 0, 0, maxd, cp, N, N_t, N_r, isi, y_p, x_cp_p)
+        d, nforget = int(r[6]), int(r[7])
+        assert d == out["_delay"] and nforget == out["_transient"]
+        assert rel_err(out["_W_out"][g].cpu().numpy(), esn.W_out) < 1e-6
+        for f in range(per):
+            fi = g * per + f
+            _, y = rx(const[dat_idx[fi]], taps[g], nz_d[fi])
+            tb = orc.indices_to_bits(dat_idx[fi], m)
+            Xe = orc.esn_output_to_freq(esn.predict(orc.pack_rx(y, d), nforget, continuation=False), N, N_t, Pi)
+            Y = orc.rx_fft(y, cp, N)
+            cand = dict(ESN=Xe, Perfect_ZF=orc.equalize(Y, H_true, math.sqrt(Pi), 1e-12),
+                        LS_ZF=orc.equalize(Y, H_LS, math.sqrt(Pi), 1e-12), MMSE=orc.equalize(Y, H_MM, math.sqrt(Pi), No / Pi))
+            for k, X in cand.items():
+                errs[k] += int((orc.indices_to_bits(orc.hard_demap_indices(X, const), m) != tb).sum())
+    total = G * per * N * N_t * m
+    for k in linksim.DETECTORS:
+        assert int(out[k][1]) == total
+        assert abs(int(out[k][0]) - errs[k]) <= 2, (k, int(out[k][0]), errs[k])
+    print("linksim errors", {k: int(out[k][0]) for k in linksim.DETECTORS}, "oracle", errs)
+
+
+def test_linksim_ber_curve_runs_and_orders_detectors():
+    """A short device-resident BER curve (tensor-core detect): BER falls with SNR for the baselines, the
+    MMSE estimate is not worse than plain LS, and the ESN beats chance.  (Perfect CSI is NOT always the
+    best baseline here: the LS estimate absorbs the gain compression of the soft PA clip.)"""
+    from esn_b200 import Reservoir, linksim
+    N, N_t, N_r, m = 64, 2, 2, 4
+    rng = np.random.RandomState(3)
+    W, W_in, W_fb = orc.init_weights(rng, 2 * N_r, 2 * N_t, 128, 0.9, 0.1)
+
+    def factory(var_x):
+        return Reservoir(W, W_in, W_fb, (0.005 / var_x ** 0.5) * np.ones(2 * N_r), np.zeros(2 * N_r),
+                         5e-7 * np.ones(2 * N_t), np.zeros(2 * N_t), 0.001, True)
+    c = linksim.ber_curve(factory, N_t, N_r, N, m, [0, 12, 24], n_blocks=8, frames_per_block=128, seed=4)
+    assert c["EBN0"] == [0, 12, 24]
+    for k in ("Perfect_ZF", "LS_ZF", "MMSE"):
+        assert c[k][0] > c[k][1] > c[k][2]
+    print("ber curve", {k: [round(v, 4) for v in c[k]] for k in linksim.DETECTORS})
+    assert all(mm <= l + 2e-3 for mm, l in zip(c["MMSE"], c["LS_ZF"]))
+    assert all(0.0 <= v <= 0.6 for k in linksim.DETECTORS for v in c[k])
+    assert c["ESN"][2] < 0.45
