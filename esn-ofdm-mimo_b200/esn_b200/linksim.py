@@ -27,6 +27,37 @@ def isi_profile(isi, device):
     return mag / mag.sum()
 
 
+# 3GPP TR 38.901 Table 7.7.2-2, TDL-B: normalised delays and powers [dB] of the 23 paths (the table the
+# reference's CDL demo uses, system_model_2/Demo_MIMO_4x8_Sionna_CDL_ESN_v2.py:127-137)
+TDLB_NORM_DELAYS = (0.0000, 0.1072, 0.2155, 0.2095, 0.2870, 0.2986, 0.3752, 0.5055, 0.3681, 0.3697, 0.5700, 0.5283,
+                    1.1021, 1.2756, 1.5474, 1.7842, 2.0169, 2.8294, 3.0219, 3.6187, 4.1067, 4.2790, 4.7834)
+TDLB_POW_DB = (0.0, -2.2, -4.0, -3.2, -9.8, -1.2, -3.4, -5.2, -7.6, -3.0, -8.9, -9.0, -4.8, -5.7, -7.5, -1.9, -7.6,
+               -12.2, -9.8, -11.4, -14.9, -9.2, -11.3)
+
+
+def tdlb_taps(G, N_r, N_t, isi, fs_hz, ds_ns, generator, device):
+    """Block-fading taps [G, N_r, N_t, isi] from the TDL-B profile scaled to an RMS delay spread of `ds_ns`
+    (Demo_MIMO_4x8_Sionna_CDL_ESN_v2.py:139-177): every path gets an independent CN(0, p) gain, lands on
+    the sample grid with a linear split between the two neighbouring taps, paths beyond `isi` taps are
+    dropped, and each link is normalised to unit energy."""
+    p = torch.tensor(TDLB_POW_DB, dtype=torch.float64, device=device)
+    p = 10 ** (p / 10)
+    p = p / p.sum()
+    d = torch.tensor(TDLB_NORM_DELAYS, dtype=torch.float64, device=device) * ds_ns * 1e-9 * fs_hz
+    i0 = torch.floor(d).long()
+    frac = d - i0
+    n_path = p.numel()
+    g = (torch.randn((G, N_r, N_t, n_path), generator=generator, device=device, dtype=torch.float64)
+         + 1j * torch.randn((G, N_r, N_t, n_path), generator=generator, device=device, dtype=torch.float64)) / math.sqrt(2)
+    g = g * p.sqrt()
+    h = torch.zeros((G, N_r, N_t, isi + 1), dtype=torch.complex128, device=device)
+    ok0, ok1 = i0 < isi, (i0 + 1) < isi
+    h.index_add_(3, i0[ok0], g[..., ok0] * (1 - frac[ok0]).to(torch.complex128))
+    h.index_add_(3, (i0 + 1)[ok1], g[..., ok1] * frac[ok1].to(torch.complex128))
+    h = h[..., :isi]
+    return h / h.abs().pow(2).sum(dim=3, keepdim=True).sqrt()
+
+
 def comb_pilot(pil_idx):
     """LS comb pilot: Tx `tx` keeps the pilot symbols on subcarriers tx::N_t, the rest is empty (:287-289)."""
     G, N, N_t = pil_idx.shape
@@ -94,8 +125,26 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
     fr = ofdm.synth_frames(data_idx, taps.to(torch.complex64 if dd == torch.float32 else torch.complex128), Pi, A_clip,
                            N, cp, qam_bits, std, delay=delay, chan_index=block_of_frame, noise=noise_data,
                            seed=seed + 1, dtype=dd)
-    y = res.predict(fr["esn_in"], W_out, transient=transient, group_ids=block_of_frame, precision=detect_precision,
+    esn_in, gids, pick = fr["esn_in"], block_of_frame, None
+    if detect_precision == "tc":
+        # the tensor-core kernel wants one readout per 128-frame tile: lay every block out on whole tiles
+        # (the filler frames are zeros and are dropped again before the FFT / slicer)
+        tile = res.tc_tile_frames()
+        per = B // G
+        regular = B == G * per and bool((block_of_frame.view(G, per) == torch.arange(G, device=dev, dtype=block_of_frame.dtype)[:, None]).all())
+        if not regular:
+            raise ValueError("tensor-core detect needs block-contiguous frames, the same number per block")
+        if per % tile:
+            padded = -(-per // tile) * tile
+            pick = (torch.arange(G, device=dev)[:, None] * padded + torch.arange(per, device=dev)[None, :]).reshape(-1)
+            big = torch.zeros((G * padded,) + tuple(esn_in.shape[1:]), dtype=esn_in.dtype, device=dev)
+            big[pick] = esn_in
+            esn_in = big
+            gids = (torch.arange(G * padded, device=dev) // padded).to(torch.int32)
+    y = res.predict(esn_in, W_out, transient=transient, group_ids=gids, precision=detect_precision,
                     seed=state_noise_seed + 1)
+    if pick is not None:
+        y = y[pick].contiguous()
     out = {}
     total = B * N * N_t * qam_bits
     _, _, c = ofdm.unpack_fft_demap(y, N, N_t, Pi, qam_bits, tx_idx=data_idx, want_xhat=False, want_idx=False)
@@ -112,11 +161,13 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
 
 
 def ber_curve(res_factory, N_t, N_r, N, qam_bits, ebno_db_list, n_blocks, frames_per_block, isi=8, No=1e-5, seed=0,
-              fit_precision="fp64", detect_precision="tc", device=None):
+              fit_precision="fp64", detect_precision="tc", device=None, channel="rayleigh", fs_hz=2 * 1.024e6,
+              ds_ns=300.0):
     """BER-vs-SNR Monte-Carlo: for every Eb/N0, `n_blocks` coherence blocks of `frames_per_block` data
     symbols (blocks sharded over ranks, counters summed over ranks).  `res_factory(var_x)` returns the
     Reservoir for an SNR point (the template scales the inputs by 0.005 / sqrt(var_x)).  Returns
-    {detector: [BER per SNR]} plus 'EBN0'."""
+    {detector: [BER per SNR]} plus 'EBN0'.  channel: 'rayleigh' (exponential 8-tap profile of the NBF
+    template) or 'tdlb' (the CDL demo's TDL-B taps at sample rate fs_hz, delay spread ds_ns)."""
     device = device or torch.device("cuda", torch.cuda.current_device())
     rank, world = D.rank(), D.world()
     g0, g1 = D.shard_range(n_blocks, rank, world)
@@ -127,10 +178,13 @@ def ber_curve(res_factory, N_t, N_r, N, qam_bits, ebno_db_list, n_blocks, frames
         gen.manual_seed(seed * 100003 + si * 1009 + rank)
         counts = torch.zeros((len(DETECTORS), 2), dtype=torch.int64, device=device)
         if G > 0:
-            mag = isi_profile(isi, device)
-            taps = (torch.randn((G, N_r, N_t, isi), generator=gen, device=device, dtype=torch.float64)
-                    + 1j * torch.randn((G, N_r, N_t, isi), generator=gen, device=device, dtype=torch.float64)) / math.sqrt(2)
-            taps = taps * mag.sqrt()
+            if channel == "tdlb":
+                taps = tdlb_taps(G, N_r, N_t, isi, fs_hz, ds_ns, gen, device)
+            else:                                       # exponential-profile Rayleigh taps of the NBF template (:276-277)
+                mag = isi_profile(isi, device)
+                taps = (torch.randn((G, N_r, N_t, isi), generator=gen, device=device, dtype=torch.float64)
+                        + 1j * torch.randn((G, N_r, N_t, isi), generator=gen, device=device, dtype=torch.float64)) / math.sqrt(2)
+                taps = taps * mag.sqrt()
             pil_idx = torch.randint(0, 2 ** qam_bits, (G, N, N_t), generator=gen, device=device, dtype=torch.uint8)
             data_idx = torch.randint(0, 2 ** qam_bits, (G * frames_per_block, N, N_t), generator=gen, device=device,
                                      dtype=torch.uint8)

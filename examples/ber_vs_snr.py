@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--frames-per-block", type=int, default=128)
     ap.add_argument("--fit-precision", default="fp64", choices=["fp64", "fp32", "tc"])
     ap.add_argument("--detect-precision", default="tc", choices=["tc", "fp32", "fp64"])
+    ap.add_argument("--channel", default="rayleigh", choices=["rayleigh", "tdlb"],
+                    help="rayleigh: exponential 8-tap profile of the NBF template; tdlb: TDL-B taps of the CDL demo")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--out", default="results_ber_run")
     a = ap.parse_args()
@@ -57,7 +59,8 @@ def main():
                          np.zeros(no), 0.001, True)
     t0 = time.time()
     c = linksim.ber_curve(factory, a.nt, a.nr, a.nsub, a.qam_bits, ebno, a.blocks, a.frames_per_block,
-                          seed=a.seed, fit_precision=a.fit_precision, detect_precision=a.detect_precision)
+                          seed=a.seed, fit_precision=a.fit_precision, detect_precision=a.detect_precision,
+                          channel=a.channel)
     torch.cuda.synchronize()
     dt = time.time() - t0
     if rank == 0:
@@ -66,7 +69,7 @@ def main():
         meta = {"N": a.nsub, "N_t": a.nt, "N_r": a.nr, "IsiDuration": 8, "CP": 7,
                 "NumOfdmSymbols": a.blocks * (a.frames_per_block + 1),
                 "esn": {"n_reservoir": a.nres, "spectral_radius": 0.9, "input_scaler": 0.005, "teacher_scaling_base": 5e-7},
-                "channel": {"model": "block-fading Rayleigh, 8 taps, exponential profile"},
+                "channel": {"model": "CDL-B (TDL-equivalent)" if a.channel == "tdlb" else "block-fading Rayleigh, 8 taps, exponential profile"},
                 "all_detectors": {k: c[k] for k in linksim.DETECTORS}, "gpus": world, "seconds": dt}
         results.write_results_pkl(os.path.join(a.out, "results_ber.pkl"),
                                   results.results_bundle(c["EBN0"], c["ESN"], c["MMSE"], meta=meta))

@@ -264,3 +264,27 @@ def test_linksim_ber_curve_runs_and_orders_detectors():
     assert all(mm <= l + 2e-3 for mm, l in zip(c["MMSE"], c["LS_ZF"]))
     assert all(0.0 <= v <= 0.6 for k in linksim.DETECTORS for v in c[k])
     assert c["ESN"][2] < 0.45
+
+
+def test_cdl_demo_curve_matches_the_reference_published_results():
+    """The CDL demo's configuration (4x8, 128 subcarriers, 300 neurons, TDL-B taps, 16-QAM, L = 75) on the
+    device against the uncoded BERs the reference itself published for that script
+    (results/results_4x8_cdl_coded_uncoded/CDLB_run_01/results_ber.csv; 1000 OFDM symbols per point, i.e.
+    13 channel draws -- a noisy target, hence 15 %)."""
+    from esn_b200 import Reservoir, linksim
+    published = {0: (0.39036279296875, 0.3196171875), 15: (0.20868408203125, 0.05450439453125),
+                 30: (0.15689892578125, 0.0189169921875)}          # EbNo -> (ESN_uncoded, MMSE_uncoded)
+    N, N_t, N_r, m, n_res = 128, 4, 8, 4, 300
+    rng = np.random.RandomState(42)
+    W, W_in, W_fb = orc.init_weights(rng, 2 * N_r, 2 * N_t, n_res, 0.9, 0.1)
+
+    def factory(var_x):
+        return Reservoir(W, W_in, W_fb, (0.005 / var_x ** 0.5) * np.ones(2 * N_r), np.zeros(2 * N_r),
+                         5e-7 * np.ones(2 * N_t), np.zeros(2 * N_t), 0.001, True)
+    c = linksim.ber_curve(factory, N_t, N_r, N, m, sorted(published), n_blocks=148, frames_per_block=74, seed=1,
+                          channel="tdlb", detect_precision="tc")
+    for i, e in enumerate(sorted(published)):
+        esn_ref, mmse_ref = published[e]
+        assert abs(c["ESN"][i] - esn_ref) < 0.15 * esn_ref, (e, c["ESN"][i], esn_ref)
+        assert abs(c["MMSE"][i] - mmse_ref) < 0.15 * mmse_ref, (e, c["MMSE"][i], mmse_ref)
+    print("CDL demo curve", {k: [round(v, 4) for v in c[k]] for k in ("ESN", "MMSE")})
