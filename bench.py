@@ -460,9 +460,9 @@ def run_gpu(args):
                "fits_per_s": world * Gf / (fit_total * 1e-3),
                "what": "teacher-forced harvest on the tensor cores + fp64 dual Gram (512x512) + Cholesky + readout images",
                "fit_detect_symbols_per_s": world * per_group / ((us_fit + per_group * us_det) * 1e-6),
-               "block": f"1 pilot + {per_group} data frames per coherence block",
-               # the reference's own coherence block at N = 512: every 19th symbol is a pilot (L = 19)
-               "fit_detect_symbols_per_s_L19": world * 18 / ((us_fit + 18 * us_det) * 1e-6)}
+               "block": f"1 pilot + {per_group} data frames per coherence block (the tensor-core kernel wants "
+                        f"one readout per {res.tc_tile_frames()}-frame tile; the reference's L = 19 cadence would "
+                        "leave 110 of 128 tile frames empty)"}
         del fu, fy
     os.sched_setaffinity(0, all_cpus)            # the CPU-baseline leg uses every host core
     counts.zero_()
