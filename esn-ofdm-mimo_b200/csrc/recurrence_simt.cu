@@ -4,6 +4,28 @@
 
 int esn_simt_launch_f32(const esn_simt::RecParams &p, cudaStream_t st);
 int esn_simt_launch_f64(const esn_simt::RecParams &p, cudaStream_t st);
+int esn_cluster_launch(const esn_simt::RecParams &p, int dtype, cudaStream_t st);   // recurrence_cluster.cu
+
+int esn_cluster_auto_limit(const esn_simt::RecParams &p, int dtype);                  // recurrence_cluster.cu
+
+// Batches of at most this many frames take the cluster kernel (weights resident in the shared memory of a
+// thread-block cluster, ~3 us per time step) instead of the streaming SIMT kernel (~90 us per step while its
+// grid does not fill the GPU).  -1 = automatic (esn_cluster_auto_limit, from the measured crossover).
+static int g_small_batch_limit = -2;
+static int small_batch_setting() {
+    if (g_small_batch_limit == -2) {
+        const char *e = getenv("ESN_CLUSTER_MAX_B");
+        g_small_batch_limit = e ? atoi(e) : -1;
+        if (g_small_batch_limit < 0) g_small_batch_limit = -1;
+    }
+    return g_small_batch_limit;
+}
+
+extern "C" int esn_set_small_batch_limit(int max_frames) {
+    const int old = small_batch_setting();
+    g_small_batch_limit = max_frames < 0 ? -1 : max_frames;
+    return old;
+}
 
 extern "C" int esn_pad_sizes(int N, int n_in, int n_out, int *N_pad, int *K_aug_pad) {
     if (N <= 0 || n_in <= 0 || n_out <= 0 || !N_pad || !K_aug_pad) return ESN_E_BADARG;
@@ -41,6 +63,11 @@ extern "C" int esn_recurrence_run(const esn_recurrence_args *a, void *stream) {
     p.group_ids = a->group_ids; p.x0 = a->x0; p.y0 = a->y0; p.noise = a->noise_uniforms;
     p.ext_out = a->ext_out; p.y_out = a->y_out; p.workspace = a->workspace;
     cudaStream_t st = (cudaStream_t)stream;
+    const int limit = small_batch_setting() >= 0 ? small_batch_setting() : esn_cluster_auto_limit(p, a->dtype);
+    if (a->B <= limit) {
+        const int rc = esn_cluster_launch(p, a->dtype, st);
+        if (rc != ESN_E_UNSUPPORTED && rc != ESN_E_TOOLARGE) return rc;
+    }
     if (a->dtype == ESN_F32) return esn_simt_launch_f32(p, st);
     return esn_simt_launch_f64(p, st);
 }

@@ -60,6 +60,7 @@ SIGNATURES = {
     "esn_device_info": (_i, [C.c_char_p, _i, C.POINTER(_i), C.POINTER(_i)]),
     "esn_noise_uniform_host": (C.c_float, [C.c_uint64, C.c_uint, C.c_uint, C.c_uint]),
     "esn_pad_sizes": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "esn_set_small_batch_limit": (_i, [_i]),
     "esn_recurrence_run": (_i, [C.POINTER(RecurrenceArgs), _vp]),
     "esn_tc_supported": (_i, [_i, _i, _i]),
     "esn_tc_weight_bytes": (C.c_longlong, [_i, _i]),

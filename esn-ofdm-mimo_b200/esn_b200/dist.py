@@ -44,6 +44,20 @@ def shard_range(n_items, rank_, world_):
     return begin, begin + base + (1 if rank_ < extra else 0)
 
 
+def assign_by_cost(costs, world_):
+    """Whole work items (sweep configurations) -> ranks, longest-processing-time first: items sorted by
+    descending cost, each given to the currently least-loaded rank.  Deterministic (ties by index), so
+    every rank computes the same plan without talking.  Returns a list of item-index lists, one per rank,
+    each in descending-cost order."""
+    loads = [0.0] * int(world_)
+    plan = [[] for _ in range(int(world_))]
+    for i in sorted(range(len(costs)), key=lambda i: (-float(costs[i]), i)):
+        r = min(range(len(loads)), key=lambda r: (loads[r], r))
+        plan[r].append(i)
+        loads[r] += float(costs[i])
+    return plan
+
+
 def allreduce_sum_(t):
     """In-place sum over ranks (no-op for a single process)."""
     if dist.is_initialized() and dist.get_world_size() > 1:

@@ -162,18 +162,22 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
 
 def ber_curve(res_factory, N_t, N_r, N, qam_bits, ebno_db_list, n_blocks, frames_per_block, isi=8, No=1e-5, seed=0,
               fit_precision="fp64", detect_precision="tc", device=None, channel="rayleigh", fs_hz=2 * 1.024e6,
-              ds_ns=300.0):
+              ds_ns=300.0, shard=True):
     """BER-vs-SNR Monte-Carlo: for every Eb/N0, `n_blocks` coherence blocks of `frames_per_block` data
     symbols (blocks sharded over ranks, counters summed over ranks).  `res_factory(var_x)` returns the
     Reservoir for an SNR point (the template scales the inputs by 0.005 / sqrt(var_x)).  Returns
     {detector: [BER per SNR]} plus 'EBN0'.  channel: 'rayleigh' (exponential 8-tap profile of the NBF
-    template) or 'tdlb' (the CDL demo's TDL-B taps at sample rate fs_hz, delay spread ds_ns)."""
+    template) or 'tdlb' (the CDL demo's TDL-B taps at sample rate fs_hz, delay spread ds_ns).
+    shard=False: this rank runs all blocks by itself and no collective is issued (hyper-parameter sweeps
+    place whole configurations on ranks instead, examples/esn_sweep.py); the counters are returned under
+    '_counts' ([n_snr, n_detectors, 2] int64) for the caller to gather."""
     device = device or torch.device("cuda", torch.cuda.current_device())
-    rank, world = D.rank(), D.world()
+    rank, world = (D.rank(), D.world()) if shard else (0, 1)
     g0, g1 = D.shard_range(n_blocks, rank, world)
     G = g1 - g0
     gen = torch.Generator(device=device)
     curves = {k: [] for k in DETECTORS}
+    all_counts = []
     for si, ebno in enumerate(ebno_db_list):
         gen.manual_seed(seed * 100003 + si * 1009 + rank)
         counts = torch.zeros((len(DETECTORS), 2), dtype=torch.int64, device=device)
@@ -195,8 +199,11 @@ def ber_curve(res_factory, N_t, N_r, N, qam_bits, ebno_db_list, n_blocks, frames
                               seed=seed * 7919 + si * 31 + rank * 3 + 11, state_noise_seed=seed + 17 * si + rank)
             for di, k in enumerate(DETECTORS):
                 counts[di] = r[k]
-        D.allreduce_sum_(counts)
+        if shard:
+            D.allreduce_sum_(counts)
+        all_counts.append(counts)
         for di, k in enumerate(DETECTORS):
             curves[k].append(float(counts[di, 0]) / max(1, int(counts[di, 1])))
     curves["EBN0"] = [int(e) if float(e).is_integer() else float(e) for e in ebno_db_list]
+    curves["_counts"] = torch.stack(all_counts)
     return curves

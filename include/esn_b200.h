@@ -102,6 +102,15 @@ typedef struct esn_recurrence_args {
 
 int esn_pad_sizes(int N, int n_in, int n_out, int *N_pad_host, int *K_aug_pad_host);
 int esn_recurrence_run(const esn_recurrence_args *args_host, void *stream);
+/* esn_recurrence_run picks between two kernels.  Small batches with N <= 512 (the call shape of the
+ * unmodified demos: one OFDM symbol per ESN.predict, one pilot per ESN.fit, libs/pyESN.py:154,218) run on one
+ * thread-block cluster per 1-8 frames with [W | W_in | W_fb] resident in the cluster's shared memory and the
+ * new state exchanged through DSMEM (~3 us per time step at N = 512); larger batches stream the weights from
+ * L2 through the tiled SIMT kernel.  max_frames >= 0 fixes the largest batch the cluster kernel takes (0
+ * disables it); a negative value restores the automatic choice (a multiple of the resident-cluster wave,
+ * from the measured crossover; also the ESN_CLUSTER_MAX_B environment variable).  Returns the previous
+ * setting (-1 = automatic). */
+int esn_set_small_batch_limit(int max_frames);
 
 /* ---------------------------------------------------------------------------
  * Tensor-core recurrence (tcgen05 + TMEM), free-running predict.  Same reference

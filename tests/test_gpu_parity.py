@@ -281,12 +281,24 @@ def test_predict_is_batch_invariant_and_deterministic():
     W_out = _cuda(rng.randn(2, c["n_out"], c["n_res"] + c["n_in"]) * 1e-6, torch.float32)
     gid = _cuda((np.arange(B) % 2).astype(np.int32))
     noise = _cuda(rng.rand(B, c["T"], c["n_res"]), torch.float32)
-    y1 = eng.predict(us, W_out, transient=10, group_ids=gid, noise_uniforms=noise)
-    y2 = eng.predict(us, W_out, transient=10, group_ids=gid, noise_uniforms=noise)
-    assert torch.equal(y1, y2)
-    sub = torch.tensor([5, 17, 69, 33], device="cuda")
-    y3 = eng.predict(us[sub], W_out, transient=10, group_ids=gid[sub], noise_uniforms=noise[sub])
-    assert torch.allclose(y3, y1[sub], rtol=1e-5, atol=0)
+    from esn_b200 import _lib
+    lib = _lib.load()
+    for limit in (0, 1 << 20):                             # streaming kernel, then the cluster kernel
+        old = lib.esn_set_small_batch_limit(limit)
+        try:
+            y1 = eng.predict(us, W_out, transient=10, group_ids=gid, noise_uniforms=noise)
+            y2 = eng.predict(us, W_out, transient=10, group_ids=gid, noise_uniforms=noise)
+            assert torch.equal(y1, y2)
+            # same kernel, other batch composition / tile
+            sub = torch.cat([torch.tensor([5, 17, 69, 33], device="cuda"), torch.arange(20, 60, device="cuda")])
+            y3 = eng.predict(us[sub], W_out, transient=10, group_ids=gid[sub], noise_uniforms=noise[sub])
+            assert torch.allclose(y3, y1[sub], rtol=1e-5, atol=0)
+        finally:
+            lib.esn_set_small_batch_limit(old)
+        if limit == 0:
+            y_stream = y1
+    # the two kernels sum in a different order: equal to fp32 accuracy
+    assert float((y1 - y_stream).norm() / y_stream.norm()) < 1e-5
     assert y1.shape == (B, c["T"] - 10, c["n_out"]) and torch.isfinite(y1).all()
 
 
@@ -305,6 +317,47 @@ def test_odd_shapes_predict(n_res, n_in, n_out):
         for b in range(B):
             ref = orc.predict(W, W_in, W_fb, W_out[0], us[b], 0, 0.001, uni[b])
             assert rel_err(y[b], ref) < tol, (precision, b)
+
+
+@pytest.mark.parametrize("path", ["cluster", "stream"])
+@pytest.mark.parametrize("n_res,n_in,n_out,B", [(40, 2, 2, 1), (100, 4, 4, 3), (200, 2, 2, 5), (300, 16, 8, 9),
+                                                  (512, 16, 8, 1), (512, 16, 8, 2), (512, 16, 8, 7)])
+def test_small_batch_cluster_and_streaming_kernels_agree_with_oracle(path, n_res, n_in, n_out, B):
+    """The two kernels behind esn_recurrence_run (weights resident in a thread-block cluster's shared memory
+    for the demos' one-frame calls, weights streamed for large batches) against the oracle on the same
+    inputs, in both modes: harvest (libs/pyESN.py:179-182) and predict with continuation state
+    (libs/pyESN.py:226-253).  Ragged batches (B not a multiple of the frames-per-cluster tile) included."""
+    from esn_b200 import Reservoir
+    from esn_b200 import _lib
+    lib = _lib.load()
+    old = lib.esn_set_small_batch_limit(1 << 20 if path == "cluster" else 0)
+    try:
+        rng = np.random.RandomState(n_res + B)
+        W, W_in, W_fb = orc.init_weights(rng, n_in, n_out, n_res, 0.9, 0.1)
+        T = 41
+        aff = dict(input_scaling=0.05 * np.ones(n_in), input_shift=0.01 * np.ones(n_in),
+                   teacher_scaling=5e-3 * np.ones(n_out), teacher_shift=1e-4 * np.ones(n_out))
+        eng = Reservoir(W, W_in, W_fb, aff["input_scaling"], aff["input_shift"], aff["teacher_scaling"],
+                        aff["teacher_shift"], 0.001, True)
+        us, ys = rng.randn(B, T, n_in), rng.randn(B, T, n_out)
+        uni_h, uni_p = rng.rand(B, T - 1, n_res), rng.rand(B, T, n_res)
+        W_out = rng.randn(2, n_out, n_res + n_in) * 1e-2
+        gid = (np.arange(B) % 2).astype(np.int32)
+        x0, y0 = rng.randn(B, n_res) * 0.1, rng.randn(B, n_out) * 5e-3
+        for precision, tol in (("fp64", 1e-11), ("fp32", STATE_TOL)):
+            ext = eng.harvest(_cuda(us), _cuda(ys), precision=precision, noise_uniforms=_cuda(uni_h))
+            y, pext = eng.predict(_cuda(us), _cuda(W_out), transient=3, group_ids=_cuda(gid), precision=precision,
+                                  noise_uniforms=_cuda(uni_p), x0=_cuda(x0), y0=_cuda(y0), return_ext=True)
+            ext, y, pext = (t.double().cpu().numpy() for t in (ext, y, pext))
+            for b in range(B):
+                r = orc.fit(W, W_in, W_fb, us[b], ys[b], 0, 0.001, uni_h[b], teacher_forcing=True, **aff)
+                assert rel_err(ext[b, :, :n_res], r["states"]) < tol, (precision, b)
+                ref, st = orc.predict(W, W_in, W_fb, W_out[gid[b]], us[b], 3, 0.001, uni_p[b], x0=x0[b], y0=y0[b],
+                                      return_states=True, **aff)
+                assert rel_err(pext[b, :, :n_res], st) < tol, (precision, b)
+                assert rel_err(y[b], ref) < (1e-9 if precision == "fp64" else 1e-4), (precision, b)
+    finally:
+        lib.esn_set_small_batch_limit(old)
 
 
 # --------------------------------------------------------------------------

@@ -134,6 +134,25 @@ def test_shard_range():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_sweep_configurations_are_balanced_over_ranks():
+    """cfg4: whole (size, rho, sparsity) configurations per rank, largest first; every configuration is
+    placed exactly once, the plan is the same on every rank, and no rank carries more than the lightest
+    one plus the largest single item."""
+    sys.path.insert(0, os.path.join(ROOT, "esn-ofdm-mimo_b200"))
+    from esn_b200.dist import assign_by_cost
+    sizes = [64, 128, 256, 512, 1024, 2048]
+    cost = [n * (n + 24) * (12.0 if n > 512 else 1.0) for n in sizes for _ in range(9)]
+    for w in (1, 2, 3, 8):
+        plan = assign_by_cost(cost, w)
+        assert plan == assign_by_cost(list(cost), w)
+        assert sorted(i for p in plan for i in p) == list(range(len(cost)))
+        loads = [sum(cost[i] for i in p) for p in plan]
+        assert max(loads) - min(loads) <= max(cost) + 1e-9
+        for p in plan:
+            assert [cost[i] for i in p] == sorted((cost[i] for i in p), reverse=True)
+    assert assign_by_cost([], 4) == [[], [], [], []]
+
+
 def _gloo_worker(rank, world, port, tmp):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
                       MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
