@@ -381,8 +381,8 @@ int cl_cluster_size(int N) {
 // Largest batch the cluster kernel should take (esn_recurrence_run's automatic choice).  One wave of
 // resident clusters costs the same whatever its fill, and the streaming kernel is latency-bound (one
 // CTA pulls the whole weight matrix through L2 every step) until its own grid fills the GPU: measured on
-// B200 (profiles/small_batch_crossover.py) the streaming kernel takes as long as ~11-19 cluster waves in
-// fp64 and ~8-11 in fp32, so the cluster kernel keeps batches up to 10 (fp64) / 6 (fp32) waves.
+// B200 (profiles/r1_small_batch_crossover.txt) the streaming kernel takes as long as 11 (100 neurons) to 19
+// (512 neurons) cluster waves in fp64 and 8 to 11 in fp32; the cluster kernel keeps batches up to ~0.8 of that.
 int esn_cluster_auto_limit(const esn_simt::RecParams &p, int dtype) {
     if (p.N > 512) return 0;
     const int CS = cl_cluster_size(p.N);
@@ -390,7 +390,7 @@ int esn_cluster_auto_limit(const esn_simt::RecParams &p, int dtype) {
     int &c = cache[dtype == ESN_F64 ? 1 : 0][CS];
     if (c == 0) c = 1 + (dtype == ESN_F64 ? cl_resident_clusters<double, 4>(p, CS) : cl_resident_clusters<float, 8>(p, CS));
     const int resident = c - 1;
-    return dtype == ESN_F64 ? 4 * resident * 10 : 8 * resident * 6;
+    return dtype == ESN_F64 ? 4 * resident * (9 + CS / 3) : 8 * resident * (6 + CS / 5);
 }
 
 // Small-batch dispatch (called by esn_recurrence_run): returns ESN_E_UNSUPPORTED when the shape does not

@@ -3,12 +3,13 @@ oracle's generator, and a small BER-vs-SNR Monte-Carlo (train on the pilot, dete
 frames in one batched launch, demap + count on the device) against the oracle run on the very
 same bits, channels and noise.  "BER-vs-SNR curves must match" (BASELINE.json)."""
 import math
+import os
 
 import numpy as np
 import pytest
 import torch
 
-from conftest import rel_err
+from conftest import ROOT, rel_err
 from oracle import esn_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -288,3 +289,33 @@ def test_cdl_demo_curve_matches_the_reference_published_results():
         assert abs(c["ESN"][i] - esn_ref) < 0.15 * esn_ref, (e, c["ESN"][i], esn_ref)
         assert abs(c["MMSE"][i] - mmse_ref) < 0.15 * mmse_ref, (e, c["MMSE"][i], mmse_ref)
     print("CDL demo curve", {k: [round(v, 4) for v in c[k]] for k in ("ESN", "MMSE")})
+
+
+def test_siso_demo_loop_matches_reference_counts():
+    """BASELINE.json configs[0]: the SISO QPSK / AWGN demo loop (reference
+    Demo_SISO_QPSK_AWGN_LDPC_ESN_with_ZF_LS.py:179-277, uncoded) driven through the drop-in pyESN one frame
+    per call, numpy's global generator seeded as the demo does.  The golden counts come from the same loop
+    run with the live reference pyESN (tests/golden/make_golden_siso.py): identical bits, channel and noise,
+    so the conventional detectors must agree exactly and the ESN's errors symbol by symbol, up to symbols
+    within 1e-5 of a decision boundary (counted)."""
+    import importlib.util
+    from pyESN import ESN
+    spec = importlib.util.spec_from_file_location("siso_qpsk_awgn", os.path.join(ROOT, "examples", "siso_qpsk_awgn.py"))
+    demo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(demo)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "siso_demo_golden.npz"))
+    state = np.random.get_state()
+    try:
+        r = demo.run(ESN, [float(e) for e in g["ebno"]], int(g["symbols"]), int(g["nres"]), seed=int(g["seed"]),
+                     keep_first=True)
+    finally:
+        np.random.set_state(state)
+    assert r["bits"] == g["bits"].tolist()
+    for k in ("MMSE", "ZF", "LS"):
+        assert r[k] == g["err_" + k].tolist(), k
+    for si in range(len(r["bits"])):
+        assert rel_err(r["first_xhat"][si], g["first_xhat"][si]) < 1e-6
+        slack = r["near_boundary"][si]
+        assert abs(r["ESN"][si] - int(g["err_ESN"][si])) <= slack
+        for a, b in zip(r["esn_per_symbol"][si], g["esn_per_symbol"][si]):
+            assert abs(a - int(b)) <= slack

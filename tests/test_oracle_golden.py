@@ -165,3 +165,27 @@ def test_oracle_soft_outputs_match_reference(soft_golden, m):
     assert np.array_equal(hard[0], np.moveaxis(((idx_hat[:, :, None] >> np.arange(m)) & 1), 2, 1))
     cal = orc.calibrate_llrs(llr, ab[:, 0], ab[:, 1], 20.0)
     assert cal.shape == llr.shape and np.all(np.abs(cal) <= 20.0)
+
+
+def test_siso_demo_loop_oracle_matches_reference_counts():
+    """BASELINE.json configs[0]: the SISO QPSK / AWGN demo loop (examples/siso_qpsk_awgn.py) driven by the
+    oracle ESN reproduces the error counts of the same loop driven by the live reference pyESN
+    (tests/golden/make_golden_siso.py), detector by detector and symbol by symbol."""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("siso_qpsk_awgn", os.path.join(ROOT, "examples", "siso_qpsk_awgn.py"))
+    demo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(demo)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "siso_demo_golden.npz"))
+    state = np.random.get_state()
+    try:
+        r = demo.run(orc.OracleESN, [float(e) for e in g["ebno"]], int(g["symbols"]), int(g["nres"]),
+                     seed=int(g["seed"]), keep_first=True)
+    finally:
+        np.random.set_state(state)
+    assert r["bits"] == g["bits"].tolist()
+    for k in ("ESN", "MMSE", "ZF", "LS"):
+        assert r[k] == g["err_" + k].tolist(), k
+    assert np.array_equal(np.array(r["esn_per_symbol"]), g["esn_per_symbol"])
+    assert rel_err(np.array(r["first_xhat"]), g["first_xhat"]) < 1e-9
