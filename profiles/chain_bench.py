@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""Achieved HBM rate of the OFDM chain kernels (csrc/ofdm.cu) at the bench shape: 4x8, 512 subcarriers,
+CP 7, 16-QAM, B = 9472 frames in 74 coherence blocks, fp32.  Algorithmic bytes = every input read once +
+every output written once.  L2 is flushed between repetitions (256 MiB memset); best of 5, CUDA events.
+Peak: MEASURED_PEAKS.json hbm_gbs (6541.8 GB/s on this pool) unless the file says otherwise."""
+import json
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "esn-ofdm-mimo_b200"))
+import esn_b200  # noqa: E402
+from esn_b200 import linksim, ofdm  # noqa: E402
+
+esn_b200.load()
+peak = 6541.8
+try:
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+dev = "cuda"
+G, per, N, N_t, N_r, cp, m, isi = 74, 128, 512, 4, 8, 7, 4, 8
+B = G * per
+No, ebno = 1e-5, 15.0
+Pi = 10 ** (ebno / 10) * No
+A = math.sqrt(Pi * N) * 10 ** (3 / 20)
+std = math.sqrt((N + cp) * No / 2)
+gen = torch.Generator(device=dev).manual_seed(1)
+taps = (torch.randn((G, N_r, N_t, isi), generator=gen, device=dev) + 1j * torch.randn((G, N_r, N_t, isi), generator=gen, device=dev)) / math.sqrt(2)
+taps = (taps * linksim.isi_profile(isi, dev).sqrt().float()).to(torch.complex64)
+idx = torch.randint(0, 16, (B, N, N_t), generator=gen, device=dev, dtype=torch.uint8)
+blk = (torch.arange(B, device=dev) // per).to(torch.int32)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def nbytes(*ts):
+    return sum(t.numel() * t.element_size() for t in ts if t is not None)
+
+
+def timed(fn):
+    best = 1e9
+    for _ in range(5):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    return best, out
+
+
+rows = []
+
+
+def report(name, ms, byts, note=""):
+    gbs = byts / ms / 1e6
+    rows.append((name, ms * 1e3, byts / 1e6, gbs, gbs / peak, note))
+
+
+ms, fr = timed(lambda: ofdm.synth_frames(idx, taps, Pi, A, N, cp, m, std, delay=3, chan_index=blk, seed=5))
+report("ofdm_synth_frames", ms, nbytes(idx, fr["y_cp"], fr["esn_in"]), "bits -> QAM -> IFFT -> CP -> PA -> FIR -> AWGN -> ESN input")
+y_cp = fr["y_cp"]
+ms, Y = timed(lambda: ofdm.rx_fft(y_cp, N, cp))
+report("ofdm_rx_fft", ms, nbytes(y_cp, Y), "CP strip + FFT per (frame, antenna)")
+pil = idx[::per].contiguous()
+const = linksim.const_table(m, dev, torch.complex64)
+X_LS = torch.where(linksim.comb_pilot(pil) == 255, torch.zeros((), dtype=const.dtype, device=dev), const[pil.long()])
+ls = ofdm.synth_frames(linksim.comb_pilot(pil), taps, Pi, A, N, cp, m, std, seed=6, want_esn_in=False)
+Y_LS = ofdm.rx_fft(ls["y_cp"], N, cp)
+ms, (H_LS, H_MM) = timed(lambda: ofdm.chanest(Y_LS, X_LS, Pi, linksim.isi_profile(isi, dev).float(), isi, No))
+report("ofdm_chanest (74 blocks)", ms, nbytes(Y_LS, X_LS, H_LS, H_MM), "comb LS -> interpolation -> IFFT -> tap MMSE -> FFT")
+ms, X = timed(lambda: ofdm.equalize(Y, H_MM, No / Pi, math.sqrt(Pi), h_index=blk))
+report("ofdm_equalize (MMSE)", ms, nbytes(Y, X) + nbytes(H_MM), "per-subcarrier solve(H^H H + eps I, H^H y), 8x4")
+ms, _ = timed(lambda: ofdm.demap_count(X, m, tx_idx=idx, want_idx=False))
+report("ofdm_demap_count", ms, nbytes(X, idx), "slicer + bit-error popcount")
+ms, (s2, llr) = timed(lambda: ofdm.soft_demap(X, m))
+report("ofdm_soft_demap", ms, nbytes(X, s2, llr), "sigma2 + max-log LLRs")
+y = torch.randn(B, N, 2 * N_t, device=dev)
+ms, _ = timed(lambda: ofdm.unpack_fft_demap(y, N, N_t, Pi, m, tx_idx=idx, want_xhat=False, want_idx=False))
+report("ofdm_unpack_fft_demap", ms, nbytes(y, idx), "ESN output -> FFT -> slicer -> error count")
+print(f"OFDM chain kernels, fp32, B = {B} frames (4x8, N_sub = 512); HBM peak {peak:.1f} GB/s")
+print(f"{'kernel':28s} {'us':>9s} {'MB':>9s} {'GB/s':>8s} {'of peak':>8s}")
+for n, us, mb, gbs, fr_, note in rows:
+    print(f"{n:28s} {us:9.1f} {mb:9.1f} {gbs:8.0f} {fr_:8.3f}  {note}")
