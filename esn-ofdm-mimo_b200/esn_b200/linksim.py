@@ -74,6 +74,17 @@ def const_table(qam_bits, device, dtype=torch.complex128):
     return (c / math.sqrt(2.0 * (side * side - 1) / 3.0)).to(dtype)
 
 
+_SIDE = {}
+
+
+def _side_stream(dev):
+    """One side stream per device for the work that runs beside the readout training."""
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=key)
+    return _SIDE[key]
+
+
 def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_bits, isi=8, No=1e-5,
                   clip_db=3.0, delay=None, fit_precision="fp64", detect_precision="fp32", seed=0,
                   noise_pilot=None, noise_data=None, state_noise_seed=1):
@@ -101,30 +112,51 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
     transient = delay + cp
     rd = torch.float64 if fit_precision == "fp64" else torch.float32
     taps = taps.to(dev)
-    # ---- pilot symbol of every block: ESN training pair and the comb pilot through the same channel/noise
+    # Two streams.  The readout-training chain (pilot harvest on a few 16-CTA clusters, Gram, one Cholesky CTA per
+    # block) is latency-bound and leaves most SMs idle; everything that does not depend on the readouts -- data
+    # frame synthesis, the channel estimates and the three comparison detectors -- runs beside it on a side stream
+    # and joins the main stream before the ESN detects (esn_in) and at the end (the counters).
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    side.wait_stream(main)
+    # ---- pilot symbol of every block: ESN training pair through the same channel / noise as the comb pilot
+    # (enqueued first, so that the harvest clusters are placed before the side stream fills the other SMs)
     pil = ofdm.synth_frames(pil_idx, taps, Pi, A_clip, N, cp, qam_bits, std, delay=delay, noise=noise_pilot,
                             seed=seed, dtype=torch.float64, want_x_cp=True)
-    ls = ofdm.synth_frames(comb_pilot(pil_idx), taps, Pi, A_clip, N, cp, qam_bits, std, noise=noise_pilot,
-                           seed=seed, dtype=torch.float64, want_esn_in=False)
     teacher = torch.zeros((G, N + cp + delay, 2 * N_t), dtype=torch.float64, device=dev)
     teacher[:, delay:, :] = torch.view_as_real(pil["x_cp"]).reshape(G, N + cp, 2 * N_t)
     ext = res.harvest(pil["esn_in"].to(rd), teacher.to(rd), precision=fit_precision, seed=state_noise_seed)
     W_out, info = res.train_readout(ext, teacher, transient)
+    dd = torch.float32 if detect_precision in ("fp32", "tc") else torch.float64
+    out = {}
+    with torch.cuda.stream(side):
+        fr = ofdm.synth_frames(data_idx, taps.to(torch.complex64 if dd == torch.float32 else torch.complex128), Pi, A_clip,
+                               N, cp, qam_bits, std, delay=delay, chan_index=block_of_frame, noise=noise_data,
+                               seed=seed + 1, dtype=dd)
+        frames_ready = torch.cuda.Event()
+        frames_ready.record(side)
+        # channel estimates from the comb pilot (:316-334) and the true channel
+        ls = ofdm.synth_frames(comb_pilot(pil_idx), taps, Pi, A_clip, N, cp, qam_bits, std, noise=noise_pilot,
+                               seed=seed, dtype=torch.float64, want_esn_in=False)
+        const = const_table(qam_bits, dev)
+        X_LS = torch.where(comb_pilot(pil_idx) == 255, torch.zeros((), dtype=const.dtype, device=dev),
+                           const[pil_idx.long()])
+        Y_LS = ofdm.rx_fft(ls["y_cp"], N, cp)
+        H_LS, H_MMSE = ofdm.chanest(Y_LS, X_LS, Pi, isi_profile(isi, dev), isi, No)
+        H_true = torch.fft.fft(taps.to(torch.complex128), n=N, dim=3).permute(0, 3, 1, 2).contiguous()   # [G,N,N_r,N_t]
+        Y = ofdm.rx_fft(fr["y_cp"], N, cp)
+        cd = Y.dtype
+        for name, H, reg in (("Perfect_ZF", H_true, 1e-12), ("LS_ZF", H_LS, 1e-12), ("MMSE", H_MMSE, No / Pi)):
+            X = ofdm.equalize(Y, H.to(cd), reg, math.sqrt(Pi), h_index=block_of_frame)
+            _, c = ofdm.demap_count(X, qam_bits, tx_idx=data_idx, want_idx=False)
+            out[name] = c
+            del X
     if int(info.abs().max()) != 0:
         raise np.linalg.LinAlgError("readout training failed for block %d" % int(torch.nonzero(info)[0]))
     del ext
-    # ---- channel estimates from the comb pilot (:316-334) and the true channel
-    const = const_table(qam_bits, dev)
-    X_LS = torch.where(comb_pilot(pil_idx) == 255, torch.zeros((), dtype=const.dtype, device=dev),
-                       const[pil_idx.long()])
-    Y_LS = ofdm.rx_fft(ls["y_cp"], N, cp)
-    H_LS, H_MMSE = ofdm.chanest(Y_LS, X_LS, Pi, isi_profile(isi, dev), isi, No)
-    H_true = torch.fft.fft(taps.to(torch.complex128), n=N, dim=3).permute(0, 3, 1, 2).contiguous()   # [G,N,N_r,N_t]
     # ---- data symbols
-    dd = torch.float32 if detect_precision in ("fp32", "tc") else torch.float64
-    fr = ofdm.synth_frames(data_idx, taps.to(torch.complex64 if dd == torch.float32 else torch.complex128), Pi, A_clip,
-                           N, cp, qam_bits, std, delay=delay, chan_index=block_of_frame, noise=noise_data,
-                           seed=seed + 1, dtype=dd)
+    main.wait_event(frames_ready)
+    fr["esn_in"].record_stream(main)
     esn_in, gids, pick = fr["esn_in"], block_of_frame, None
     if detect_precision == "tc":
         # the tensor-core kernel wants one readout per 128-frame tile: lay every block out on whole tiles
@@ -145,17 +177,14 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
                     seed=state_noise_seed + 1)
     if pick is not None:
         y = y[pick].contiguous()
-    out = {}
     total = B * N * N_t * qam_bits
     _, _, c = ofdm.unpack_fft_demap(y, N, N_t, Pi, qam_bits, tx_idx=data_idx, want_xhat=False, want_idx=False)
     out["ESN"] = c
-    Y = ofdm.rx_fft(fr["y_cp"], N, cp)
-    cd = Y.dtype
-    for name, H, reg in (("Perfect_ZF", H_true, 1e-12), ("LS_ZF", H_LS, 1e-12), ("MMSE", H_MMSE, No / Pi)):
-        X = ofdm.equalize(Y, H.to(cd), reg, math.sqrt(Pi), h_index=block_of_frame)
-        _, c = ofdm.demap_count(X, qam_bits, tx_idx=data_idx, want_idx=False)
-        out[name] = c
-    res_ = {k: torch.stack([v[0], torch.tensor(total, dtype=v.dtype, device=dev)]) for k, v in out.items()}
+    main.wait_stream(side)
+    for v in out.values():
+        v.record_stream(main)
+    tot_t = torch.full((), total, dtype=torch.int64, device=dev)
+    res_ = {k: torch.stack([v[0], tot_t.to(v.dtype)]) for k, v in out.items()}
     res_["_W_out"], res_["_delay"], res_["_transient"] = W_out, delay, transient
     return res_
 

@@ -20,8 +20,18 @@ def _real_dtype(t):
     return {torch.complex64: torch.float32, torch.complex128: torch.float64}.get(t.dtype, t.dtype)
 
 
+def _dev(v, dtype, device):
+    """Python / numpy scalars become a device tensor through a fill kernel: no pageable host-to-device copy,
+    hence no stream synchronisation in the middle of an enqueued chain."""
+    if isinstance(v, torch.Tensor):
+        return v.to(device=device, dtype=dtype)
+    if not hasattr(v, "__len__"):
+        return torch.full((1,), float(v), dtype=dtype, device=device)
+    return torch.as_tensor(v, dtype=dtype, device=device)
+
+
 def _scalar_vec(v, B, dtype, device):
-    t = torch.as_tensor(v, dtype=dtype, device=device).reshape(-1)
+    t = _dev(v, dtype, device).reshape(-1)
     if t.numel() not in (1, B):
         raise ValueError("expected a scalar or one value per frame")
     return t.contiguous(), (0 if t.numel() == 1 else 1)
@@ -68,11 +78,11 @@ def chanest(Y_LS, X_LS, Pi, isi_magnitude, taps, No):
     B, N, N_r = Y_LS.shape
     N_t = X_LS.shape[2]
     rd = _real_dtype(Y_LS)
-    pi = torch.as_tensor(Pi, dtype=rd, device=Y_LS.device).reshape(-1)
+    pi = _dev(Pi, rd, Y_LS.device).reshape(-1)
     if pi.numel() == 1:
         pi = pi.expand(B)
     pi = pi.contiguous()
-    mag = torch.as_tensor(isi_magnitude, dtype=rd, device=Y_LS.device).contiguous()
+    mag = _dev(isi_magnitude, rd, Y_LS.device).contiguous()
     H_LS = torch.empty((B, N, N_r, N_t), dtype=Y_LS.dtype, device=Y_LS.device)
     H_MM = torch.empty_like(H_LS)
     check(lib.ofdm_chanest(_CODE[rd], ptr(_cplx_view(Y_LS)), ptr(_cplx_view(X_LS)), B, N, N_r, N_t, ptr(pi),
@@ -157,9 +167,9 @@ def synth_frames(tx_idx, taps, Pi, A_clip, N, cp, qam_bits, noise_std, delay=0, 
     taps = taps.to(device=dev, dtype=cd).contiguous()
     _, N_r, _, ntaps = taps.shape
     tx_idx = tx_idx.to(torch.uint8).contiguous()
-    pi = torch.as_tensor(Pi, dtype=dtype, device=dev).reshape(-1)
+    pi = _dev(Pi, dtype, dev).reshape(-1)
     pi = (pi.expand(B) if pi.numel() == 1 else pi).contiguous()
-    ac = torch.as_tensor(A_clip, dtype=dtype, device=dev).reshape(-1)
+    ac = _dev(A_clip, dtype, dev).reshape(-1)
     ac = (ac.expand(B) if ac.numel() == 1 else ac).contiguous()
     if chan_index is not None:
         chan_index = chan_index.to(device=dev, dtype=torch.int32).contiguous()
