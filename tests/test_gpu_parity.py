@@ -319,6 +319,35 @@ def test_odd_shapes_predict(n_res, n_in, n_out):
             assert rel_err(y[b], ref) < tol, (precision, b)
 
 
+@pytest.mark.parametrize("name,kw,T,one_d", [
+    ("1-D inputs and outputs (reshape path, libs/pyESN.py:168-171)", dict(n_inputs=1, n_outputs=1, n_reservoir=30), 40, True),
+    ("two time steps", dict(n_inputs=2, n_outputs=2, n_reservoir=20), 2, False),
+    ("one-row predict", dict(n_inputs=2, n_outputs=2, n_reservoir=20), 12, False),
+    ("a single neuron", dict(n_inputs=2, n_outputs=1, n_reservoir=1, sparsity=0.0), 20, False),
+    ("513 neurons (past the cluster and tensor-core sizes)", dict(n_inputs=3, n_outputs=2, n_reservoir=513, sparsity=0.2), 30, False),
+    ("scalar scalings and shifts (correct_dimensions broadcast)", dict(n_inputs=2, n_outputs=2, n_reservoir=25, input_scaling=0.3,
+                                                                       input_shift=0.1, teacher_scaling=2.0, teacher_shift=-0.5), 30, False),
+    ("teacher_forcing=False", dict(n_inputs=2, n_outputs=2, n_reservoir=25, teacher_forcing=False), 30, False)])
+def test_dropin_edge_shapes_match_oracle(name, kw, T, one_d):
+    """Edge shapes of the reference API through the drop-in ESN (fit, then predict with continuation) against
+    the oracle on the same seed: degenerate lengths, 1-D arrays, scalar scalings, sizes just past a kernel's
+    range."""
+    from pyESN import ESN
+    a, o = ESN(random_state=5, **kw), orc.OracleESN(random_state=5, **kw)
+    rng = np.random.RandomState(1)
+    ni, no = kw["n_inputs"], kw["n_outputs"]
+    u = rng.randn(T) if one_d else rng.randn(T, ni)
+    y = rng.randn(T) if one_d else rng.randn(T, no)
+    pa, po = a.fit(u, y), o.fit(u.reshape(T, -1), y.reshape(T, -1))
+    assert pa.shape == po.shape == (T, no)
+    assert rel_err(pa, po) < 1e-9 and rel_err(a.W_out, o.W_out) < 1e-9
+    Tp = 1 if name == "one-row predict" else T
+    u2 = rng.randn(Tp) if one_d else rng.randn(Tp, ni)
+    qa, qo = a.predict(u2), o.predict(u2.reshape(Tp, -1))
+    assert qa.shape == qo.shape == (Tp, no)
+    assert rel_err(qa, qo) < 1e-6
+
+
 @pytest.mark.parametrize("path", ["cluster", "stream"])
 @pytest.mark.parametrize("n_res,n_in,n_out,B", [(40, 2, 2, 1), (100, 4, 4, 3), (200, 2, 2, 5), (300, 16, 8, 9),
                                                   (512, 16, 8, 1), (512, 16, 8, 2), (512, 16, 8, 7)])
