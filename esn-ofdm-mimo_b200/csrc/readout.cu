@@ -88,6 +88,117 @@ syrk_f64_kernel(const TE *__restrict__ ext, int T, int p, int transient, int fra
         }
 }
 
+// The same Gram tile on the fp64 tensor cores (mma.sync m8n8k4, DMMA): 8 warps, each a 16 x 32 sub-tile =
+// 2 x 4 accumulator fragments; per k4 step a warp loads 2 A and 4 B fragments (one double per lane each)
+// for 8 MMAs, i.e. 6 shared-memory loads per 2048 FMAs where the FMA kernel above needs 8 per 512 (it is
+// bound by shared-memory bandwidth at ~40 % of the fp64 rate).  Fragment layouts (PTX ISA, m8n8k4 .f64):
+// A[row = lane / 4][k = lane % 4], B[k = lane % 4][col = lane / 4], C[row = lane / 4][col = 2 (lane % 4) + {0, 1}].
+// Panels are stored so that the global-memory fetch order is also the conflict-free store order: [k][i]
+// with a row stride of TS + 4 doubles in the primal case (lanes walk i), [i][k] with a row stride of DK + 4
+// in the dual case (lanes walk k; a [k][i] store there is an 8-way bank conflict that costs as much as the
+// MMAs).  With either stride the 4 x 4 doubles a half-warp reads per fragment fall into distinct banks.
+// The next panel is fetched into registers while this one is multiplied.
+constexpr int DK = 32, DLD = TS + 4, DLT = DK + 4;
+constexpr int DPANEL = DK * DLD > TS * DLT ? DK * DLD : TS * DLT;
+
+__device__ __forceinline__ void dmma8x8x4(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+template <typename TE, bool DUAL>
+__global__ void __launch_bounds__(256)
+syrk_dmma_kernel(const TE *__restrict__ ext, int T, int p, int transient, int frames_per_cta,
+                 int B, int shared, int accumulate, double *__restrict__ G) {
+    const int m = T - transient;
+    const int n = DUAL ? m : p;              // order of G
+    const int kdim = DUAL ? p : m;           // contraction length
+    int tl = blockIdx.x, ti = 0;
+    while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
+    const int tj = tl - ti * (ti + 1) / 2;
+    const int i0 = ti * TS, j0 = tj * TS;
+    const bool diag = ti == tj;              // the j panel IS the i panel
+
+    __shared__ double As[DPANEL], Bs[DPANEL];
+    auto at = [](int k, int i) { return DUAL ? i * DLT + k : k * DLD + i; };
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = (warp >> 1) * 16, c0 = (warp & 1) * 32;            // sub-tile of this warp
+    const int fk = lane & 3, fi = lane >> 2;
+    double acc[2][4][2] = {};
+    const int fbeg = blockIdx.y * frames_per_cta;
+    const int fend = min(B, fbeg + frames_per_cta);
+    constexpr int PER = DK * TS / 256;                               // panel elements per thread
+    double va[PER], vb[PER];
+
+    auto fetch = [&](const TE *E, int k0) {
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int e = tid + q * 256;
+            int kk, ii;
+            if (DUAL) { kk = e % DK; ii = e / DK; } else { ii = e % TS; kk = e / TS; }
+            const int k = k0 + kk, ia = i0 + ii, ib = j0 + ii;
+            va[q] = (k < kdim && ia < n) ? (double)(DUAL ? E[(size_t)ia * p + k] : E[(size_t)k * p + ia]) : 0.0;
+            vb[q] = (!diag && k < kdim && ib < n) ? (double)(DUAL ? E[(size_t)ib * p + k] : E[(size_t)k * p + ib]) : 0.0;
+        }
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int e = tid + q * 256;
+            int kk, ii;
+            if (DUAL) { kk = e % DK; ii = e / DK; } else { ii = e % TS; kk = e / TS; }
+            As[at(kk, ii)] = va[q];
+            if (!diag) Bs[at(kk, ii)] = vb[q];
+        }
+    };
+    const double *Bp = diag ? As : Bs;
+    const int nchunk = (kdim + DK - 1) / DK;
+    for (int b = fbeg; b < fend; ++b) {
+        const TE *E = ext + ((size_t)b * T + transient) * p;   // [m][p]
+        fetch(E, 0);
+        for (int ch = 0; ch < nchunk; ++ch) {
+            __syncthreads();                                         // previous panel fully consumed
+            stash();
+            __syncthreads();
+            if (ch + 1 < nchunk) fetch(E, (ch + 1) * DK);            // in flight during the MMAs
+#pragma unroll
+            for (int k4 = 0; k4 < DK; k4 += 4) {
+                double a[2], bb[4];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) a[r] = As[at(k4 + fk, r0 + 8 * r + fi)];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) bb[c] = Bp[at(k4 + fk, c0 + 8 * c + fi)];
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) dmma8x8x4(acc[r][c], a[r], bb[c]);
+            }
+        }
+    }
+    double *Gb = G + (shared ? 0 : (size_t)fbeg * n * n);
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = i0 + r0 + 8 * r + fi, j = j0 + c0 + 8 * c + 2 * fk + h;
+                const double v = acc[r][c][h];
+                if (i < n && j < n && j <= i) {
+                    if (shared) {
+                        atomicAdd(&Gb[(size_t)i * n + j], v);
+                        if (i != j) atomicAdd(&Gb[(size_t)j * n + i], v);
+                    } else if (accumulate) {
+                        Gb[(size_t)i * n + j] += v;
+                        if (i != j) Gb[(size_t)j * n + i] += v;
+                    } else {
+                        Gb[(size_t)i * n + j] = v;
+                        Gb[(size_t)j * n + i] = v;
+                    }
+                }
+            }
+}
+
 // ------------------------------------------------------------------- X^T Y --
 // out(i, o) = sum_r E[r][i] * Y(r, o), r over the m kept rows of each frame.
 // Y is either a scaled teacher (TY raw, scale/shift applied) or a plain fp64
@@ -425,10 +536,14 @@ extern "C" int esn_gram_f64(const void *ext, int ext_dtype, const void *teacher,
         ESN_CUDA_TRY(cudaMemsetAsync(G, 0, sizeof(double) * (size_t)n * n, st));
         ESN_CUDA_TRY(cudaMemsetAsync(rhs, 0, sizeof(double) * (size_t)p * n_out, st));
     }
-#define SYRK(TE, D) syrk_f64_kernel<TE, D><<<grid, 256, 0, st>>>((const TE *)ext, T, p, transient, fpc, B, shared, accumulate, G)
+    // fp64 tensor cores (DMMA); ESN_GRAM_FMA=1 selects the plain FMA kernel (kept as the cross-check)
+    static const bool use_fma = getenv("ESN_GRAM_FMA") != nullptr;
+#define SYRK(TE, D) (use_fma ? syrk_f64_kernel<TE, D><<<grid, 256, 0, st>>>((const TE *)ext, T, p, transient, fpc, B, shared, accumulate, G) : syrk_dmma_kernel<TE, D><<<grid, 256, 0, st>>>((const TE *)ext, T, p, transient, fpc, B, shared, accumulate, G))
+#define SYRK_OLD(TE, D) syrk_f64_kernel<TE, D><<<grid, 256, 0, st>>>((const TE *)ext, T, p, transient, fpc, B, shared, accumulate, G)
     if (dual) { if (f32) SYRK(float, true); else SYRK(double, true); }
     else      { if (f32) SYRK(float, false); else SYRK(double, false); }
 #undef SYRK
+#undef SYRK_OLD
     int rc = esn_launch_status();
     if (rc) return rc;
     if (dual) {
