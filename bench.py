@@ -239,6 +239,40 @@ def run_reference(args):
     emit(line)
 
 
+def dropin_latency(reps=5):
+    """The reference's own call shape -- ONE frame per call, host float64 numpy arrays in and out -- through the
+    drop-in modules (libs/pyESN.py, libs/helper_mimo_esn_generic.py) at the bench shape: milliseconds per
+    ESN.fit, ESN.predict and trainMIMOESN_generic (2 fits + 1 predict), fp64 on the small-batch cluster kernel.
+    The MT19937 state-noise draw that parity with the reference's generator requires is inside the timing."""
+    import torch
+    from pyESN import ESN
+    from helper_mimo_esn_generic import trainMIMOESN_generic
+    N, N_t, N_r, cp = CFG["N_sub"], CFG["N_t"], CFG["N_r"], CFG["cp"]
+    rng = np.random.RandomState(0)
+    esn = ESN(n_inputs=2 * N_r, n_outputs=2 * N_t, n_reservoir=CFG["n_res"], spectral_radius=0.9, sparsity=0.1,
+              input_scaling=0.005 * np.ones(2 * N_r), input_shift=np.zeros(2 * N_r),
+              teacher_scaling=5e-7 * np.ones(2 * N_t), teacher_shift=np.zeros(2 * N_t), random_state=42)
+    y_CP = rng.randn(N + cp, N_r) + 1j * rng.randn(N + cp, N_r)
+    x_CP = rng.randn(N + cp, N_t) + 1j * rng.randn(N + cp, N_t)
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e3
+    r = trainMIMOESN_generic(esn, 0, 0, 6, cp, N, N_t, N_r, 8, y_CP, x_CP)
+    ein, eout, nf = r[0], r[1], r[7]
+    out = {"what": "one frame per call through the drop-in pyESN / helper modules, host float64 numpy arrays, fp64",
+           "trainMIMOESN_generic_ms": timed(lambda: trainMIMOESN_generic(esn, 0, 0, 6, cp, N, N_t, N_r, 8, y_CP, x_CP)),
+           "fit_ms": timed(lambda: esn.fit(ein, eout, nf)),
+           "predict_ms": timed(lambda: esn.predict(ein, nf, continuation=False))}
+    out["predict_symbols_per_s"] = 1e3 / out["predict_ms"]
+    return out
+
+
 def bind_to_gpu_numa(local):
     """Pin this process to the CPUs next to GPU `local` (sysfs local_cpulist) so that the pinned
     staging buffers of the end-to-end leg are allocated on the GPU's own NUMA node."""
@@ -464,6 +498,9 @@ def run_gpu(args):
                         f"one readout per {res.tc_tile_frames()}-frame tile; the reference's L = 19 cadence would "
                         "leave 110 of 128 tile frames empty)"}
         del fu, fy
+    dropin = None
+    if world == 1 and not args.no_dropin:
+        dropin = dropin_latency()
     os.sched_setaffinity(0, all_cpus)            # the CPU-baseline leg uses every host core
     counts.zero_()
     step(frames)
@@ -510,6 +547,7 @@ def run_gpu(args):
                      "algorithmic_flop_per_symbol": algorithmic_flops_per_symbol(),
                      "kernel_share_of_step": kms / (ms / args.steps)},
         "fit": fit,
+        "dropin": dropin,
         "cpu_baseline": cpu,
         "clocks": clk.summary(),
     }
@@ -547,6 +585,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="size of the CPU-baseline sample")
     ap.add_argument("--ref-frames-per-worker", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the one-frame-per-call drop-in latency leg")
     ap.add_argument("--ebno", type=float, default=15.0, help="Eb/N0 (dB) of the simulated link")
     ap.add_argument("--fit-precision", default="fp64", choices=["fp64", "fp32", "tc"],
                     help="harvest precision of the readouts the timed detection uses")
