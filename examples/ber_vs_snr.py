@@ -76,6 +76,8 @@ def main():
         frames = len(ebno) * a.blocks * a.frames_per_block
         print(json.dumps({"ebno": c["EBN0"], **{k: [round(v, 5) for v in c[k]] for k in linksim.DETECTORS},
                           "frames": frames, "seconds": round(dt, 2), "gpus": world}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

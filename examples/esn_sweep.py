@@ -105,6 +105,8 @@ def main():
                           "best_at_top_snr": {"n_reservoir": cfgs[best][0], "spectral_radius": cfgs[best][1],
                                               "sparsity": cfgs[best][2], "ber": round(float(ber[best, -1, 0]), 5)}}))
     D.barrier()
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
