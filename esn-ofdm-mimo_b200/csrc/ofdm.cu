@@ -251,6 +251,43 @@ __global__ void rx_fft_kernel(const T *__restrict__ y_cp, int N, int cp, int N_r
     }
 }
 
+// Whole-frame version: one CTA per frame reads the N rows behind the CP as one contiguous block, runs the N_r
+// FFTs side by side (three radix-2 layers per shared-memory pass) and writes Y [N][N_r] as contiguous rows.
+template <typename T>
+__global__ void __launch_bounds__(512)
+rx_fft_frame_kernel(const T *__restrict__ y_cp, int N, int cp, int N_r, T *__restrict__ Y) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int tot = N * N_r, tots = tot + (tot >> 5) + 1;
+    T *re = reinterpret_cast<T *>(sm), *im = re + tots, *twr = im + tots, *twi = twr + N / 2;
+    const int b = blockIdx.x, logn = ilog2(N), W2 = 2 * N_r;
+    fft_make_twiddles(twr, twi, N);
+    const T *src = y_cp + ((size_t)b * (N + cp) + cp) * W2;
+    for (int e0 = 0; e0 < N * W2; e0 += 8 * blockDim.x) {             // contiguous, coalesced, 8 loads in flight
+        T v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = e0 + i * blockDim.x + threadIdx.x;
+            v[i] = e < N * W2 ? src[e] : (T)0;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = e0 + i * blockDim.x + threadIdx.x;
+            if (e < N * W2) {
+                const int t = e / W2, c = e - t * W2;
+                ((c & 1) ? im : re)[skew((c >> 1) * N + bitrev(t, logn))] = v[i];
+            }
+        }
+    }
+    __syncthreads();
+    fft_batched_radix8(re, im, twr, twi, N, logn, N_r);
+    const T scale = (T)1 / (T)N;
+    T *dst = Y + (size_t)b * N * W2;
+    for (int e = threadIdx.x; e < N * W2; e += blockDim.x) {           // e = (k N_r + rx) 2 + {re, im}: contiguous
+        const int k = e / W2, c = e - k * W2;
+        dst[e] = ((c & 1) ? im : re)[skew((c >> 1) * N + k)] * scale;
+    }
+}
+
 // ---- pilot LS + linear inter/extrapolation + time-domain MMSE ---------------
 template <typename T>
 __global__ void chanest_kernel(const T *__restrict__ Y_LS, const T *__restrict__ X_LS, int N, int N_r,
@@ -640,6 +677,112 @@ __global__ void synth_frames_kernel(const uint8_t *__restrict__ tx_idx, const T 
     }
 }
 
+// Whole-frame version (used whenever the N_t streams fit in shared memory together, i.e. at every demo
+// size): the frame's symbol indices are read as one contiguous block, the N_t IFFTs run side by side with
+// three radix-2 layers per shared-memory pass (IFFT(X) = conj(FFT(conj(X))), so the forward passes of the
+// unpack kernel are reused), the channel taps sit in shared memory, and a thread filters TB consecutive
+// samples of one Rx antenna so that a tap is read once per TB products.  ncu on the first version: 44 % of
+// the stall samples in the nine-barrier radix-2 IFFTs, 42 % in the FIR fetching its taps from global memory.
+template <typename T>
+__global__ void __launch_bounds__(256)
+synth_frames_frame_kernel(const uint8_t *__restrict__ tx_idx, const T *__restrict__ taps,
+                          const int *__restrict__ chan_index, const T *__restrict__ Pi,
+                          const T *__restrict__ A_clip, const T *__restrict__ noise, T noise_std,
+                          unsigned long long seed, int N, int cp, int N_t, int N_r, int ntaps,
+                          int qam_bits, int delay, T *__restrict__ x_cp_out, T *__restrict__ y_cp,
+                          T *__restrict__ esn_in) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    constexpr int TB = 4;
+    const int L = N + cp, b = blockIdx.x, logn = ilog2(N), rows = L + delay;
+    const int tot = N * N_t, tots = tot + (tot >> 5) + 1, ntap_all = N_r * N_t * ntaps;
+    T *re = reinterpret_cast<T *>(sm), *im = re + tots, *twr = im + tots, *twi = twr + N / 2;
+    T *xr = twi + N / 2, *xi = xr + (size_t)N_t * L;          // clipped Tx samples [N_t][L]
+    T *tr = xi + (size_t)N_t * L, *ti = tr + ntap_all;         // channel taps [N_r][N_t][ntaps]
+    fft_make_twiddles(twr, twi, N);
+    const T *cb = taps + (size_t)(chan_index ? chan_index[b] : b) * ntap_all * 2;
+    for (int e = threadIdx.x; e < ntap_all; e += blockDim.x) { tr[e] = cb[2 * e]; ti[e] = cb[2 * e + 1]; }
+    const int side = 1 << (qam_bits / 2);
+    const T cs = (T)1 / sqrt_t((T)(2.0 * (side * side - 1) / 3.0));
+    const T sp = sqrt_t(Pi[b]), A = A_clip[b];
+    const uint8_t *ib = tx_idx + (size_t)b * tot;
+    for (int e = threadIdx.x; e < tot; e += blockDim.x) {              // e = k N_t + tx: contiguous
+        const int k = e / N_t, tx = e - k * N_t, id = ib[e];
+        const int o = skew(tx * N + bitrev(k, logn));
+        // index = side*i_re + i_im; 255 = empty subcarrier (the comb pilot of the LS estimator); conjugated
+        re[o] = id == 255 ? (T)0 : (T)(2 * (id / side) - (side - 1)) * cs;
+        im[o] = id == 255 ? (T)0 : -(T)(2 * (id % side) - (side - 1)) * cs;
+    }
+    __syncthreads();
+    fft_batched_radix8(re, im, twr, twi, N, logn, N_t);               // conj(result) = N * ifft(X)
+    const T inv_A2 = (T)1 / (A * A);
+    for (int e = threadIdx.x; e < N_t * L; e += blockDim.x) {          // e = t N_t + tx: contiguous x_cp rows
+        const int t = e / N_t, tx = e - t * N_t;
+        const int src = t < cp ? N - cp + t : t - cp;
+        const T vr = re[skew(tx * N + src)] * sp, vi = -im[skew(tx * N + src)] * sp;
+        if (x_cp_out) {
+            const size_t o = ((size_t)b * L * N_t + e) * 2;
+            x_cp_out[o] = vr; x_cp_out[o + 1] = vi;
+        }
+        const T g = (T)1 / sqrt_t((T)1 + (vr * vr + vi * vi) * inv_A2);
+        xr[tx * L + t] = vr * g; xi[tx * L + t] = vi * g;
+    }
+    __syncthreads();
+    const int nblk = (L + TB - 1) / TB;
+    for (int e = threadIdx.x; e < nblk * N_r; e += blockDim.x) {
+        const int tb = e / N_r, rx = e - tb * N_r, t0 = tb * TB;
+        T yr[TB], yi[TB];
+#pragma unroll
+        for (int j = 0; j < TB; ++j) { yr[j] = 0; yi[j] = 0; }
+        for (int tx = 0; tx < N_t; ++tx) {
+            const T *c_r = tr + (rx * N_t + tx) * ntaps, *c_i = ti + (rx * N_t + tx) * ntaps;
+            const T *x_r = xr + tx * L, *x_i = xi + tx * L;
+            for (int k = 0; k < ntaps; ++k) {
+                const T ar = c_r[k], ai = c_i[k];
+#pragma unroll
+                for (int j = 0; j < TB; ++j) {
+                    const int t = t0 + j - k;
+                    if (t >= 0 && t0 + j < L) {
+                        const T br = x_r[t], bi = x_i[t];
+                        yr[j] += ar * br - ai * bi; yi[j] += ar * bi + ai * br;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < TB; ++j) {
+            const int t = t0 + j;
+            if (t >= L) break;
+            T nr, ni;
+            if (noise) {
+                const size_t o = (((size_t)b * L + t) * N_r + rx) * 2;
+                nr = noise[o]; ni = noise[o + 1];
+            } else {
+                const uint32_t key = esn_noise_key(seed ^ 0xA5A5A5A5ULL, (uint32_t)b, (uint32_t)t);
+                const uint32_t h1 = esn_mix32(key + (uint32_t)rx * 0xC2B2AE35U);
+                const uint32_t h2 = esn_mix32(h1 ^ 0x68E31DA4U);
+                const T u1 = ((T)(h1 >> 8) + (T)0.5) * (T)(1.0 / 16777216.0);
+                const T u2 = (T)(h2 >> 8) * (T)(1.0 / 16777216.0);
+                const T rad = sqrt_t((T)-2 * (T)log((double)u1));
+                T sn, cn;
+                sincospi_t((T)2 * u2, &sn, &cn);
+                nr = rad * cn; ni = rad * sn;
+            }
+            const T vr = yr[j] + noise_std * nr, vi = yi[j] + noise_std * ni;
+            if (y_cp) {
+                const size_t o = (((size_t)b * L + t) * N_r + rx) * 2;
+                y_cp[o] = vr; y_cp[o + 1] = vi;
+            }
+            if (esn_in) {
+                const size_t o = ((size_t)b * rows + t) * 2 * N_r + 2 * rx;
+                esn_in[o] = vr; esn_in[o + 1] = vi;
+            }
+        }
+    }
+    if (esn_in)                                                        // the `delay` trailing zero rows
+        for (int e = threadIdx.x; e < delay * 2 * N_r; e += blockDim.x)
+            esn_in[((size_t)b * rows + L) * 2 * N_r + e] = (T)0;
+}
+
 template <typename K>
 inline int allow_smem(K kern, size_t smem) {
     if (smem > 48 * 1024)
@@ -695,6 +838,19 @@ extern "C" int ofdm_rx_fft(int dtype, const void *y_cp, int B, int N, int cp, in
     if (!y_cp || !Y || B <= 0 || N_r <= 0 || cp < 0 || !pow2_ok(N)) return ESN_E_BADARG;
     dim3 grid(N_r, B);
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t tot = (size_t)N * N_r, esz = dtype == ESN_F64 ? sizeof(double) : sizeof(float);
+    const size_t frame_smem = (2 * (tot + tot / 32 + 1) + N) * esz;
+    if (frame_smem <= 160 * 1024 && (dtype == ESN_F32 || dtype == ESN_F64)) {
+        const int threads = (int)std::min<size_t>(512, std::max<size_t>(64, tot / 8));
+        if (dtype == ESN_F32) {
+            if (int rc = allow_smem(rx_fft_frame_kernel<float>, frame_smem)) return rc;
+            rx_fft_frame_kernel<float><<<B, threads, frame_smem, st>>>((const float *)y_cp, N, cp, N_r, (float *)Y);
+        } else {
+            if (int rc = allow_smem(rx_fft_frame_kernel<double>, frame_smem)) return rc;
+            rx_fft_frame_kernel<double><<<B, threads, frame_smem, st>>>((const double *)y_cp, N, cp, N_r, (double *)Y);
+        }
+        return esn_launch_status();
+    }
     if (int rc = dtype == ESN_F64 ? allow_smem(rx_fft_kernel<double>, 3 * (size_t)N * sizeof(double)) : 0) return rc;
     if (dtype == ESN_F32)
         rx_fft_kernel<float><<<grid, fft_threads(N), 3 * N * sizeof(float), st>>>((const float *)y_cp, N, cp, N_r, (float *)Y);
@@ -901,6 +1057,24 @@ extern "C" int ofdm_synth_frames(int dtype, const uint8_t *tx_idx, const void *t
     if (qam_bits != 2 && qam_bits != 4 && qam_bits != 6) return ESN_E_BADARG;
     const size_t el = 3 * (size_t)N + 2 * (size_t)N_t * (N + cp);
     cudaStream_t st = (cudaStream_t)stream;
+    // whole-frame kernel when the N_t streams, the clipped samples and the taps fit in shared memory together
+    const size_t tot = (size_t)N * N_t;
+    const size_t el_frame = 2 * (tot + tot / 32 + 1) + N + 2 * (size_t)N_t * (N + cp) + 2 * (size_t)N_r * N_t * ntaps;
+    const size_t esz = dtype == ESN_F64 ? sizeof(double) : sizeof(float);
+    if (el_frame * esz <= 160 * 1024 && (dtype == ESN_F32 || dtype == ESN_F64)) {
+        if (dtype == ESN_F32) {
+            if (int rc = allow_smem(synth_frames_frame_kernel<float>, el_frame * esz)) return rc;
+            synth_frames_frame_kernel<float><<<B, 256, el_frame * esz, st>>>(
+                tx_idx, (const float *)taps, chan_index, (const float *)Pi, (const float *)A_clip, (const float *)noise,
+                (float)noise_std, seed, N, cp, N_t, N_r, ntaps, qam_bits, delay, (float *)x_cp, (float *)y_cp, (float *)esn_in);
+        } else {
+            if (int rc = allow_smem(synth_frames_frame_kernel<double>, el_frame * esz)) return rc;
+            synth_frames_frame_kernel<double><<<B, 256, el_frame * esz, st>>>(
+                tx_idx, (const double *)taps, chan_index, (const double *)Pi, (const double *)A_clip, (const double *)noise,
+                noise_std, seed, N, cp, N_t, N_r, ntaps, qam_bits, delay, (double *)x_cp, (double *)y_cp, (double *)esn_in);
+        }
+        return esn_launch_status();
+    }
     if (dtype == ESN_F32) {
         if (int rc = allow_smem(synth_frames_kernel<float>, el * sizeof(float))) return rc;
         synth_frames_kernel<float><<<B, fft_threads(N), el * sizeof(float), st>>>(
