@@ -191,7 +191,7 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
 
 def ber_curve(res_factory, N_t, N_r, N, qam_bits, ebno_db_list, n_blocks, frames_per_block, isi=8, No=1e-5, seed=0,
               fit_precision="fp64", detect_precision="tc", device=None, channel="rayleigh", fs_hz=2 * 1.024e6,
-              ds_ns=300.0, shard=True):
+              ds_ns=300.0, shard=True, max_blocks_per_launch=148):
     """BER-vs-SNR Monte-Carlo: for every Eb/N0, `n_blocks` coherence blocks of `frames_per_block` data
     symbols (blocks sharded over ranks, counters summed over ranks).  `res_factory(var_x)` returns the
     Reservoir for an SNR point (the template scales the inputs by 0.005 / sqrt(var_x)).  Returns
@@ -199,7 +199,10 @@ def ber_curve(res_factory, N_t, N_r, N, qam_bits, ebno_db_list, n_blocks, frames
     template) or 'tdlb' (the CDL demo's TDL-B taps at sample rate fs_hz, delay spread ds_ns).
     shard=False: this rank runs all blocks by itself and no collective is issued (hyper-parameter sweeps
     place whole configurations on ranks instead, examples/esn_sweep.py); the counters are returned under
-    '_counts' ([n_snr, n_detectors, 2] int64) for the caller to gather."""
+    '_counts' ([n_snr, n_detectors, 2] int64) for the caller to gather.
+    A rank's blocks are processed `max_blocks_per_launch` at a time (148 blocks x 128 frames = 2.5 GB of
+    frames and intermediates), so a point of BASELINE.json configs[4] -- 10^6 frames per Eb/N0 -- runs in
+    bounded memory; the counters accumulate on the device."""
     device = device or torch.device("cuda", torch.cuda.current_device())
     rank, world = (D.rank(), D.world()) if shard else (0, 1)
     g0, g1 = D.shard_range(n_blocks, rank, world)
@@ -210,24 +213,26 @@ def ber_curve(res_factory, N_t, N_r, N, qam_bits, ebno_db_list, n_blocks, frames
     for si, ebno in enumerate(ebno_db_list):
         gen.manual_seed(seed * 100003 + si * 1009 + rank)
         counts = torch.zeros((len(DETECTORS), 2), dtype=torch.int64, device=device)
-        if G > 0:
+        res = res_factory(10 ** (ebno / 10) * No * N) if G > 0 else None
+        for ci, c0 in enumerate(range(0, G, max(1, int(max_blocks_per_launch)))):
+            Gc = min(int(max_blocks_per_launch), G - c0)
             if channel == "tdlb":
-                taps = tdlb_taps(G, N_r, N_t, isi, fs_hz, ds_ns, gen, device)
+                taps = tdlb_taps(Gc, N_r, N_t, isi, fs_hz, ds_ns, gen, device)
             else:                                       # exponential-profile Rayleigh taps of the NBF template (:276-277)
                 mag = isi_profile(isi, device)
-                taps = (torch.randn((G, N_r, N_t, isi), generator=gen, device=device, dtype=torch.float64)
-                        + 1j * torch.randn((G, N_r, N_t, isi), generator=gen, device=device, dtype=torch.float64)) / math.sqrt(2)
+                taps = (torch.randn((Gc, N_r, N_t, isi), generator=gen, device=device, dtype=torch.float64)
+                        + 1j * torch.randn((Gc, N_r, N_t, isi), generator=gen, device=device, dtype=torch.float64)) / math.sqrt(2)
                 taps = taps * mag.sqrt()
-            pil_idx = torch.randint(0, 2 ** qam_bits, (G, N, N_t), generator=gen, device=device, dtype=torch.uint8)
-            data_idx = torch.randint(0, 2 ** qam_bits, (G * frames_per_block, N, N_t), generator=gen, device=device,
+            pil_idx = torch.randint(0, 2 ** qam_bits, (Gc, N, N_t), generator=gen, device=device, dtype=torch.uint8)
+            data_idx = torch.randint(0, 2 ** qam_bits, (Gc * frames_per_block, N, N_t), generator=gen, device=device,
                                      dtype=torch.uint8)
-            blk = (torch.arange(G * frames_per_block, device=device) // frames_per_block).to(torch.int32)
-            res = res_factory(10 ** (ebno / 10) * No * N)
+            blk = (torch.arange(Gc * frames_per_block, device=device) // frames_per_block).to(torch.int32)
             r = detect_blocks(res, pil_idx, data_idx, blk, taps, ebno, N, qam_bits, isi=isi, No=No,
                               fit_precision=fit_precision, detect_precision=detect_precision,
-                              seed=seed * 7919 + si * 31 + rank * 3 + 11, state_noise_seed=seed + 17 * si + rank)
+                              seed=seed * 7919 + si * 31 + rank * 3 + 11 + ci * 104729,
+                              state_noise_seed=seed + 17 * si + rank + ci * 7907)
             for di, k in enumerate(DETECTORS):
-                counts[di] = r[k]
+                counts[di] += r[k]
         if shard:
             D.allreduce_sum_(counts)
         all_counts.append(counts)

@@ -57,6 +57,9 @@ def main():
     def factory(var_x):
         return Reservoir(W, W_in, W_fb, (0.005 / var_x ** 0.5) * np.ones(ni), np.zeros(ni), 5e-7 * np.ones(no),
                          np.zeros(no), 0.001, True)
+    warm = torch.zeros(1, device="cuda")
+    D.allreduce_sum_(warm)                                # NCCL communicator set-up stays out of the timing
+    torch.cuda.synchronize()
     t0 = time.time()
     c = linksim.ber_curve(factory, a.nt, a.nr, a.nsub, a.qam_bits, ebno, a.blocks, a.frames_per_block,
                           seed=a.seed, fit_precision=a.fit_precision, detect_precision=a.detect_precision,

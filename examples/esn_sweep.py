@@ -67,6 +67,8 @@ def main():
     mine = D.assign_by_cost(cost, world)[rank]
     counts = torch.zeros((len(cfgs), len(ebno), len(linksim.DETECTORS), 2), dtype=torch.int64, device=dev)
     secs = torch.zeros((len(cfgs),), dtype=torch.float64, device=dev)
+    D.allreduce_sum_(secs)                                # NCCL communicator set-up stays out of the timing
+    torch.cuda.synchronize()
     t_all = time.time()
     with cf.ThreadPoolExecutor(max_workers=2) as pool:
         futs = {i: pool.submit(init_weights, a.seed + i, cfgs[i][0], ni, no, cfgs[i][1], cfgs[i][2]) for i in mine}
