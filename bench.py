@@ -492,7 +492,7 @@ def run_gpu(args):
         us_det = (ms / args.steps) * 1e3 / B                   # microseconds per detected frame
         fit = {"pilots_per_batch": Gf, "ms_per_batch": fit_total, "harvest_ms": best[0], "solve_ms": best[1],
                "fits_per_s": world * Gf / (fit_total * 1e-3),
-               "what": "teacher-forced harvest on the tensor cores + fp64 dual Gram (512x512) + Cholesky + readout images",
+               "what": "teacher-forced harvest on the tensor cores (tcgen05) + dual Gram 512x512 on the fp64 tensor cores (DMMA) + Cholesky + readout images",
                "fit_detect_symbols_per_s": world * per_group / ((us_fit + per_group * us_det) * 1e-6),
                "block": f"1 pilot + {per_group} data frames per coherence block (the tensor-core kernel wants "
                         f"one readout per {res.tc_tile_frames()}-frame tile; the reference's L = 19 cadence would "

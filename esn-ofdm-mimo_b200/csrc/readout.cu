@@ -107,7 +107,7 @@ __device__ __forceinline__ void dmma8x8x4(double (&c)[2], double a, double b) {
 }
 
 template <typename TE, bool DUAL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)        // 80 registers, no spills: three CTAs per SM (11.5 -> 7.5 ms per 1184 pilots)
 syrk_dmma_kernel(const TE *__restrict__ ext, int T, int p, int transient, int frames_per_cta,
                  int B, int shared, int accumulate, double *__restrict__ G) {
     const int m = T - transient;
@@ -288,7 +288,7 @@ __device__ __forceinline__ void group_sync(int g, int NG) {
 }
 
 template <int NG>
-__global__ void __launch_bounds__(CH_GROUP * NG, NG == 1 ? 2 : 1)
+__global__ void __launch_bounds__(CH_GROUP * NG, NG == 1 ? 3 : 1)
 cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_all, int n, int n_rhs,
                           int *__restrict__ info_all) {
     constexpr int CH_THREADS = CH_GROUP * NG;
