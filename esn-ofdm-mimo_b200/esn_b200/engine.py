@@ -101,6 +101,23 @@ class Reservoir:
             t_shift=_vec(teacher_shift, self.n_out, 0.0, self.device))}
         self._aff[ESN_F32] = {k: v.to(torch.float32) for k, v in self._aff[ESN_F64].items()}
 
+    def rescaled(self, input_scaling=None, input_shift=None, teacher_scaling=None, teacher_shift=None, noise=None):
+        """The same reservoir with other affine I/O maps (the demos rescale the inputs by 0.005 / sqrt(var_x) at
+        every Eb/N0, OFDM_MIMO_2-2_NBF_LDPC.py:237-241): shares the device copies of the weights and the
+        tensor-core weight images, so nothing is uploaded or rebuilt.  Arguments left at None are kept."""
+        import copy
+        other = copy.copy(self)
+        cur = self._aff[ESN_F64]
+        other._aff = {ESN_F64: dict(
+            in_scale=cur["in_scale"] if input_scaling is None else _vec(input_scaling, self.n_in, 1.0, self.device),
+            in_shift=cur["in_shift"] if input_shift is None else _vec(input_shift, self.n_in, 0.0, self.device),
+            t_scale=cur["t_scale"] if teacher_scaling is None else _vec(teacher_scaling, self.n_out, 1.0, self.device),
+            t_shift=cur["t_shift"] if teacher_shift is None else _vec(teacher_shift, self.n_out, 0.0, self.device))}
+        other._aff[ESN_F32] = {k: v.to(torch.float32) for k, v in other._aff[ESN_F64].items()}
+        if noise is not None:
+            other.noise = float(noise)
+        return other
+
     # ------------------------------------------------------------------ run --
     def _run(self, mode, code, inputs, teachers=None, W_out=None, group_ids=None, x0=None,
              y0=None, noise_uniforms=None, seed=0, transient=0, want_ext=False):

@@ -135,6 +135,8 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
                                seed=seed + 1, dtype=dd)
         frames_ready = torch.cuda.Event()
         frames_ready.record(side)
+        # the input pre-scale of the tensor-core detect (max |u| of the frames, one host sync) off the main stream
+        su_exp = res.input_scale_exponent(fr["esn_in"]) if detect_precision == "tc" else None
         # channel estimates from the comb pilot (:316-334) and the true channel
         ls = ofdm.synth_frames(comb_pilot(pil_idx), taps, Pi, A_clip, N, cp, qam_bits, std, noise=noise_pilot,
                                seed=seed, dtype=torch.float64, want_esn_in=False)
@@ -173,7 +175,8 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
             big[pick] = esn_in
             esn_in = big
             gids = (torch.arange(G * padded, device=dev) // padded).to(torch.int32)
-    y = res.predict(esn_in, W_out, transient=transient, group_ids=gids, precision=detect_precision,
+    readout = res.tc_prepare(W_out, su_exp) if detect_precision == "tc" else W_out
+    y = res.predict(esn_in, readout, transient=transient, group_ids=gids, precision=detect_precision,
                     seed=state_noise_seed + 1)
     if pick is not None:
         y = y[pick].contiguous()

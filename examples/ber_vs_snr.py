@@ -54,9 +54,10 @@ def main():
     W *= 0.9 / np.max(np.abs(np.linalg.eigvals(W)))
     W_in, W_fb = rng.rand(N, ni) * 2 - 1, rng.rand(N, no) * 2 - 1
 
-    def factory(var_x):
-        return Reservoir(W, W_in, W_fb, (0.005 / var_x ** 0.5) * np.ones(ni), np.zeros(ni), 5e-7 * np.ones(no),
-                         np.zeros(no), 0.001, True)
+    base = Reservoir(W, W_in, W_fb, 0.005 * np.ones(ni), np.zeros(ni), 5e-7 * np.ones(no), np.zeros(no), 0.001, True)
+
+    def factory(var_x):                                   # same device weights, inputs rescaled per Eb/N0 (:237-241)
+        return base.rescaled(input_scaling=(0.005 / var_x ** 0.5) * np.ones(ni))
     warm = torch.zeros(1, device="cuda")
     D.allreduce_sum_(warm)                                # NCCL communicator set-up stays out of the timing
     torch.cuda.synchronize()

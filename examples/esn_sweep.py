@@ -76,9 +76,10 @@ def main():
             N, rho, sp = cfgs[i]
             W, W_in, W_fb = futs.pop(i).result()
 
-            def factory(var_x):
-                return Reservoir(W, W_in, W_fb, (0.005 / var_x ** 0.5) * np.ones(ni), np.zeros(ni), 5e-7 * np.ones(no),
-                                 np.zeros(no), 0.001, True)
+            base = Reservoir(W, W_in, W_fb, 0.005 * np.ones(ni), np.zeros(ni), 5e-7 * np.ones(no), np.zeros(no), 0.001, True)
+
+            def factory(var_x, base=base):                # same device weights, inputs rescaled per Eb/N0
+                return base.rescaled(input_scaling=(0.005 / var_x ** 0.5) * np.ones(ni))
             t0 = time.time()
             c = linksim.ber_curve(factory, a.nt, a.nr, a.nsub, a.qam_bits, ebno, a.blocks, a.frames_per_block,
                                   seed=a.seed, fit_precision=a.fit_precision,

@@ -8,8 +8,11 @@ rng = np.random.RandomState(42)
 N, ni, no = 512, 16, 8
 W = rng.rand(N, N) - 0.5; W[rng.rand(N, N) < 0.1] = 0; W *= 0.9 / np.max(np.abs(np.linalg.eigvals(W)))
 W_in, W_fb = rng.rand(N, ni) * 2 - 1, rng.rand(N, no) * 2 - 1
+base = Reservoir(W, W_in, W_fb, 0.005 * np.ones(ni), np.zeros(ni), 5e-7 * np.ones(no), np.zeros(no), 0.001, True)
+
+
 def factory(var_x):
-    return Reservoir(W, W_in, W_fb, (0.005 / var_x ** 0.5) * np.ones(ni), np.zeros(ni), 5e-7 * np.ones(no), np.zeros(no), 0.001, True)
+    return base.rescaled(input_scaling=(0.005 / var_x ** 0.5) * np.ones(ni))
 eb = [0, 15, 30]
 linksim.ber_curve(factory, 4, 8, 512, 4, eb, 74, 128, seed=1)
 torch.cuda.synchronize()
