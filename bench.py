@@ -490,32 +490,37 @@ def run_gpu(args):
         # steady state with two streams: the harvest of batch k + 1 (latency-bound, 10 CTA pairs) runs beside the
         # Gram / Cholesky of batch k (every other SM)
         s_h, s_s = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+        def pipeline(nb):
+            p0, p1 = ev(), ev()
+            s_h.wait_stream(stream)
+            s_s.wait_stream(stream)
+            exts, dones = {}, {}
+            with torch.cuda.stream(s_h):
+                exts[0] = res.harvest(fu, fy, precision="tc", seed=11)
+                dones[0] = ev()
+                dones[0].record(s_h)
+            p0.record(s_s)
+            for k in range(nb):
+                if k + 1 < nb:
+                    with torch.cuda.stream(s_h):
+                        exts[k + 1] = res.harvest(fu, fy, precision="tc", seed=12 + k)
+                        dones[k + 1] = ev()
+                        dones[k + 1].record(s_h)
+                with torch.cuda.stream(s_s):
+                    s_s.wait_event(dones[k])
+                    exts[k].record_stream(s_s)
+                    w, info = res.train_readout(exts[k], fy, TRANSIENT)
+                    res.tc_prepare(w, su_fit, y_absmax=y_absmax)
+                del exts[k], w
+            p1.record(s_s)
+            torch.cuda.synchronize()
+            return p0.elapsed_time(p1)
         nb = 6
-        p0, p1 = ev(), ev()
-        s_h.wait_stream(stream)
-        s_s.wait_stream(stream)
-        exts, dones = {}, {}
-        with torch.cuda.stream(s_h):
-            exts[0] = res.harvest(fu, fy, precision="tc", seed=11)
-            dones[0] = ev()
-            dones[0].record(s_h)
-        p0.record(s_s)
-        for k in range(nb):
-            if k + 1 < nb:
-                with torch.cuda.stream(s_h):
-                    exts[k + 1] = res.harvest(fu, fy, precision="tc", seed=12 + k)
-                    dones[k + 1] = ev()
-                    dones[k + 1].record(s_h)
-            with torch.cuda.stream(s_s):
-                s_s.wait_event(dones[k])
-                exts[k].record_stream(s_s)
-                w, info = res.train_readout(exts[k], fy, TRANSIENT)
-                res.tc_prepare(w, su_fit, y_absmax=y_absmax)
-            del exts[k], w
-        p1.record(s_s)
-        torch.cuda.synchronize()
+        pipeline(3)                                            # untimed: fills the two streams' allocator pools
+        piped_total = min(pipeline(nb), pipeline(nb))
         # the first harvest is not overlapped: nb solves + 1 exposed harvest; report the per-batch time of the rest
-        piped_ms = D.max_over_ranks((p0.elapsed_time(p1) - best[0]) / nb, dev)
+        piped_ms = D.max_over_ranks((piped_total - best[0]) / nb, dev)
         fit_total = D.max_over_ranks(sum(best), dev)
         us_fit = fit_total * 1e3 / Gf                          # microseconds per trained readout
         us_fit_piped = piped_ms * 1e3 / Gf
