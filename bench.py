@@ -532,9 +532,12 @@ def run_gpu(args):
                "pipelined": {"ms_per_batch": piped_ms, "fits_per_s": world * Gf / (piped_ms * 1e-3),
                              "fit_detect_symbols_per_s": world * per_group / ((us_fit_piped + per_group * us_det) * 1e-6),
                              "what": "steady state over two CUDA streams: harvest of batch k+1 beside the Gram / Cholesky of batch k"},
-               "block": f"1 pilot + {per_group} data frames per coherence block (the tensor-core kernel wants "
-                        f"one readout per {res.tc_tile_frames()}-frame tile; the reference's L = 19 cadence would "
-                        "leave 110 of 128 tile frames empty)"}
+               "block": f"1 pilot + {per_group} data frames per coherence block",
+               "reference_cadence_L19": {
+                   "fit_detect_symbols_per_s": world * 18 / ((us_fit_piped + res.tc_tile_frames() * us_det) * 1e-6),
+                   "what": f"1 pilot + 18 data frames per block as in the reference's demos: a readout is shared by "
+                           f"{res.tc_tile_frames()} tile frames on the tensor-core kernel, so 18 of {res.tc_tile_frames()} "
+                           "frame slots carry data"}}
         del fu, fy
     dropin = None
     if world == 1 and not args.no_dropin:

@@ -225,7 +225,7 @@ struct TcParams {
     const unsigned char *readouts;           // [G][readout_bytes]
     const float *yscale;                     // [G]
     const float *in, *in_scale, *in_shift, *t_scale, *t_shift;
-    const int *group_ids;                    // [B] or null; uniform within each 128-frame tile
+    const int *group_ids;                    // [B] or null; uniform within each aligned 64 (n_out <= 8) / 128 frames
     const float *x0, *y0;                    // [B][N], [B][n_out] (scaled domain) or null
     const float *noise;                      // [B][T][N] uniforms or null
     float *ext_out;                          // [B][T][N+n_in] or null
@@ -496,7 +496,16 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
     const TcGeom gm = tc_geom(p.N, p.n_in);
     const int S = gm.S, C = gm.C, J = S >> 1;
     const bool two = J == 2;                                 // two neuron groups: G0 plain, G1 with the readout
-    const int UO = p.n_out <= 8 ? 8 : 16;                    // readout rows appended in CTA 0
+    // Readout rows appended in CTA 0: 8 or 16.  With at most 8 outputs the 16 rows can hold TWO readouts -- rows
+    // 0..7 the one of CTA 0's 64 frames, rows 8..15 the one of CTA 1's -- so a readout is shared by 64 frames,
+    // not 128 (short coherence blocks pad to half a tile).  Every frame's accumulator row then carries both
+    // outputs; its frame warp reads the columns of its own CTA's readout.
+    const int pair0_ = (blockIdx.x >> 1) * PF;
+    const int gA = p.group_ids ? p.group_ids[min(pair0_, p.B - 1)] : 0;
+    const int gB = p.group_ids ? p.group_ids[min(pair0_ + FT, p.B - 1)] : 0;
+    const bool dual = p.n_out <= 8 && gA != gB && p.teacher == nullptr;
+    const int UF = p.n_out <= 8 ? 8 : 16;                    // readout rows a frame uses
+    const int UO = dual ? 16 : UF;                           // readout rows in the MMA
     const int XC = two ? 128 : 0, RC = XC + 128;             // TMEM columns of the readout group and of the readout
     unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     unsigned char *st_hi = base, *ring = base + (size_t)2 * C * STILE;
@@ -506,7 +515,7 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
     const uint32_t rank = cluster_ctarank();
     const int pair0 = (blockIdx.x >> 1) * PF;               // first frame of the pair
     const int tile0 = pair0 + (int)rank * FT;               // first frame owned by this CTA
-    const int g = p.group_ids ? p.group_ids[min(pair0, p.B - 1)] : 0;
+    const int g = rank == 0 ? gA : gB;                       // this CTA's readout
     const int P = p.N + p.n_in;
     const bool tl0 = TL && p.timeline && blockIdx.x == 0;
     const bool harvest = p.teacher != nullptr;               // teacher-forced: y_{t-1} comes from the teacher rows
@@ -568,7 +577,7 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
         const uint32_t row = smem_u32(st_hi) + gm.ca * STILE + (f >> 3) * 1024 + (f & 7) * 128;
         const int fx = f & 7, ng = gm.UW >> 3, yg = gm.YO >> 3;
         const float su = ldexpf(1.0f, p.su), sy = ldexpf(1.0f, p.sy), ys = harvest ? 0.f : p.yscale[g];
-        const uint32_t lane_tm = tmem + ((uint32_t)(warp * 32) << 16) + RC;
+        const uint32_t lane_tm = tmem + ((uint32_t)(warp * 32) << 16) + RC + (dual ? 8u * rank : 0u);
         float cur[24], nxt[24], ut[16];   // u_it, u_{it+1} (scaled 2^su), W_out_u u_{it-1} (accumulator units)
 #pragma unroll
         for (int j = 0; j < 24; ++j) { cur[j] = 0.f; nxt[j] = 0.f; }
@@ -618,7 +627,7 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
             auto publish_step = [&]() {
                 write_inputs();
                 store8(yg, tn);
-                if (UO == 16) store8(yg + 1, tn + 8);
+                if (UF == 16) store8(yg + 1, tn + 8);
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) { arrive0(&bar_tB, r_tB); arrive0(&bar_yready, r_yr); }
@@ -646,7 +655,7 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
             float y[16];
             {
                 uint32_t yv[16];
-                if (UO == 8) {
+                if (UF == 8) {
                     uint32_t y8[8];
                     tmem_ld8(lane_tm, y8);
 #pragma unroll
@@ -667,7 +676,7 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
 #pragma unroll
                 for (int o = 0; o < 16; ++o) ysc[o] = p.feedback ? y[o] * sy : 0.f;
                 store8(yg, ysc);
-                if (UO == 16) store8(yg + 1, ysc + 8);
+                if (UF == 16) store8(yg + 1, ysc + 8);
                 fence_async_smem();
                 tc_fence_before();
                 __syncwarp();
@@ -684,7 +693,7 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
 #pragma unroll
             for (int o = 0; o < 16; ++o) {
                 float a = 0.f;
-                if (o < UO) {
+                if (o < UF) {
 #pragma unroll
                     for (int i = 0; i < 24; ++i)
                         if (i < gm.UW) a = fmaf(s_wu[o * 24 + i], cur[i], a);
@@ -704,7 +713,8 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
         // full barrier; CTA 0's producer posts the byte count of both halves.
         if (elect_one()) {
             const uint32_t ybytes = (uint32_t)UO * 128u;
-            const int yrow0 = (int)(((size_t)g * gm.readout_bytes) / 512);
+            const int yrow0 = (int)(((size_t)gA * gm.readout_bytes) / 512);      // (only CTA 0 loads readout rows)
+            const int yrow1 = (int)(((size_t)gB * gm.readout_bytes) / 512);
             const uint32_t ring_s = smem_u32(ring);
             uint32_t r_full[NST];
 #pragma unroll
@@ -718,7 +728,11 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
                 y = y && !harvest;
                 if (rank == 0) mbar_expect_tx(&bar_full[slot], 2u * SLOT + (y ? ybytes : 0u));
                 tma2_g2s(dst, &map_w, 0, ((s * C + c) * 2 + h) * (SLOT / 512), r_full[slot]);
-                if (y && rank == 0) tma2_g2s(dst + SLOT, &map_y, 0, yrow0 + (c * 2 + h) * (YTILE / 512), r_full[slot]);
+                if (y && rank == 0) {
+                    tma2_g2s(dst + SLOT, &map_y, 0, yrow0 + (c * 2 + h) * (YTILE / 512), r_full[slot]);
+                    if (dual)                                     // second readout: its 8 rows behind the first
+                        tma2_g2s(dst + SLOT + 1024, &map_y, 0, yrow1 + (c * 2 + h) * (YTILE / 512), r_full[slot]);
+                }
                 ++item;
             };
             auto chunk = [&](int j, int c) {          // the two items (hi, lo) of slab 2j + r, chunk c

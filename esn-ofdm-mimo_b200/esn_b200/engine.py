@@ -195,9 +195,10 @@ class Reservoir:
         return bool(self.lib.esn_tc_supported(self.N, self.n_in, self.n_out))
 
     def tc_tile_frames(self):
-        """Frames that must share one readout on the tensor-core path: the 128
-        frames of a CTA pair."""
-        return 128
+        """Frames that must share one readout on the tensor-core path: the 64 frames of one CTA of a pair when
+        the ESN has at most 8 outputs (the 16 readout rows of the MMA hold one readout per CTA), else the 128
+        frames of the pair."""
+        return 64 if self.n_out <= 8 else 128
 
     def input_scale_exponent(self, inputs):
         """su_exp for the tensor-core path: the power of two that brings the

@@ -118,8 +118,10 @@ int esn_set_small_batch_limit(int max_frames);
  * hi/lo operand split (three MMAs per product, fp32 accumulation in TMEM), 64
  * frames per CTA; reservoirs padded to 256 or 512 neurons run on CTA pairs
  * (cta_group::2, 128 frames per pair, state halves exchanged through DSMEM).
- * The frames of one tile (64, or 128 for the pair kernel) share one readout
- * (group_ids uniform per tile).  N <= 512, n_in <= 24, n_out <= 16.
+ * Frames share a readout in aligned runs: group_ids must be uniform over every
+ * aligned 64 frames when n_out <= 8 (the 16 readout rows of the MMA then carry one
+ * readout per CTA of the pair), over every aligned 128 frames otherwise.
+ * N <= 512, n_in <= 24, n_out <= 16.
  *
  * esn_tc_prepare_weights builds the UMMA-ready (pre-swizzled, fp16 hi/lo) image
  * of [W | W_in | 0 | W_feedb] once per reservoir -- it is shared by all CTAs and

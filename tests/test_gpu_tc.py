@@ -91,6 +91,27 @@ def test_tc_cfg3_shape_grouped_with_noise():
     print("tc cfg3 worst state err %.2e, output err %.2e" % (ws, wy))
 
 
+@pytest.mark.parametrize("n_res,n_in,n_out", [(512, 16, 8), (100, 4, 4)])
+def test_tc_two_readouts_in_one_pair_tile(n_res, n_in, n_out):
+    """With at most 8 outputs the two CTAs of a pair may use different readouts (rows 0..7 / 8..15 of the
+    readout block of the MMA): groups change every 64 frames, including inside a 128-frame tile, the same
+    group on both halves of another tile, and a ragged last tile."""
+    rng, Ws, aff, eng = _setup(n_res, n_in, n_out, seed=11, noise=0.001, in_scale=0.005)
+    assert eng.tc_tile_frames() == 64
+    T, transient = 60, 10
+    gid = np.array([0] * 64 + [1] * 64 + [2] * 128 + [1] * 64 + [0] * 37)
+    B = len(gid)
+    us = rng.randn(B, T, n_in)
+    W_outs = rng.randn(3, n_out, n_res + n_in) * np.array([1e-6, 3e-6, 5e-7])[:, None, None]
+    uni = rng.rand(B, T, n_res)
+    _check(eng, Ws, aff, us, W_outs, gid, T, transient, 0.001, uni,
+           frames=[0, 63, 64, 127, 128, 200, 255, 256, 319, 320, 356])
+    with pytest.raises(Exception):                         # a change inside a 64-frame run is refused
+        bad = gid.copy()
+        bad[10] = 2
+        eng.predict(_cuda(us), _cuda(W_outs), transient=transient, group_ids=_cuda(bad.astype(np.int32)), precision="tc")
+
+
 def test_tc_device_noise_and_no_feedback():
     from esn_b200.noise import device_noise_uniforms
     rng, Ws, aff, eng = _setup(256, 16, 8, seed=5, noise=0.001, feedback=False)
