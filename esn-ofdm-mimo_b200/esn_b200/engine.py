@@ -108,12 +108,16 @@ class Reservoir:
         import copy
         other = copy.copy(self)
         cur = self._aff[ESN_F64]
+        if "_y_absmax" not in cur:
+            cur["_y_absmax"] = float((cur["t_scale"].abs() * 4 + cur["t_shift"].abs()).max().item())
         other._aff = {ESN_F64: dict(
             in_scale=cur["in_scale"] if input_scaling is None else _vec(input_scaling, self.n_in, 1.0, self.device),
             in_shift=cur["in_shift"] if input_shift is None else _vec(input_shift, self.n_in, 0.0, self.device),
             t_scale=cur["t_scale"] if teacher_scaling is None else _vec(teacher_scaling, self.n_out, 1.0, self.device),
             t_shift=cur["t_shift"] if teacher_shift is None else _vec(teacher_shift, self.n_out, 0.0, self.device))}
-        other._aff[ESN_F32] = {k: v.to(torch.float32) for k, v in other._aff[ESN_F64].items()}
+        if teacher_scaling is None and teacher_shift is None:
+            other._aff[ESN_F64]["_y_absmax"] = cur["_y_absmax"]
+        other._aff[ESN_F32] = {k: v.to(torch.float32) for k, v in other._aff[ESN_F64].items() if k != "_y_absmax"}
         if noise is not None:
             other.noise = float(noise)
         return other
@@ -243,9 +247,11 @@ class Reservoir:
             raise EsnB200Error("tensor-core path needs N <= 512, n_inputs <= 24, n_outputs <= 16")
         W_out = self._as(W_out, torch.float64, 3)
         G = W_out.shape[0]
-        if y_absmax is None:
-            aff = self._aff[ESN_F64]
-            y_absmax = float((aff["t_scale"].abs() * 4 + aff["t_shift"].abs()).max().item())
+        if y_absmax is None:                               # cached per teacher map: a device reduction + sync here
+            aff = self._aff[ESN_F64]                       # would stall the thread that is enqueueing the detect
+            if "_y_absmax" not in aff:
+                aff["_y_absmax"] = float((aff["t_scale"].abs() * 4 + aff["t_shift"].abs()).max().item())
+            y_absmax = aff["_y_absmax"]
         sy_exp = self.output_scale_exponent(y_absmax)
         weights = self._tc_weights(su_exp, sy_exp)
         nbytes = int(self.lib.esn_tc_readout_bytes(self.N, self.n_in))

@@ -116,6 +116,10 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
     # block) is latency-bound and leaves most SMs idle; everything that does not depend on the readouts -- data
     # frame synthesis, the channel estimates and the three comparison detectors -- runs beside it on a side stream
     # and joins the main stream before the ESN detects (esn_in) and at the end (the counters).
+    if detect_precision == "tc":                        # checked first, while nothing is queued: a host sync here is free
+        per_ = B // G
+        if not (B == G * per_ and bool((block_of_frame.view(G, per_) == torch.arange(G, device=dev, dtype=block_of_frame.dtype)[:, None]).all())):
+            raise ValueError("tensor-core detect needs block-contiguous frames, the same number per block")
     main = torch.cuda.current_stream(dev)
     side = _side_stream(dev)
     side.wait_stream(main)
@@ -153,8 +157,6 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
             _, c = ofdm.demap_count(X, qam_bits, tx_idx=data_idx, want_idx=False)
             out[name] = c
             del X
-    if int(info.abs().max()) != 0:
-        raise np.linalg.LinAlgError("readout training failed for block %d" % int(torch.nonzero(info)[0]))
     del ext
     # ---- data symbols
     main.wait_event(frames_ready)
@@ -165,9 +167,6 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
         # (the filler frames are zeros and are dropped again before the FFT / slicer)
         tile = res.tc_tile_frames()
         per = B // G
-        regular = B == G * per and bool((block_of_frame.view(G, per) == torch.arange(G, device=dev, dtype=block_of_frame.dtype)[:, None]).all())
-        if not regular:
-            raise ValueError("tensor-core detect needs block-contiguous frames, the same number per block")
         if per % tile:
             padded = -(-per // tile) * tile
             pick = (torch.arange(G, device=dev)[:, None] * padded + torch.arange(per, device=dev)[None, :]).reshape(-1)
@@ -175,14 +174,19 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
             big[pick] = esn_in
             esn_in = big
             gids = (torch.arange(G * padded, device=dev) // padded).to(torch.int32)
-    readout = res.tc_prepare(W_out, su_exp) if detect_precision == "tc" else W_out
-    y = res.predict(esn_in, readout, transient=transient, group_ids=gids, precision=detect_precision,
-                    seed=state_noise_seed + 1)
+    if detect_precision == "tc":                        # layout checked above: straight to the kernel, no host sync
+        y = res.predict_tc(esn_in, res.tc_prepare(W_out, su_exp), transient=transient, group_ids=gids,
+                           seed=state_noise_seed + 1)
+    else:
+        y = res.predict(esn_in, W_out, transient=transient, group_ids=gids, precision=detect_precision,
+                        seed=state_noise_seed + 1)
     if pick is not None:
         y = y[pick].contiguous()
     total = B * N * N_t * qam_bits
     _, _, c = ofdm.unpack_fft_demap(y, N, N_t, Pi, qam_bits, tx_idx=data_idx, want_xhat=False, want_idx=False)
     out["ESN"] = c
+    if int(info.abs().max()) != 0:                      # after the detect is queued: the check costs no GPU idle time
+        raise np.linalg.LinAlgError("readout training failed for block %d" % int(torch.nonzero(info)[0]))
     main.wait_stream(side)
     for v in out.values():
         v.record_stream(main)

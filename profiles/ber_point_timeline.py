@@ -45,7 +45,7 @@ end = t0
 for e in ev:
     gap = e["ts"] - end
     name = e["name"].replace("void (anonymous namespace)::", "").split("(")[0][:50]
-    if e["dur"] > 150 or gap > 200:
+    if e["dur"] > 150 or gap > 200 or (len(sys.argv) > 1 and float(sys.argv[1]) * 1e3 <= e["ts"] - t0 <= float(sys.argv[2]) * 1e3):
         print("%8.2f ms  +%6.2f  dur %7.3f ms  stream %-3s %s%s" % ((e["ts"] - t0) / 1e3, max(gap, 0) / 1e3, e["dur"] / 1e3,
               e.get("args", {}).get("stream", "?"), name, "   <-- idle gap before" if gap > 200 else ""))
     end = max(end, e["ts"] + e["dur"])
