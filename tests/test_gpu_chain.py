@@ -319,3 +319,39 @@ def test_siso_demo_loop_matches_reference_counts():
         assert abs(r["ESN"][si] - int(g["err_ESN"][si])) <= slack
         for a, b in zip(r["esn_per_symbol"][si], g["esn_per_symbol"][si]):
             assert abs(a - int(b)) <= slack
+
+
+def test_rescaled_reservoir_equals_a_fresh_one_and_chunked_curve_adds_up():
+    """Reservoir.rescaled (same device weights, other input scaling) gives the outputs of a freshly built
+    Reservoir, bit for bit, on every recurrence path; and ber_curve's counters do not depend on how a rank's
+    blocks are cut into launches beyond the per-chunk seeds (one chunk == the unchunked run; the error totals of
+    a chunked run are those of its chunks)."""
+    from esn_b200 import Reservoir, linksim
+    rng = np.random.RandomState(3)
+    N, ni, no, T, B = 128, 4, 4, 40, 70
+    W, W_in, W_fb = orc.init_weights(rng, ni, no, N, 0.9, 0.1)
+    base = Reservoir(W, W_in, W_fb, 0.005 * np.ones(ni), np.zeros(ni), 5e-7 * np.ones(no), np.zeros(no), 0.001, True)
+    fresh = Reservoir(W, W_in, W_fb, 0.02 * np.ones(ni), np.zeros(ni), 5e-7 * np.ones(no), np.zeros(no), 0.001, True)
+    other = base.rescaled(input_scaling=0.02 * np.ones(ni))
+    us = _cuda(rng.randn(B, T, ni), torch.float32)
+    W_out = _cuda(rng.randn(1, no, N + ni) * 1e-6)
+    for prec in ("fp64", "fp32", "tc"):
+        ya = other.predict(us, W_out, transient=5, precision=prec, seed=9)
+        yb = fresh.predict(us, W_out, transient=5, precision=prec, seed=9)
+        assert torch.equal(ya, yb), prec
+    yc = base.predict(us, W_out, transient=5, precision="fp32", seed=9)
+    assert not torch.equal(yc, other.predict(us, W_out, transient=5, precision="fp32", seed=9))   # base untouched
+    # chunking
+    N_t, N_r, Ns, m = 2, 2, 64, 4
+    W2, W_in2, W_fb2 = orc.init_weights(np.random.RandomState(5), 2 * N_r, 2 * N_t, 64, 0.9, 0.1)
+    b2 = Reservoir(W2, W_in2, W_fb2, 0.005 * np.ones(2 * N_r), np.zeros(2 * N_r), 5e-7 * np.ones(2 * N_t), np.zeros(2 * N_t), 0.001, True)
+
+    def factory(var_x):
+        return b2.rescaled(input_scaling=(0.005 / var_x ** 0.5) * np.ones(2 * N_r))
+    kw = dict(seed=4, detect_precision="fp32")
+    whole = linksim.ber_curve(factory, N_t, N_r, Ns, m, [12], n_blocks=6, frames_per_block=8, **kw)
+    one = linksim.ber_curve(factory, N_t, N_r, Ns, m, [12], n_blocks=6, frames_per_block=8, max_blocks_per_launch=6, **kw)
+    assert torch.equal(whole["_counts"], one["_counts"])
+    cut = linksim.ber_curve(factory, N_t, N_r, Ns, m, [12], n_blocks=6, frames_per_block=8, max_blocks_per_launch=4, **kw)
+    assert cut["_counts"][0, :, 1].tolist() == whole["_counts"][0, :, 1].tolist()              # same number of bits
+    assert 0 < int(cut["_counts"][0, 0, 0]) < int(cut["_counts"][0, 0, 1])
