@@ -59,6 +59,7 @@ SIGNATURES = {
     "esn_version": (_i, []),
     "esn_device_info": (_i, [C.c_char_p, _i, C.POINTER(_i), C.POINTER(_i)]),
     "esn_noise_uniform_host": (C.c_float, [C.c_uint64, C.c_uint, C.c_uint, C.c_uint]),
+    "esn_mt19937_uniforms": (_i, [_vp, C.c_longlong, _i, _vp, _vp, _vp]),
     "esn_pad_sizes": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "esn_set_small_batch_limit": (_i, [_i]),
     "esn_recurrence_run": (_i, [C.POINTER(RecurrenceArgs), _vp]),

@@ -34,3 +34,45 @@ def device_noise_uniforms(seed, B, steps, N, first_frame=0):
     h = (m & _M) ^ (m >> np.uint64(32))
     bits = np.where(odd, h >> np.uint64(16), h & np.uint64(0xFFFF))
     return bits.astype(np.float64) / 65536.0
+
+
+class DeviceRandomState:
+    """The MT19937 stream of a numpy `RandomState` continued on the device (esn_mt19937_uniforms): `rand(rows,
+    cols)` returns the very doubles `rs.rand(rows, cols)` would, as a CUDA tensor, without the 1.3 ms host draw
+    and the 2 MB upload a cfg3 frame costs; `finalize()` reads the advanced state back (one small copy) and
+    installs it in `rs`, so the caller's generator -- possibly numpy's global one -- continues as after the
+    reference's own draws.  Several draws chain on the device between upload and finalize."""
+
+    def __init__(self, rs, device="cuda"):
+        import torch
+        from . import _lib
+        st = rs.get_state(legacy=True)
+        if st[0] != "MT19937":
+            raise ValueError("not an MT19937 RandomState")
+        self._rs, self._tail = rs, (st[3], st[4])
+        self._lib, self._torch = _lib, torch
+        self.device = torch.device(device)
+        host = np.empty(625, dtype=np.uint32)
+        host[:624] = st[1]
+        host[624] = st[2]
+        self._state = torch.from_numpy(host.view(np.int32)).to(self.device)
+        self._keep = []
+
+    def rand(self, rows, cols, dtype=None):
+        torch, L = self._torch, self._lib
+        dtype = dtype or torch.float64
+        count = int(rows) * int(cols)
+        out = torch.empty((int(rows), int(cols)), dtype=dtype, device=self.device)
+        if count == 0:
+            return out
+        words = torch.empty((2 * count,), dtype=torch.int32, device=self.device)
+        code = L.ESN_F64 if dtype == torch.float64 else L.ESN_F32
+        L.check(L.load().esn_mt19937_uniforms(L.ptr(self._state), count, code, L.ptr(words), L.ptr(out),
+                                             torch.cuda.current_stream().cuda_stream), "esn_mt19937_uniforms")
+        self._keep.append(words)
+        return out
+
+    def finalize(self):
+        h = self._state.cpu().numpy().view(np.uint32)
+        self._rs.set_state(("MT19937", h[:624].copy(), int(h[624]), self._tail[0], self._tail[1]))
+        self._keep.clear()

@@ -130,6 +130,17 @@ class ESN():
         return teacher_scaled
 
     # ---- fit / predict ----------------------------------------------------
+    def _device_rng(self):
+        """The noise generator continued on the device (esn_b200.noise.DeviceRandomState): the same doubles as
+        `random_state_.rand(...)`, without the host draw.  None for a generator that is not numpy's MT19937
+        RandomState (then the rows are drawn on the host, as the reference does)."""
+        import torch
+        from esn_b200.noise import DeviceRandomState
+        try:
+            return DeviceRandomState(self.random_state_), (torch.float64 if self.precision == "fp64" else torch.float32)
+        except (ValueError, AttributeError, TypeError):
+            return None, None
+
     def fit(self, inputs, outputs, transient=0, inspect=False):
         """Harvest states under teacher forcing, solve the readout, return the
         train-set prediction on all rows (reference :154-216)."""
@@ -141,9 +152,18 @@ class ESN():
             print("harvesting states...")
         # one rand(N) row per step n = 1..T-1, drawn even when noise == 0 so the
         # generator stays in step with the reference
-        uni = self.random_state_.rand(max(T - 1, 0), self.n_reservoir)
-        ext = eng.harvest(inputs[None], outputs[None], precision=self.precision,
-                          noise_uniforms=uni[None] if self.noise != 0 and T > 1 else None)
+        drng, dt = self._device_rng()
+        if drng is not None:
+            try:
+                uni = drng.rand(max(T - 1, 0), self.n_reservoir, dt)
+                ext = eng.harvest(inputs[None], outputs[None], precision=self.precision,
+                                  noise_uniforms=uni[None] if self.noise != 0 and T > 1 else None)
+            finally:
+                drng.finalize()
+        else:
+            uni = self.random_state_.rand(max(T - 1, 0), self.n_reservoir)
+            ext = eng.harvest(inputs[None], outputs[None], precision=self.precision,
+                              noise_uniforms=uni[None] if self.noise != 0 and T > 1 else None)
         if not self.silent:
             print("fitting...")
         teach = torch.from_numpy(np.ascontiguousarray(outputs, dtype=np.float64)[None])
@@ -179,11 +199,22 @@ class ESN():
             x0, y0 = self.laststate[None], np.asarray(self.lastoutput, dtype=np.float64).reshape(1, -1)
         W_out = self.W_out                      # AttributeError before fit(), as the reference
         eng = self._engine()
+        import torch
+        drng, dt = self._device_rng()
+        if drng is not None:
+            try:
+                uni = drng.rand(T, self.n_reservoir, dt)
+                y = eng.predict(inputs[None], W_out[None], transient=transient, x0=x0, y0=y0,
+                                precision=self.precision,
+                                noise_uniforms=uni[None] if self.noise != 0 else None)
+                y = y[0].to(torch.float64).cpu().numpy()
+            finally:
+                drng.finalize()
+            return y
         uni = self.random_state_.rand(T, self.n_reservoir)
         y = eng.predict(inputs[None], W_out[None], transient=transient, x0=x0, y0=y0,
                         precision=self.precision,
                         noise_uniforms=uni[None] if self.noise != 0 else None)
-        import torch
         return y[0].to(torch.float64).cpu().numpy()
 
     def fit_predict_many(self, cases):
@@ -212,14 +243,27 @@ class ESN():
         m, Tp = ms.pop(), max(Ts)
         X_in = np.zeros((n, Tp, self.n_inputs))
         X_out = np.zeros((n, Tp, self.n_outputs))
-        uni_fit = np.full((n, Tp - 1, N), 0.5)         # 0.5 = no noise on the zero-padded tail
-        uni_pred = np.full((n, Tp, N), 0.5)
-        for k, (i, o, t) in enumerate(cases):
-            T = Ts[k]
-            X_in[k, :T], X_out[k, :T] = i, o
-            uni_fit[k, :T - 1] = self.random_state_.rand(T - 1, N)
-            uni_pred[k, :T] = self.random_state_.rand(T, N)
         eng = self._engine()
+        drng, dt = self._device_rng()
+        if drng is not None:
+            try:
+                uni_fit = torch.full((n, Tp - 1, N), 0.5, dtype=dt, device=drng.device)   # 0.5 = no noise on the padded tail
+                uni_pred = torch.full((n, Tp, N), 0.5, dtype=dt, device=drng.device)
+                for k, (i, o, t) in enumerate(cases):
+                    T = Ts[k]
+                    X_in[k, :T], X_out[k, :T] = i, o
+                    uni_fit[k, :T - 1] = drng.rand(T - 1, N, dt)
+                    uni_pred[k, :T] = drng.rand(T, N, dt)
+            finally:
+                drng.finalize()
+        else:
+            uni_fit = np.full((n, Tp - 1, N), 0.5)
+            uni_pred = np.full((n, Tp, N), 0.5)
+            for k, (i, o, t) in enumerate(cases):
+                T = Ts[k]
+                X_in[k, :T], X_out[k, :T] = i, o
+                uni_fit[k, :T - 1] = self.random_state_.rand(T - 1, N)
+                uni_pred[k, :T] = self.random_state_.rand(T, N)
         noisy = self.noise != 0
         ext = eng.harvest(X_in, X_out, precision=self.precision, noise_uniforms=uni_fit if noisy else None)
         dev = ext.device

@@ -50,6 +50,15 @@ int esn_device_info(char *name_host, int n, int *sm_major_host, int *sm_minor_ho
  * recurrence kernels draw for (seed, frame, noise row, neuron). */
 float esn_noise_uniform_host(unsigned long long seed, unsigned frame, unsigned row, unsigned neuron);
 
+/* numpy's legacy generator on the device.  pyESN draws its state noise from `random_state_.rand(N_res)`, once
+ * per time step (libs/pyESN.py:125): MT19937 through numpy's random_sample.  state_dev holds the generator's
+ * state as get_state() returns it -- 624 key words followed by the position -- and is advanced in place by
+ * 2 * count outputs; out receives the `count` uniforms rand() would have returned (dtype ESN_F64, or ESN_F32 =
+ * the same doubles rounded); words_scratch: 2 * count 32-bit words, 8-byte aligned.  The host puts the advanced
+ * state back with set_state(), so the caller's generator continues exactly where the reference's would. */
+int esn_mt19937_uniforms(uint32_t *state_dev, long long count, int dtype, uint32_t *words_scratch, void *out,
+                         void *stream);
+
 /* ---------------------------------------------------------------------------
  * Reservoir recurrence.  Replaces the Python time loops and ESN._update:
  *   libs/pyESN.py:111-125 (_update), :179-182 (harvest loop of fit),

@@ -348,6 +348,42 @@ def test_dropin_edge_shapes_match_oracle(name, kw, T, one_d):
     assert rel_err(qa, qo) < 1e-6
 
 
+@pytest.mark.parametrize("prelude", ["fresh", "odd", "mid-block", "global"])
+def test_device_mt19937_continues_the_numpy_stream(prelude):
+    """esn_mt19937_uniforms: the doubles of `RandomState.rand` reproduced on the device bit for bit from the
+    host generator's state (any position inside a 624-word block, draws spanning many blocks, several draws
+    chained), and the state handed back so that the host generator continues as if it had drawn them itself."""
+    from esn_b200.noise import DeviceRandomState
+    saved = np.random.get_state()
+    try:
+        if prelude == "global":
+            np.random.seed(123)
+            rs, ref = np.random.mtrand._rand, np.random.RandomState(123)
+        else:
+            rs, ref = np.random.RandomState(77), np.random.RandomState(77)
+        if prelude == "odd":                               # an odd number of 32-bit outputs consumed
+            rs.randint(0, 2 ** 31, size=3, dtype=np.int32), ref.randint(0, 2 ** 31, size=3, dtype=np.int32)
+        if prelude == "mid-block":
+            rs.rand(1000), ref.rand(1000)
+            rs.randn(3), ref.randn(3)                      # leaves a cached gaussian in the state
+        d = DeviceRandomState(rs)
+        a = d.rand(521, 512)                               # 852 twists
+        b = d.rand(7, 3, torch.float32)
+        c = d.rand(0, 5)
+        e = d.rand(1, 1)
+        d.finalize()
+        ra, rb, rc, re = ref.rand(521, 512), ref.rand(7, 3), ref.rand(0, 5), ref.rand(1, 1)
+        assert np.array_equal(a.cpu().numpy(), ra)
+        assert np.array_equal(b.cpu().numpy(), rb.astype(np.float32))
+        assert tuple(c.shape) == rc.shape and np.array_equal(e.cpu().numpy(), re)
+        assert np.array_equal(rs.rand(2000), ref.rand(2000))            # the host generator continues in step
+        assert np.array_equal(rs.randn(5), ref.randn(5))
+        sa, sb = rs.get_state(), ref.get_state()
+        assert np.array_equal(sa[1], sb[1]) and sa[2:] == sb[2:]
+    finally:
+        np.random.set_state(saved)
+
+
 @pytest.mark.parametrize("path", ["cluster", "stream"])
 @pytest.mark.parametrize("n_res,n_in,n_out,B", [(40, 2, 2, 1), (100, 4, 4, 3), (200, 2, 2, 5), (300, 16, 8, 9),
                                                   (512, 16, 8, 1), (512, 16, 8, 2), (512, 16, 8, 7)])
