@@ -428,7 +428,15 @@ cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_al
             int i = e / n_rhs, o = e - i * n_rhs;
             const double *Lrow = A + (size_t)(k0 + nb + i) * n + k0;
             double s = 0.0;
-            for (int c = 0; c < nb; ++c) s = fma(Lrow[c], P0[c][o], s);
+            if (nb == NB) {                                          // all 32 loads of the row in flight at once
+                double l[NB];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) l[c] = Lrow[c];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) s = fma(l[c], P0[c][o], s);
+            } else {
+                for (int c = 0; c < nb; ++c) s = fma(Lrow[c], P0[c][o], s);
+            }
             Bm[(size_t)(k0 + nb + i) * n_rhs + o] -= s;
         }
         __syncthreads();
@@ -457,7 +465,15 @@ cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_al
         for (int e = tid; e < k0 * n_rhs; e += CH_THREADS) {
             int i = e / n_rhs, o = e - i * n_rhs;
             double s = 0.0;
-            for (int c = 0; c < nb; ++c) s = fma(A[(size_t)(k0 + c) * n + i], P0[c][o], s);
+            if (nb == NB) {
+                double l[NB];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) l[c] = A[(size_t)(k0 + c) * n + i];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) s = fma(l[c], P0[c][o], s);
+            } else {
+                for (int c = 0; c < nb; ++c) s = fma(A[(size_t)(k0 + c) * n + i], P0[c][o], s);
+            }
             Bm[(size_t)i * n_rhs + o] -= s;
         }
         __syncthreads();
