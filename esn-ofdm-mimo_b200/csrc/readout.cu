@@ -290,7 +290,7 @@ __device__ __forceinline__ void group_sync(int g, int NG) {
 template <int NG>
 __global__ void __launch_bounds__(CH_GROUP * NG, NG == 1 ? 3 : 1)
 cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_all, int n, int n_rhs,
-                          int *__restrict__ info_all) {
+                          int *__restrict__ info_all, double *__restrict__ pivots) {
     constexpr int CH_THREADS = CH_GROUP * NG;
     double *A = Gall + (size_t)blockIdx.x * n * n;
     double *Bm = rhs_all + (size_t)blockIdx.x * n * n_rhs;
@@ -299,10 +299,11 @@ cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_al
     PanelTile *Pall = reinterpret_cast<PanelTile *>(ch_smem);       // [NG] panel rows of the i-tile
     PanelTile *Qall = Pall + NG;                                     // [NG] panel rows of the j-tile
     __shared__ int s_info;
+    __shared__ double s_pmin, s_pmax;         // smallest / largest pivot d_jj = l_jj^2: max / min bounds cond(G) from below
     const int tid = threadIdx.x, grp = tid / CH_GROUP, gt = tid % CH_GROUP;
     PanelTile &Pn = Pall[grp], &Qn = Qall[grp];
     PanelTile &P0 = Pall[0];
-    if (tid == 0) s_info = 0;
+    if (tid == 0) { s_info = 0; s_pmin = INFINITY; s_pmax = 0.0; }
     __syncthreads();
 
     for (int k0 = 0; k0 < n; k0 += NB) {
@@ -316,6 +317,8 @@ cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_al
         for (int j = 0; j < nb; ++j) {
             if (tid == 0) {
                 double d = D[j][j];
+                s_pmin = fmin(s_pmin, d);
+                s_pmax = fmax(s_pmax, d);
                 if (!(d > 0.0)) {
                     if (s_info == 0) s_info = k0 + j + 1;
                     d = nan("");
@@ -479,6 +482,7 @@ cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_al
         __syncthreads();
     }
     if (tid == 0 && info_all) info_all[blockIdx.x] = s_info;
+    if (tid == 0 && pivots) { pivots[2 * blockIdx.x] = s_pmin; pivots[2 * blockIdx.x + 1] = s_pmax; }
 }
 
 // ---------------------------------------------------------- apply readout ---
@@ -581,6 +585,11 @@ extern "C" int esn_gram_f64(const void *ext, int ext_dtype, const void *teacher,
 
 extern "C" int esn_cholesky_solve_f64(double *G, double *rhs, int batch, int n, int n_rhs, int32_t *info,
                                       void *stream) {
+    return esn_cholesky_solve_piv_f64(G, rhs, batch, n, n_rhs, info, nullptr, stream);
+}
+
+extern "C" int esn_cholesky_solve_piv_f64(double *G, double *rhs, int batch, int n, int n_rhs, int32_t *info,
+                                          double *pivots, void *stream) {
     if (!G || !rhs || batch <= 0 || n <= 0 || n_rhs <= 0 || n_rhs > ESN_MAX_OUT) return ESN_E_BADARG;
     // many problems: 256 threads each, two CTAs per SM; no more problems than SMs: two groups per problem
     // (measured 2.15 -> 1.74 ms for one 512 x 512 problem, 2.51 -> 1.87 ms for 74; four groups leave 64
@@ -589,9 +598,9 @@ extern "C" int esn_cholesky_solve_f64(double *G, double *rhs, int batch, int n, 
     if (batch <= 148) {
         constexpr size_t smem = 2 * 2 * sizeof(PanelTile);
         ESN_CUDA_TRY(cudaFuncSetAttribute(cholesky_solve_f64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cholesky_solve_f64_kernel<2><<<batch, CH_GROUP * 2, smem, st>>>(G, rhs, n, n_rhs, info);
+        cholesky_solve_f64_kernel<2><<<batch, CH_GROUP * 2, smem, st>>>(G, rhs, n, n_rhs, info, pivots);
     } else {
-        cholesky_solve_f64_kernel<1><<<batch, CH_GROUP, 2 * sizeof(PanelTile), st>>>(G, rhs, n, n_rhs, info);
+        cholesky_solve_f64_kernel<1><<<batch, CH_GROUP, 2 * sizeof(PanelTile), st>>>(G, rhs, n, n_rhs, info, pivots);
     }
     return esn_launch_status();
 }

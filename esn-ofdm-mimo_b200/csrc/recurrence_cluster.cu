@@ -108,13 +108,13 @@ __global__ void __launch_bounds__(CL_THREADS, 1) esn_recurrence_cluster(const Re
     if (predict) {
         for (int i = tid; i < FO * CL_NS; i += CL_THREADS) {
             const int f = i / (n_out * CL_NS), o = (i / CL_NS) % n_out, c = i % CL_NS, b = f0 + f;
-            const int g = (p.group_ids && b < p.B) ? p.group_ids[b] : 0;
+            const int g = (p.group_ids && b < p.B) ? min(max(p.group_ids[b], 0), p.n_groups - 1) : 0;
             const int n = rank * CL_NS + c;
             wos[i] = (b < p.B && n < N) ? gW_out[((size_t)g * n_out + o) * P + n] : (T)0;
         }
         for (int i = tid; i < FO * n_in; i += CL_THREADS) {
             const int f = i / (n_out * n_in), o = (i / n_in) % n_out, j = i % n_in, b = f0 + f;
-            const int g = (p.group_ids && b < p.B) ? p.group_ids[b] : 0;
+            const int g = (p.group_ids && b < p.B) ? min(max(p.group_ids[b], 0), p.n_groups - 1) : 0;
             wou[i] = b < p.B ? gW_out[((size_t)g * n_out + o) * P + N + j] : (T)0;
         }
     }

@@ -96,7 +96,7 @@ esn_recurrence_simt(const RecParams p) {
     for (int i = tid; i < Kp * RS; i += THREADS) xs[i] = (T)0;
     if (tid < BT) {
         int b = tile0 + tid;
-        s_group[tid] = (predict && p.group_ids && b < p.B) ? p.group_ids[b] : 0;
+        s_group[tid] = (predict && p.group_ids && b < p.B) ? min(max(p.group_ids[b], 0), p.n_groups - 1) : 0;   // clamped: a bad id must not read outside W_out
     }
     __syncthreads();
     if (tid == 0) {

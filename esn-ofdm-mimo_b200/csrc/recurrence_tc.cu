@@ -232,6 +232,7 @@ struct TcParams {
     float *y_out;                            // [B][T-transient][n_out]
     long long *timeline;                     // [T+1][8] SM-clock stamps of CTA 0 (profiling aid) or null
     const float *teacher;                    // pair kernel, harvest mode: [B][T][n_out] raw teachers fed back (or null)
+    int n_groups;                            // readouts in `readouts` (group ids are clamped to it)
     int steps, row0;                         // recurrence steps and first input row: T, 0 (predict) / T-1, 1 (harvest)
 };
 
@@ -501,8 +502,8 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
     // not 128 (short coherence blocks pad to half a tile).  Every frame's accumulator row then carries both
     // outputs; its frame warp reads the columns of its own CTA's readout.
     const int pair0_ = (blockIdx.x >> 1) * PF;
-    const int gA = p.group_ids ? p.group_ids[min(pair0_, p.B - 1)] : 0;
-    const int gB = p.group_ids ? p.group_ids[min(pair0_ + FT, p.B - 1)] : 0;
+    const int gA = p.group_ids ? min(max(p.group_ids[min(pair0_, p.B - 1)], 0), p.n_groups - 1) : 0;
+    const int gB = p.group_ids ? min(max(p.group_ids[min(pair0_ + FT, p.B - 1)], 0), p.n_groups - 1) : 0;
     const bool dual = p.n_out <= 8 && gA != gB && p.teacher == nullptr;
     const int UF = p.n_out <= 8 ? 8 : 16;                    // readout rows a frame uses
     const int UO = dual ? 16 : UF;                           // readout rows in the MMA
@@ -985,6 +986,7 @@ extern "C" int esn_tc_predict(const esn_tc_predict_args *a, void *stream) {
     p.group_ids = a->group_ids; p.x0 = a->x0; p.y0 = a->y0; p.noise = a->noise_uniforms;
     p.ext_out = a->ext_out; p.y_out = a->y_out; p.timeline = (long long *)a->timeline;
     p.teacher = a->teacher;
+    p.n_groups = a->n_groups > 0 ? a->n_groups : 1;
     p.steps = harvest ? a->T - 1 : a->T;
     p.row0 = harvest ? 1 : 0;
     const TcGeom gm = tc_geom(a->N, a->n_in);

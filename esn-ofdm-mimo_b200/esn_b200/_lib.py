@@ -71,6 +71,7 @@ SIGNATURES = {
     "esn_tc_predict": (_i, [C.POINTER(TcPredictArgs), _vp]),
     "esn_gram_f64": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "esn_cholesky_solve_f64": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "esn_cholesky_solve_piv_f64": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "esn_readout_from_dual_f64": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "esn_transpose_rhs_f64": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "esn_apply_readout": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),

@@ -122,6 +122,27 @@ class Reservoir:
             other.noise = float(noise)
         return other
 
+    def with_affine(self, input_scaling, input_shift, teacher_scaling, teacher_shift, noise):
+        """The same reservoir with ALL affine maps and the noise amplitude replaced (None = the reference's
+        "no scaling / no shift"); shares the weight uploads and tensor-core images."""
+        import copy
+        other = copy.copy(self)
+        other._aff = {ESN_F64: dict(in_scale=_vec(input_scaling, self.n_in, 1.0, self.device),
+                                    in_shift=_vec(input_shift, self.n_in, 0.0, self.device),
+                                    t_scale=_vec(teacher_scaling, self.n_out, 1.0, self.device),
+                                    t_shift=_vec(teacher_shift, self.n_out, 0.0, self.device))}
+        other._aff[ESN_F32] = {k: v.to(torch.float32) for k, v in other._aff[ESN_F64].items()}
+        other.noise = float(noise)
+        return other
+
+    @staticmethod
+    def _check_group_ids(group_ids, n_groups):
+        """Host-resident ids are validated for free; device-resident ones are clamped by the kernels."""
+        if isinstance(group_ids, np.ndarray) or (isinstance(group_ids, torch.Tensor) and not group_ids.is_cuda):
+            g = np.asarray(group_ids)
+            if g.size and (g.min() < 0 or g.max() >= n_groups):
+                raise ValueError(f"group_ids must lie in [0, {n_groups}), got [{g.min()}, {g.max()}]")
+
     # ------------------------------------------------------------------ run --
     def _run(self, mode, code, inputs, teachers=None, W_out=None, group_ids=None, x0=None,
              y0=None, noise_uniforms=None, seed=0, transient=0, want_ext=False):
@@ -168,7 +189,8 @@ class Reservoir:
             a.W_out, a.n_groups = ptr(W_out), W_out.shape[0]
             keep.append(W_out)
             if group_ids is not None:
-                group_ids = group_ids.to(device=self.device, dtype=torch.int32).contiguous()
+                self._check_group_ids(group_ids, W_out.shape[0])
+                group_ids = torch.as_tensor(group_ids).to(device=self.device, dtype=torch.int32).contiguous()
                 a.group_ids = ptr(group_ids)
                 keep.append(group_ids)
             elif W_out.shape[0] != 1:
@@ -281,7 +303,8 @@ class Reservoir:
         a.t_scale, a.t_shift = ptr(aff["t_scale"]), ptr(aff["t_shift"])
         keep = [inputs]
         if group_ids is not None:
-            group_ids = group_ids.to(device=self.device, dtype=torch.int32).contiguous()
+            self._check_group_ids(group_ids, readout.n_groups)
+            group_ids = torch.as_tensor(group_ids).to(device=self.device, dtype=torch.int32).contiguous()
             a.group_ids = ptr(group_ids)
             keep.append(group_ids)
         elif readout.n_groups != 1:
@@ -358,10 +381,11 @@ class Reservoir:
         using readout W_out[group_ids[b]].  Returns y [B, T-transient, n_out]
         in teacher units (and E if return_ext)."""
         if precision == "tc":
+            inputs = self._as(inputs, torch.float32, 3)
             if not isinstance(W_out, TcReadout):
                 W_out = self.tc_prepare(W_out, self.input_scale_exponent(inputs))
             if group_ids is not None:
-                tiles = group_ids.to(self.device).reshape(-1)
+                tiles = torch.as_tensor(group_ids).to(self.device).reshape(-1)
                 tile = self.tc_tile_frames()
                 pad = (-tiles.numel()) % tile
                 if pad:
@@ -377,11 +401,22 @@ class Reservoir:
         return (y, ext) if return_ext else y
 
     # -------------------------------------------------------------- readout --
-    def train_readout(self, ext, teachers, transient=0, shared=False):
+    # pivot ratio min d_jj / max d_jj below which the lambda = 0 normal equations are not trusted:
+    # cond(G) >= 1 / ratio, and the relative error of the Cholesky solution grows like cond(G) * 1e-16
+    PIVOT_RATIO_MIN = 1e-11
+
+    def train_readout(self, ext, teachers, transient=0, shared=False, stable_fallback=False):
         """fp64 normal equations with lambda = 0 + Cholesky, reproducing the
         reference's pinv solution (libs/pyESN.py:191-192).  One
         readout per frame, or ONE readout over all frames when `shared`.
-        Returns (W_out [G, n_out, P] fp64, info [G] int32)."""
+        Returns (W_out [G, n_out, P] fp64, info [G] int32).
+
+        The reference solves with an SVD (`np.linalg.pinv`, rcond 1e-15), which survives extended states
+        with cond(E) ~ 1e9 (noise = 0, long frames) where the normal equations silently lose every digit.
+        The Cholesky kernel reports its pivot range (`self.last_pivot_ratio`, [G]); with
+        `stable_fallback` the problems whose factorisation failed (info != 0) or whose pivot ratio is
+        below PIVOT_RATIO_MIN are re-solved on the device by an fp64 SVD pseudo-inverse of E with the
+        reference's rcond (one host sync; the drop-in ESN.fit uses it, the batched hot path does not)."""
         B, T, P = ext.shape
         m = T - int(transient)
         dual = (m < P) and not shared
@@ -397,7 +432,26 @@ class Reservoir:
                                     ptr(aff["t_scale"]), ptr(aff["t_shift"]), B, T, P, self.n_out,
                                     int(transient), int(dual), int(shared), 0, ptr(G), ptr(rhs), _stream()),
               "esn_gram_f64")
-        return self.solve_readout(G, rhs, ext if dual else None, transient)
+        W_out, info = self.solve_readout(G, rhs, ext if dual else None, transient)
+        if stable_fallback:
+            bad = (info != 0) | ~(self.last_pivot_ratio >= self.PIVOT_RATIO_MIN)
+            if bool(bad.any()):
+                W_out, info = self._pinv_fallback(ext, teachers, transient, shared, bad, W_out, info)
+        return W_out, info
+
+    def _pinv_fallback(self, ext, teachers, transient, shared, bad, W_out, info):
+        """Ill-conditioned problems only: W_out = (pinv(E[transient:]) Y)^T in fp64 with rcond = 1e-15, the
+        reference's own formula (libs/pyESN.py:191-192), via the device SVD."""
+        aff = self._aff[ESN_F64]
+        E = ext[:, transient:, :].to(torch.float64)
+        Y = teachers[:, transient:, :].to(torch.float64) * aff["t_scale"] + aff["t_shift"]
+        if shared:
+            E, Y = E.reshape(1, -1, E.shape[-1]), Y.reshape(1, -1, Y.shape[-1])
+        W_out, info = W_out.clone(), info.clone()
+        for g in torch.nonzero(bad).flatten().tolist():
+            W_out[g] = (torch.linalg.pinv(E[g], rtol=1e-15) @ Y[g]).T
+            info[g] = 0
+        return W_out, info
 
     def gram(self, ext, teachers, transient=0):
         """Shared-readout partial sums (G [P,P], R [P,n_out]) of this rank's
@@ -417,8 +471,10 @@ class Reservoir:
         info = torch.zeros((nprob,), dtype=torch.int32, device=self.device)
         G = G.contiguous()
         rhs = rhs.contiguous()
-        check(self.lib.esn_cholesky_solve_f64(ptr(G), ptr(rhs), nprob, n, self.n_out, ptr(info), _stream()),
-              "esn_cholesky_solve_f64")
+        piv = torch.empty((nprob, 2), dtype=torch.float64, device=self.device)
+        check(self.lib.esn_cholesky_solve_piv_f64(ptr(G), ptr(rhs), nprob, n, self.n_out, ptr(info), ptr(piv),
+                                                  _stream()), "esn_cholesky_solve_piv_f64")
+        self.last_pivot_ratio = piv[:, 0] / piv[:, 1]
         W_out = torch.empty((nprob, self.n_out, self.P), dtype=torch.float64, device=self.device)
         if ext_for_dual is not None:
             B, T, P = ext_for_dual.shape

@@ -99,12 +99,27 @@ class ESN():
         self._dev = None
 
     def _engine(self):
-        if self._dev is None:
+        """The device-side reservoir.  The reference reads W, W_in, W_feedb, the scalings, `noise` and
+        `teacher_forcing` live on every call (reference :111-152), so attributes changed after construction
+        must take effect: the weights are re-uploaded when they were replaced or edited, the affine maps and
+        the noise amplitude are refreshed in place (no upload)."""
+        def vec(v):
+            return None if v is None else np.asarray(v, dtype=np.float64).tobytes()
+        wsig = (id(self.W), id(self.W_in), id(self.W_feedb), self.W.shape, float(self.W.sum()),
+                float(self.W_in.sum()), float(self.W_feedb.sum()), bool(self.teacher_forcing))
+        asig = (vec(self.input_scaling), vec(self.input_shift), vec(self.teacher_scaling),
+                vec(self.teacher_shift), float(self.noise))
+        if self._dev is None or self._dev_wsig != wsig:
             from esn_b200 import Reservoir
             self._dev = Reservoir(self.W, self.W_in, self.W_feedb,
                                   input_scaling=self.input_scaling, input_shift=self.input_shift,
                                   teacher_scaling=self.teacher_scaling, teacher_shift=self.teacher_shift,
                                   noise=self.noise, teacher_forcing=self.teacher_forcing)
+            self._dev_wsig, self._dev_asig = wsig, asig
+        elif self._dev_asig != asig:
+            self._dev = self._dev.with_affine(self.input_scaling, self.input_shift, self.teacher_scaling,
+                                              self.teacher_shift, self.noise)
+            self._dev_asig = asig
         return self._dev
 
     # ---- the affine maps, kept for API parity (reference :127-152) -------
@@ -167,7 +182,7 @@ class ESN():
         if not self.silent:
             print("fitting...")
         teach = torch.from_numpy(np.ascontiguousarray(outputs, dtype=np.float64)[None])
-        W_out, info = eng.train_readout(ext, teach, transient)
+        W_out, info = eng.train_readout(ext, teach, transient, stable_fallback=True)
         if int(info[0]) != 0:
             raise np.linalg.LinAlgError(
                 f"readout Gram matrix is not positive definite (pivot {int(info[0])}): "
@@ -270,7 +285,8 @@ class ESN():
         rows = torch.tensor([[c[2] + r for r in range(m)] for c in cases], device=dev)       # [n, m]
         sel = torch.arange(n, device=dev)[:, None]
         teach = torch.from_numpy(X_out).to(dev)
-        W_out, info = eng.train_readout(ext[sel, rows].contiguous(), teach[sel, rows].contiguous(), 0)
+        W_out, info = eng.train_readout(ext[sel, rows].contiguous(), teach[sel, rows].contiguous(), 0,
+                                        stable_fallback=True)
         if int(info.abs().max()) != 0:
             bad = int(torch.nonzero(info)[0])
             raise np.linalg.LinAlgError(

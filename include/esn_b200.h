@@ -195,6 +195,11 @@ int esn_tc_predict(const esn_tc_predict_args *args_host, void *stream);
  * esn_cholesky_solve_f64: in-place batched Cholesky G = L L^T and solve for
  *   n_rhs right-hand sides; info[b] = 0 or the 1-based index of the first
  *   non-positive pivot (as LAPACK potrf).
+ * esn_cholesky_solve_piv_f64: the same, and pivots[b] = {min_j d_jj, max_j d_jj} (d_jj = l_jj^2, the
+ *   pivots of the factorisation): max / min is a lower bound of cond(G) = cond(E)^2.  The reference's
+ *   pinv (libs/pyESN.py:191-192) is an SVD solve and survives cond(E) ~ 1e9 where lambda = 0 normal
+ *   equations lose all digits without failing; the host uses the ratio to route such problems to a
+ *   stable solve.  `pivots` may be null.
  * esn_readout_from_dual_f64: W_out[b] = (E^T A)^T, [n_out][p].
  * esn_transpose_rhs_f64: primal: W_out[b] = rhs^T.
  * ------------------------------------------------------------------------- */
@@ -205,6 +210,8 @@ int esn_gram_f64(const void *ext, int ext_dtype, const void *teacher, int teache
                  double *G, double *rhs, void *stream);
 int esn_cholesky_solve_f64(double *G, double *rhs, int batch, int n, int n_rhs,
                            int32_t *info, void *stream);
+int esn_cholesky_solve_piv_f64(double *G, double *rhs, int batch, int n, int n_rhs,
+                               int32_t *info, double *pivots, void *stream);
 int esn_readout_from_dual_f64(const void *ext, int ext_dtype, const double *A, int B, int T,
                               int p, int n_out, int transient, double *W_out, void *stream);
 int esn_transpose_rhs_f64(const double *rhs, int B, int p, int n_out, double *W_out,

@@ -70,6 +70,8 @@ TRAINER_CASES = {
     "gen_2x2": dict(N=32, N_t=2, N_r=2, n_res=40, isi=8, seed=23, ebno=12, m=4),
     "gen_4x8": dict(N=32, N_t=4, N_r=8, n_res=48, isi=8, seed=29, ebno=15, m=4),
     "gen_1x2": dict(N=32, N_t=1, N_r=2, n_res=32, isi=8, seed=31, ebno=9, m=4),
+    # BASELINE.json configs[2] at full size: 4x8, N_sub = 512, 512 neurons (T = 522, underdetermined 512 x 528 fit)
+    "gen_4x8_n512": dict(N=512, N_t=4, N_r=8, n_res=512, isi=8, seed=37, ebno=15, m=4),
 }
 
 

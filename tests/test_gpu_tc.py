@@ -246,3 +246,117 @@ def test_tc_harvest_fit_detects_like_fp64_fit():
     d = rel_err(ytc, y64)
     print("detector outputs, tc-trained vs fp64-trained readout: %.2e" % d)
     assert d < 2e-3
+
+
+# --------------------------------------------------------------------------
+# north_star criterion 3 on the benchmarked kernel: detected symbol indices
+# --------------------------------------------------------------------------
+_IDX_CTX = {}
+
+
+def _oracle_indices(b):
+    """Oracle side of one frame (runs in a forked worker): pyESN.predict -> unpack + FFT -> nearest point."""
+    c = _IDX_CTX
+    g = c["gid"][b]
+    y = orc.predict(c["W"], c["W_in"], c["W_fb"], c["W_outs"][g], c["us"][b], c["transient"], c["noise"],
+                    c["uni"][b].astype(np.float64), **c["aff"])
+    X = orc.esn_output_to_freq(y, c["N_sub"], c["N_t"], c["Pi"])
+    return orc.hard_demap_indices(X, c["const"]).astype(np.uint8), orc.boundary_distance(X, c["m"])
+
+
+def _link_frames(n_blocks, n_data, ebno=15.0, N_sub=512, N_t=4, N_r=8, m=4, seed0=400):
+    """Pilot-trained readouts and data frames of `n_blocks` coherence blocks of the block-fading 4x8 link
+    (oracle generator = OFDM_MIMO_2-2_NBF_LDPC.py:270-312, 387-433)."""
+    blks = [orc.synth_block(seed0 + k, N_sub, N_t, N_r, m, ebno, n_data) for k in range(n_blocks)]
+    return blks
+
+
+def test_tc_cfg3_symbol_indices_match_oracle():
+    """cfg3 (4x8, 512 subcarriers, 512 neurons, T = 522), 256 data frames of two coherence blocks with their
+    own pilot-trained readouts, host-supplied state noise: the symbol indices of the tensor-core path
+    (predict -> unpack + FFT -> slicer, what bench.py times) against the oracle's pyESN.predict ->
+    FFT -> nearest-point search.  BASELINE.json: bit-exact except symbols within 1e-5 of a decision
+    boundary, which are counted.  The fp32 and fp64 kernels are held to the same statement on a subset."""
+    import multiprocessing as mp
+    import os
+    from esn_b200 import ofdm
+    c = cases.ESN_CASES["cfg3_4x8_n512"]
+    N_sub, N_t, N_r, m, d, cp, T = 512, 4, 8, 4, 3, 7, c["T"]
+    n_blocks, n_data = 2, 128
+    blks = _link_frames(n_blocks, n_data)
+    rng = np.random.RandomState(c["seed"])
+    W, W_in, W_fb = orc.init_weights(rng, c["n_in"], c["n_out"], c["n_res"], c["rho"], c["sparsity"])
+    aff = dict(input_scaling=(0.005 / blks[0]["var_x"] ** 0.5) * np.ones(c["n_in"]), input_shift=np.zeros(c["n_in"]),
+               teacher_scaling=5e-7 * np.ones(c["n_out"]), teacher_shift=np.zeros(c["n_out"]), teacher_forcing=True)
+    from esn_b200 import Reservoir
+    eng = Reservoir(W, W_in, W_fb, aff["input_scaling"], aff["input_shift"], aff["teacher_scaling"],
+                    aff["teacher_shift"], c["noise"], True)
+    W_outs = []
+    for blk in blks:                                       # reference-style training on the pilot (oracle fit)
+        ein, eout = orc.pack_io(blk["pilot"]["y_CP"], blk["pilot"]["x_CP"], d, N_sub, cp, N_t, N_r)
+        W_outs.append(orc.fit(W, W_in, W_fb, ein, eout, d + cp, c["noise"], rng.rand(T - 1, c["n_res"]), **aff)["W_out"])
+    W_outs = np.stack(W_outs)
+    us = np.stack([orc.pack_rx(f["y_CP"], d) for blk in blks for f in blk["data"]])
+    tx_idx = np.stack([f["idx"] for blk in blks for f in blk["data"]]).astype(np.uint8)
+    gid = np.repeat(np.arange(n_blocks), n_data)
+    B = us.shape[0]
+    uni = rng.rand(B, T, c["n_res"]).astype(np.float32)
+    Pi = blks[0]["Pi"]
+    _IDX_CTX.update(W=W, W_in=W_in, W_fb=W_fb, W_outs=W_outs, us=us, gid=gid, uni=uni, aff=aff,
+                    transient=d + cp, noise=c["noise"], N_sub=N_sub, N_t=N_t, Pi=Pi, m=m, const=blks[0]["const"])
+    workers = max(1, min(16, (os.cpu_count() or 2)))
+    with mp.get_context("fork").Pool(workers) as pool:
+        ref = pool.map(_oracle_indices, range(B), chunksize=4)
+    idx_ref = np.stack([r[0] for r in ref])
+    dist = np.stack([r[1] for r in ref])
+    near = dist < 1e-5
+    errs_ref = int(np.unpackbits((idx_ref ^ tx_idx)[..., None], axis=-1).sum())
+    report = {}
+    for precision, frames in (("tc", B), ("fp32", 64), ("fp64", 32)):
+        sel = slice(0, frames)
+        y = eng.predict(_cuda(us[sel]), _cuda(W_outs), transient=d + cp, group_ids=_cuda(gid[sel].astype(np.int32)),
+                        precision=precision, noise_uniforms=_cuda(uni[sel]))
+        X, idx, counts = ofdm.unpack_fft_demap(y, N_sub, N_t, Pi, m, tx_idx=_cuda(tx_idx[sel]), boundary_eps=1e-5)
+        idx = idx.cpu().numpy()
+        mism = idx != idx_ref[sel]
+        outside = mism & ~near[sel]
+        report[precision] = dict(symbols=int(mism.size), near_boundary_oracle=int(near[sel].sum()),
+                                 near_boundary_kernel=int(counts[1]), mismatches=int(mism.sum()),
+                                 mismatch_outside_band=int(outside.sum()),
+                                 worst_mismatch_distance=float(dist[sel][mism].max()) if mism.any() else 0.0)
+        if precision == "tc":
+            e_ref = errs_ref
+            assert abs(int(counts[0]) - e_ref) <= m * (int(mism.sum()) + 1)
+    print("symbol-index parity at cfg3:", report)
+    for precision, r in report.items():
+        assert r["mismatch_outside_band"] == 0, (precision, r)
+
+
+def test_tc_harvest_wout_error_is_reported_and_bounded():
+    """W_out of a readout trained on tensor-core states vs the reference's pinv solution (oracle fit on the
+    same host-supplied noise) at cfg3.  The 1e-4 parity bar holds for the fp64 harvest; the tensor-core
+    harvest is a THROUGHPUT mode: its error is measured, printed and bounded here, and bench.py labels the
+    fit figure that uses it accordingly."""
+    c = cases.ESN_CASES["cfg3_4x8_n512"]
+    kw = cases.esn_kwargs(c)
+    o = orc.OracleESN(**kw)
+    from esn_b200 import Reservoir
+    eng = Reservoir(o.W, o.W_in, o.W_feedb, kw["input_scaling"], kw["input_shift"],
+                    kw["teacher_scaling"], kw["teacher_shift"], c["noise"], c["teacher_forcing"])
+    G, T, N = 3, c["T"], c["n_res"]
+    us = np.stack([cases.esn_io(c, i)[0] for i in range(G)])
+    ys = np.stack([cases.esn_io(c, i)[1] for i in range(G)])
+    uni = np.random.RandomState(5).rand(G, T - 1, N)
+    aff = dict(input_scaling=kw["input_scaling"], input_shift=kw["input_shift"],
+               teacher_scaling=kw["teacher_scaling"], teacher_shift=kw["teacher_shift"])
+    ref = np.stack([orc.fit(o.W, o.W_in, o.W_feedb, us[g], ys[g], c["transient"], c["noise"], uni[g], **aff)["W_out"]
+                    for g in range(G)])
+    errs = {}
+    for precision in ("fp64", "fp32", "tc"):
+        ext = eng.harvest(_cuda(us), _cuda(ys), precision=precision, noise_uniforms=_cuda(uni))
+        W, info = eng.train_readout(ext, _cuda(ys), c["transient"])
+        assert int(info.abs().max()) == 0
+        errs[precision] = max(rel_err(W[g].cpu().numpy(), ref[g]) for g in range(G))
+    print("W_out relative error vs pinv at cfg3 by harvest precision:", {k: "%.2e" % v for k, v in errs.items()})
+    assert errs["fp64"] < 1e-4
+    assert errs["tc"] < 5e-2          # throughput mode: NOT parity-grade (see DESIGN.md §4.4)
