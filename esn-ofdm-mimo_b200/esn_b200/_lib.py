@@ -53,6 +53,20 @@ class TcPredictArgs(C.Structure):
     ]
 
 
+class TcsArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("T", C.c_int32), ("N", C.c_int32), ("n_in", C.c_int32), ("n_out", C.c_int32),
+        ("transient", C.c_int32), ("feedback", C.c_int32), ("su_exp", C.c_int32), ("sy_exp", C.c_int32),
+        ("n_groups", C.c_int32), ("accumulators", C.c_int32), ("ring_a", C.c_int32), ("ring_b", C.c_int32),
+        ("noise_amp", C.c_double), ("seed", C.c_uint64),
+        ("weights", C.c_void_p), ("wo_x", C.c_void_p), ("wo_u", C.c_void_p), ("inp", C.c_void_p),
+        ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("t_scale", C.c_void_p), ("t_shift", C.c_void_p),
+        ("group_ids", C.c_void_p), ("x0", C.c_void_p), ("y0", C.c_void_p), ("noise_uniforms", C.c_void_p),
+        ("ext_out", C.c_void_p), ("y_out", C.c_void_p), ("teacher", C.c_void_p), ("workspace", C.c_void_p),
+        ("timeline", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/esn_b200.h declares
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
 SIGNATURES = {
@@ -69,6 +83,11 @@ SIGNATURES = {
     "esn_tc_prepare_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "esn_tc_prepare_readout": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "esn_tc_predict": (_i, [C.POINTER(TcPredictArgs), _vp]),
+    "esn_tcs_supported": (_i, [_i, _i, _i]),
+    "esn_tcs_workspace_bytes": (C.c_longlong, [_i, _i]),
+    "esn_tcs_readout_floats": (C.c_longlong, [_i, _i, C.POINTER(C.c_longlong)]),
+    "esn_tcs_prepare_readout": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "esn_tcs_run": (_i, [C.POINTER(TcsArgs), _vp]),
     "esn_gram_f64": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "esn_cholesky_solve_f64": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "esn_cholesky_solve_piv_f64": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),

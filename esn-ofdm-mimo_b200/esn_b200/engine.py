@@ -58,6 +58,13 @@ class TcReadout:
         self.su_exp, self.sy_exp, self.n_groups = su_exp, sy_exp, n_groups
 
 
+class TcsReadout:
+    """fp32 readout tables of the streamed-state tensor-core kernel (Reservoir.tcs_prepare)."""
+
+    def __init__(self, wo_x, wo_u, n_groups):
+        self.wo_x, self.wo_u, self.n_groups = wo_x, wo_u, n_groups
+
+
 class Reservoir:
     """Device-resident reservoir weights and the affine I/O maps of one ESN
     (reference libs/pyESN.py:93-152).  Weights are uploaded once, in the
@@ -366,20 +373,148 @@ class Reservoir:
         check(self.lib.esn_tc_predict(C.byref(a), _stream()), "esn_tc_predict(harvest)")
         return ext
 
+    # ------------------------------------- tensor cores, state streamed through L2 --
+    def tcs_supported(self):
+        return bool(self.lib.esn_tcs_supported(self.N, self.n_in, self.n_out))
+
+    def tcs_prepare(self, W_out):
+        """fp32 readout tables for W_out [G, n_out, P] (any G; frames pick their readout freely)."""
+        W_out = self._as(W_out, torch.float64, 3)
+        G = W_out.shape[0]
+        nu = C.c_longlong()
+        nx = int(self.lib.esn_tcs_readout_floats(self.N, self.n_out, C.byref(nu)))
+        wo_x = torch.empty((G, nx), dtype=torch.float32, device=self.device)
+        wo_u = torch.empty((G, nu.value), dtype=torch.float32, device=self.device)
+        check(self.lib.esn_tcs_prepare_readout(ptr(W_out), self.N, self.n_in, self.n_out, G, ptr(wo_x), ptr(wo_u),
+                                               _stream()), "esn_tcs_prepare_readout")
+        return TcsReadout(wo_x, wo_u, G)
+
+    def _tcs_workspace(self, B):
+        nbytes = int(self.lib.esn_tcs_workspace_bytes(B, self.N))
+        ws = getattr(self, "_tcs_ws", None)
+        if ws is None or ws.numel() < nbytes or ws.device != self.device:
+            ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+            self._tcs_ws = ws
+        return ws
+
+    def _tcs_run(self, inputs, readout=None, teachers=None, transient=0, group_ids=None, x0=None, y0=None,
+                 noise_uniforms=None, seed=0, return_ext=False, y_absmax=None, tune=None, timeline=None):
+        if not self.tcs_supported():
+            raise EsnB200Error("tensor-core path needs N <= 4096, n_inputs <= 24, n_outputs <= 16")
+        inputs = self._as(inputs, torch.float32, 3)
+        B, T, n_in = inputs.shape
+        if n_in != self.n_in:
+            raise ValueError(f"inputs have {n_in} columns, ESN has n_inputs={self.n_in}")
+        harvest = teachers is not None
+        aff = self._aff[ESN_F32]
+        if harvest:
+            teachers = self._as(teachers, torch.float32, 3)
+            if tuple(teachers.shape) != (B, T, self.n_out):
+                raise ValueError(f"teachers must be [{B},{T},{self.n_out}]")
+            y_absmax = float((teachers * aff["t_scale"] + aff["t_shift"]).abs().max().item())
+        elif y_absmax is None:
+            a64 = self._aff[ESN_F64]
+            if "_y_absmax" not in a64:
+                a64["_y_absmax"] = float((a64["t_scale"].abs() * 4 + a64["t_shift"].abs()).max().item())
+            y_absmax = a64["_y_absmax"]
+        su_exp, sy_exp = self.input_scale_exponent(inputs), self.output_scale_exponent(y_absmax)
+        a = _lib.TcsArgs()
+        a.B, a.T, a.N, a.n_in, a.n_out = B, T, self.N, self.n_in, self.n_out
+        a.transient, a.feedback = int(transient), int(self.teacher_forcing)
+        a.su_exp, a.sy_exp = su_exp, sy_exp
+        a.noise_amp, a.seed = self.noise, int(seed) & 0xFFFFFFFFFFFFFFFF
+        if tune:
+            a.accumulators, a.ring_a, a.ring_b = (int(tune.get(k, 0)) for k in ("accumulators", "ring_a", "ring_b"))
+        weights = self._tc_weights(su_exp, sy_exp)
+        ws = self._tcs_workspace(B)
+        a.weights, a.inp, a.workspace = ptr(weights), ptr(inputs), ptr(ws)
+        a.in_scale, a.in_shift = ptr(aff["in_scale"]), ptr(aff["in_shift"])
+        a.t_scale, a.t_shift = ptr(aff["t_scale"]), ptr(aff["t_shift"])
+        steps = T - 1 if harvest else T
+        keep = [inputs, weights, ws]
+        if noise_uniforms is not None:
+            noise_uniforms = self._as(noise_uniforms, torch.float32, 3)
+            if tuple(noise_uniforms.shape) != (B, steps, self.N):
+                raise ValueError(f"noise_uniforms must be [{B},{steps},{self.N}]")
+            a.noise_uniforms = ptr(noise_uniforms)
+        ext = y = None
+        if harvest or return_ext:
+            ext = torch.empty((B, T, self.P), dtype=torch.float32, device=self.device)
+            a.ext_out = ptr(ext)
+        if harvest:
+            a.teacher = ptr(teachers)
+        else:
+            a.wo_x, a.wo_u, a.n_groups = ptr(readout.wo_x), ptr(readout.wo_u), readout.n_groups
+            if group_ids is not None:
+                self._check_group_ids(group_ids, readout.n_groups)
+                group_ids = torch.as_tensor(group_ids).to(device=self.device, dtype=torch.int32).contiguous()
+                a.group_ids = ptr(group_ids)
+            elif readout.n_groups != 1:
+                raise ValueError("group_ids required when the readout handle holds more than one readout")
+            if x0 is not None:
+                x0 = self._as(x0, torch.float32, 2)
+                a.x0 = ptr(x0)
+            if y0 is not None:
+                y0 = self._as(y0, torch.float32, 2)
+                a.y0 = ptr(y0)
+            y = torch.empty((B, T - int(transient), self.n_out), dtype=torch.float32, device=self.device)
+            a.y_out = ptr(y)
+        if timeline is not None:
+            a.timeline = ptr(timeline)
+        check(self.lib.esn_tcs_run(C.byref(a), _stream()), "esn_tcs_run")
+        return y, ext
+
+    def predict_tcs(self, inputs, readout, transient=0, group_ids=None, x0=None, y0=None, noise_uniforms=None,
+                    seed=0, return_ext=False, y_absmax=None, tune=None, timeline=None):
+        """Free-running prediction on the tensor cores with the state streamed through L2: any reservoir size up to
+        4096 neurons, any frame -> readout map.  `readout`: W_out [G, n_out, P] or the handle from tcs_prepare."""
+        if not isinstance(readout, TcsReadout):
+            readout = self.tcs_prepare(readout)
+        y, ext = self._tcs_run(inputs, readout=readout, transient=transient, group_ids=group_ids, x0=x0, y0=y0,
+                               noise_uniforms=noise_uniforms, seed=seed, return_ext=return_ext, y_absmax=y_absmax,
+                               tune=tune, timeline=timeline)
+        return (y, ext) if return_ext else y
+
+    def harvest_tcs(self, inputs, teachers, noise_uniforms=None, seed=0, tune=None):
+        """Teacher-forced harvesting with the streamed-state tensor-core kernel (throughput mode, see harvest_tc)."""
+        return self._tcs_run(inputs, teachers=teachers, noise_uniforms=noise_uniforms, seed=seed, tune=tune)[1]
+
     def harvest(self, inputs, teachers, precision="fp64", noise_uniforms=None, seed=0):
         """Teacher-forced harvesting (libs/pyESN.py:179-182).  Returns the
-        extended states E [B, T, N+n_in] = [x_n, u_n] (libs/pyESN.py:189)."""
+        extended states E [B, T, N+n_in] = [x_n, u_n] (libs/pyESN.py:189).  precision 'auto' = 'fp64': the readout
+        solve amplifies state errors, and only the fp64 harvest keeps W_out inside the 1e-4 bar with margin
+        (measured at cfg3: fp64 3e-9, fp32 1.0e-4, tensor cores 1.9e-4); 'tc' is the throughput mode."""
+        if precision == "auto":
+            precision = "fp64"
         if precision == "tc":
+            if not self.tc_supported():
+                return self.harvest_tcs(inputs, teachers, noise_uniforms=noise_uniforms, seed=seed)
             return self.harvest_tc(inputs, teachers, noise_uniforms=noise_uniforms, seed=seed)
+        if precision == "tcs":
+            return self.harvest_tcs(inputs, teachers, noise_uniforms=noise_uniforms, seed=seed)
         ext, _ = self._run(MODE_HARVEST, dtype_code(precision), inputs, teachers=teachers,
                            noise_uniforms=noise_uniforms, seed=seed)
         return ext
 
     def predict(self, inputs, W_out, transient=0, group_ids=None, x0=None, y0=None,
-                precision="fp32", noise_uniforms=None, seed=0, return_ext=False):
+                precision="auto", noise_uniforms=None, seed=0, return_ext=False):
         """Free-running prediction (libs/pyESN.py:243-255) of B frames, frame b
         using readout W_out[group_ids[b]].  Returns y [B, T-transient, n_out]
-        in teacher units (and E if return_ext)."""
+        in teacher units (and E if return_ext).  precision: 'auto' (the fastest kernel for this batch, reservoir
+        and readout layout: auto_predict_path), 'fp64' / 'fp32' (cluster or streaming SIMT kernels), 'tc' (tensor
+        cores: resident kernel, or the streamed-state kernel where that one cannot go), 'tcs'."""
+        if precision == "auto":
+            if isinstance(W_out, TcReadout):
+                precision = "tc"
+            elif isinstance(W_out, TcsReadout):
+                precision = "tcs"
+            else:
+                B = inputs.shape[0] if getattr(inputs, "ndim", 3) == 3 else 1
+                precision = self.auto_predict_path(B, group_ids)
+        if precision == "tcs" or (precision == "tc" and not isinstance(W_out, TcReadout)
+                                  and not self._tc_resident_ok(inputs, group_ids)):
+            return self.predict_tcs(inputs, W_out, transient=transient, group_ids=group_ids, x0=x0, y0=y0,
+                                    noise_uniforms=noise_uniforms, seed=seed, return_ext=return_ext)
         if precision == "tc":
             inputs = self._as(inputs, torch.float32, 3)
             if not isinstance(W_out, TcReadout):
@@ -400,10 +535,54 @@ class Reservoir:
                            seed=seed, transient=transient, want_ext=return_ext)
         return (y, ext) if return_ext else y
 
+    # ---- automatic path selection (north_star: "tcgen05 tiles at large batch, a warp-shuffle FFMA path at small
+    # batch, crossover picked from ncu tensor-pipe and HBM counters").  A tensor-core launch costs one tile time
+    # whatever the batch (a CTA pair steps 128 frames through all T steps; 74 pairs are resident), the cluster /
+    # streaming SIMT kernels cost one wave per ~48-300 frames: below AUTO_TC_MIN_FRAMES[N_pad] frames the SIMT
+    # side is faster AND more accurate (4e-7 vs 9e-6 state error).  Table measured by profiles/crossover.py
+    # (profiles/r2_crossover.txt, with the ncu counters of both sides at the boundary).
+    AUTO_TC_MIN_FRAMES = {256: 512, 512: 128}
+    AUTO_TCS_MIN_FRAMES = 64              # reservoirs above 512 neurons: streamed tensor-core kernel vs streaming SIMT
+
+    def auto_predict_path(self, B, group_ids=None):
+        """'tc' (resident tensor-core kernel), 'tcs' (streamed-state tensor-core kernel) or 'fp32' (cluster kernel
+        for small batches / streaming SIMT kernel) for a predict call of B frames."""
+        if not self.tcs_supported():
+            return "fp32"
+        if self.N > 512:
+            return "tcs" if B >= self.AUTO_TCS_MIN_FRAMES else "fp32"
+        n_pad = 256 if self.N <= 256 else 512
+        if B < self.AUTO_TC_MIN_FRAMES[n_pad]:
+            return "fp32"
+        return "tc" if self._tc_resident_ok(None, group_ids) else "tcs"
+
+    def _tc_resident_ok(self, inputs, group_ids):
+        """True when the resident tensor-core kernel can take the call: N <= 512 and every readout shared by whole
+        aligned tiles.  Host-resident group ids are inspected for free; device-resident ones cost one sync."""
+        if not self.tc_supported():
+            return False
+        if group_ids is None:
+            return True
+        tiles = torch.as_tensor(group_ids).reshape(-1)
+        key = (tiles.data_ptr(), tiles.numel(), getattr(tiles, "_version", 0)) if tiles.is_cuda else None
+        cache = getattr(self, "_tile_ok_cache", None)
+        if key is not None and cache is not None and cache[0] == key:
+            return cache[1]
+        tile = self.tc_tile_frames()
+        pad = (-tiles.numel()) % tile
+        if pad:
+            tiles = torch.cat([tiles, tiles[-1:].expand(pad)])
+        tiles = tiles.view(-1, tile)
+        ok = bool((tiles == tiles[:, :1]).all())
+        if key is not None:
+            self._tile_ok_cache = (key, ok)
+        return ok
+
     # -------------------------------------------------------------- readout --
-    # pivot ratio min d_jj / max d_jj below which the lambda = 0 normal equations are not trusted:
-    # cond(G) >= 1 / ratio, and the relative error of the Cholesky solution grows like cond(G) * 1e-16
-    PIVOT_RATIO_MIN = 1e-11
+    # pivot ratio min d_jj / max d_jj below which the lambda = 0 normal equations are not trusted.  Calibrated on
+    # reservoir Gram matrices against the SVD solution: W_out error ~ 3e-14 / ratio (ratio 2.8e-6 and error
+    # 6e-9 for a cfg3 pilot with the default noise, 3.7e-9 / 2.4e-6 with noise = 0, 9.6e-10 / 1.6e-5, 2.7e-12 / 1e-2)
+    PIVOT_RATIO_MIN = 1e-9
 
     def train_readout(self, ext, teachers, transient=0, shared=False, stable_fallback=False):
         """fp64 normal equations with lambda = 0 + Cholesky, reproducing the

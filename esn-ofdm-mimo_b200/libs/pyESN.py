@@ -15,8 +15,9 @@ track the reference on identical seeds.  Everything else -- the time loops, the
 readout solve, the train-set prediction -- runs in CUDA (no CPU fallback).
 
 Additive API (not in the reference): `fit_batched` / `predict_batched` on torch
-CUDA tensors, `precision=` ('fp64' default for the single-frame calls, 'fp32'
-for throughput).
+CUDA tensors, `precision=` ('fp64' default for the single-frame calls and for
+training; 'auto' for batched detection: tensor cores at large batch, cluster /
+SIMT fp32 kernels at small batch).
 """
 import os
 import sys
@@ -312,10 +313,12 @@ class ESN():
         ext = eng.harvest(inputs, outputs, precision=precision, noise_uniforms=noise_uniforms, seed=seed)
         return eng.train_readout(ext, outputs, transient, shared=shared)
 
-    def predict_batched(self, inputs, W_out, transient=0, group_ids=None, precision="fp32",
+    def predict_batched(self, inputs, W_out, transient=0, group_ids=None, precision="auto",
                         noise_uniforms=None, seed=0, x0=None, y0=None):
         """Detect B frames [B,T,n_in] in one launch; frame b uses readout
-        W_out[group_ids[b]].  Returns y [B,T-transient,n_out] on the device."""
+        W_out[group_ids[b]].  Returns y [B,T-transient,n_out] on the device.  precision='auto' picks the fastest
+        kernel for the batch size, reservoir size and readout layout (tensor cores at large batch, the
+        cluster / SIMT fp32 kernels at small batch; esn_b200.engine.Reservoir.auto_predict_path)."""
         return self._engine().predict(inputs, W_out, transient=transient, group_ids=group_ids,
                                       precision=precision, noise_uniforms=noise_uniforms, seed=seed,
                                       x0=x0, y0=y0)

@@ -179,6 +179,62 @@ int esn_tc_prepare_readout(const double *W_out, int N, int n_in, int n_out, int 
 int esn_tc_predict(const esn_tc_predict_args *args_host, void *stream);
 
 /* ---------------------------------------------------------------------------
+ * Tensor-core recurrence with the state streamed through L2 ("tcs"): the same
+ * reference lines and the same fp16 hi/lo arithmetic as esn_tc_predict
+ * (libs/pyESN.py:179-182, 243-255), for what the resident kernel cannot take:
+ *   - reservoirs of 513..4096 neurons (the 4x8 fast demo's 600 neurons,
+ *     system_model_2/Demo_MIMO_4x8_ChannelRank_TrainSNR_LDPC_fast.py:142; the
+ *     sweep's 1024 / 2048, BASELINE.json configs[3]);
+ *   - ANY frame -> readout map (group_ids unrestricted): the demos train a new
+ *     readout every L = 19 symbols (OFDM_MIMO_2-2_NBF_LDPC.py:151-153, 270), so
+ *     18 consecutive data frames share a W_out.
+ * The state of a CTA's 64 frames lives in `workspace` (esn_tcs_workspace_bytes)
+ * as UMMA-ready fp16 hi/lo tiles, double-buffered over time steps; the readout
+ * W_out[g(b)] [x; u] runs on the CUDA cores from fp32 tables built by
+ * esn_tcs_prepare_readout (wo_x: esn_tcs_readout_floats() floats per readout,
+ * wo_u: *wo_u_floats_host per readout).  The weight image is the one
+ * esn_tc_prepare_weights builds (it accepts N <= 4096).  n_in <= 24, n_out <= 16.
+ * accumulators (0 = automatic, 2 or 4): TMEM accumulators per 256-neuron pass -- the
+ * correction products and the main products of every (accumulators - 1)-th chunk are
+ * summed separately and added in fp32 RN by the epilogue, which keeps the tensor core's
+ * truncating accumulate chains short (2: two TMEM buffers, 4: one);
+ * ring_a / ring_b (0 = automatic): depths of the state / weight rings.
+ * ------------------------------------------------------------------------- */
+typedef struct esn_tcs_args {
+    int32_t B, T;
+    int32_t N, n_in, n_out;
+    int32_t transient;
+    int32_t feedback;
+    int32_t su_exp, sy_exp;     /* as esn_tc_predict_args */
+    int32_t n_groups;
+    int32_t accumulators, ring_a, ring_b;
+    double  noise_amp;
+    uint64_t seed;
+    const void *weights;        /* from esn_tc_prepare_weights (same su_exp, sy_exp) */
+    const float *wo_x;          /* [n_groups][esn_tcs_readout_floats] */
+    const float *wo_u;          /* [n_groups][wo_u floats] */
+    const float *in;            /* [B][T][n_in] raw inputs (fp32) */
+    const float *in_scale, *in_shift;   /* [n_in] */
+    const float *t_scale, *t_shift;     /* [n_out] */
+    const int32_t *group_ids;   /* [B] or null; any values in [0, n_groups) (clamped) */
+    const float *x0;            /* [B][N] or null */
+    const float *y0;            /* [B][n_out] (scaled domain) or null */
+    const float *noise_uniforms;/* [B][steps][N] or null (device counter stream) */
+    float *ext_out;             /* [B][T][N+n_in] or null (required in harvest mode) */
+    float *y_out;               /* [B][T-transient][n_out] (predict mode) */
+    const float *teacher;       /* harvest mode: [B][T][n_out] raw teachers, else null */
+    void *workspace;            /* esn_tcs_workspace_bytes(B, N) bytes */
+    void *timeline;             /* profiling aid: [steps][2] int64 SM-clock stamps, or null */
+} esn_tcs_args;
+
+int esn_tcs_supported(int N, int n_in, int n_out);
+long long esn_tcs_workspace_bytes(int B, int N);
+long long esn_tcs_readout_floats(int N, int n_out, long long *wo_u_floats_host);
+int esn_tcs_prepare_readout(const double *W_out, int N, int n_in, int n_out, int n_groups, float *wo_x,
+                            float *wo_u, void *stream);
+int esn_tcs_run(const esn_tcs_args *args_host, void *stream);
+
+/* ---------------------------------------------------------------------------
  * Readout training.  Replaces np.linalg.pinv + dot of ESN.fit
  * (libs/pyESN.py:189-192) by fp64 normal equations with lambda = 0:
  *   rows m = T - transient, cols p = N + n_in, E = ext[b, transient:, :]
