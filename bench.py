@@ -491,6 +491,7 @@ def run_gpu(args):
     h_out = torch.empty((B, CFG["N_sub"], CFG["N_t"]), dtype=torch.uint8).pin_memory()
     d_in = [torch.empty_like(frames), torch.empty_like(frames)]
     copy_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    d2h_stream = torch.cuda.Stream(device=dev)
     ready = [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(2)]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
     half = B // 2
@@ -511,7 +512,10 @@ def run_gpu(args):
                 stream.wait_event(ev_)
             idx = step(d_in[buf])
             consumed[buf].record(stream)
-            h_out.copy_(idx, non_blocking=True)
+            d2h_stream.wait_stream(stream)                     # the result leaves on its own stream: the next step's
+            with torch.cuda.stream(d2h_stream):                # kernels do not queue behind the 19 MB device-to-host copy
+                h_out.copy_(idx, non_blocking=True)
+            idx.record_stream(d2h_stream)
 
     for e_ in consumed:
         e_.record(stream)
@@ -536,6 +540,7 @@ def run_gpu(args):
     e0, e1 = ev(), ev()
     e0.record(stream)
     e2e_loop(args.steps)
+    stream.wait_stream(d2h_stream)                              # the last result has arrived on the host
     e1.record(stream)
     torch.cuda.synchronize()
     D.barrier()

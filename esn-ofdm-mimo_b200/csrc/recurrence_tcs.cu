@@ -40,9 +40,13 @@
 
 namespace {
 
-constexpr int TCS_THREADS = 640;
-constexpr int TCS_MAXA = 4, TCS_MAXB = 10, TCS_MAXPASS = 16;
+constexpr int TCS_THREADS = 672;           // 21 warps (80 registers per thread: the register file is split over four schedulers)
+constexpr int TCS_MAXA = 4, TCS_MAXB = 6, TCS_MAXPASS = 16;
 constexpr int ATILE = 2 * STILE;           // ring-A item: hi | lo tile of one 64-neuron state chunk (16 KB)
+constexpr int BSLOT = 2 * SLOT;            // ring-B item: hi | lo weight tile of one (slab, chunk) (32 KB, ONE bulk copy:
+                                           // a bulk-copy request costs its issuing thread ~680 cycles whatever its size,
+                                           // profiles/r2_tma_stream_probe.txt)
+constexpr int WSTAGE_SLOTS = 3;            // readouts staged per epilogue warp and pass (32 frames of 18-frame blocks: <= 3)
 
 struct TcsParams {
     int B, T, N, n_in, n_out, transient, feedback, su, sy, n_groups;
@@ -58,7 +62,7 @@ struct TcsParams {
     const float *teacher;
     unsigned char *state;                  // [CTA][2][Cx][ATILE]
     int steps, row0;
-    long long *timeline;                   // [steps][2] SM-clock stamps of the issuer of CTA 0, or null
+    long long *timeline;                   // [steps][16] SM-clock stamps of CTA 0 (issuer 0-8, epilogue warp 9-14, frame warp 15), or null
 };
 
 // fp64 W_out [G][n_out][N + n_in] -> fp32 tables of the CUDA-core readout
@@ -111,7 +115,7 @@ __device__ __forceinline__ void tcs_block32(const TcsParams &p, const uint32_t (
             if (RO) {
                 const float4 *w4 = reinterpret_cast<const float4 *>(wo + (size_t)(jj >> 1) * (2 * NOP));
 #pragma unroll
-                for (int q = 0; q < NOP / 2; ++q) wv[q] = __ldg(w4 + q);
+                for (int q = 0; q < NOP / 2; ++q) wv[q] = w4[q];        // staged in shared memory (or global: generic load)
             }
             const uint64_t z = mul2(pk2u(v[jj], v[jj + 1]), dsc2);
             const uint64_t z2 = mul2(z, z);
@@ -178,9 +182,15 @@ __device__ __forceinline__ void tcs_block32(const TcsParams &p, const uint32_t (
 
 __device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
-// Warps (640 threads): 0-1 frame warps (thread = frame: inputs, feedback, readout assembly), 2 producer,
-// 3 MMA issuer (CTA 0), 4-19 epilogue (quadrant q = warp & 3: TMEM lanes 32 q ..; cq = (warp - 4) >> 2:
-// columns 32 cq .. of every group).
+// Warps (672 threads): 0-1 frame warps (thread = frame: inputs, feedback, readout assembly), 2 weight producer
+// (ring B), 3 MMA issuer (CTA 0), 4-19 epilogue (quadrant q = warp & 3: TMEM lanes 32 q ..; cq = (warp - 4) >> 2:
+// columns 32 cq .. of every group), 20 state producer (ring A).  One producer thread per ring because a bulk-copy
+// request occupies its issuing thread for ~680 cycles on an idle SM whatever its size
+// (profiles/r2_tma_stream_probe.txt): one thread cannot feed one chunk (776 cycles of MMAs) with two requests.
+// (Measured and dropped: two threads per ring -- 1.67 K instead of 1.49 K cycles per chunk; the readout as a second
+// sweep after the state is published -- the aug chunk of the next step then waits for y.  What bounds a chunk is
+// shared-memory bandwidth: 48 KB of bulk-copy writes plus 72 KB of operand reads by its twelve MMAs = 940 cycles
+// at 128 B/cycle, next to the epilogue's own traffic.)
 template <bool DBG, int NOP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TCS_THREADS, 1)
 esn_predict_tcs(const TcsParams p, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x) {
@@ -193,7 +203,8 @@ esn_predict_tcs(const TcsParams p, const __grid_constant__ CUtensorMap map_w, co
     const int C = gm.C, Cx = p.Cx, NG = p.NG, NP = p.NG, nacc = p.nacc, nbuf = p.nbuf;
     unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     unsigned char *aug = base, *ringA = base + ATILE, *ringB = ringA + (size_t)p.nA * ATILE;
-    float *ypart = reinterpret_cast<float *>(ringB + (size_t)p.nB * SLOT);          // [8][NOP][64]
+    float *ypart = reinterpret_cast<float *>(ringB + (size_t)p.nB * BSLOT);         // [8][NOP][64]
+    unsigned char *wstage = reinterpret_cast<unsigned char *>(ypart) + (size_t)8 * NOP * FT * sizeof(float);   // [16 warps][3][1 KB] (NOP == 8)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
@@ -264,6 +275,7 @@ esn_predict_tcs(const TcsParams p, const __grid_constant__ CUtensorMap map_w, co
         const float su = ldexpf(1.0f, p.su), sy = ldexpf(1.0f, p.sy);
         const int g = (live && p.group_ids) ? min(max(p.group_ids[b], 0), p.n_groups - 1) : 0;
         const float *wu = harvest ? nullptr : p.wo_u + (size_t)g * NOP * 24;
+        int tl_it = -1;                   // step whose feedback is being published (timeline stamps)
         float cur[24], nxt[24];           // u_it, u_{it+1}: scaled inputs (reference units)
 #pragma unroll
         for (int j = 0; j < 24; ++j) { cur[j] = 0.f; nxt[j] = 0.f; }
@@ -298,6 +310,7 @@ esn_predict_tcs(const TcsParams p, const __grid_constant__ CUtensorMap map_w, co
             fence_async_smem();
             __syncwarp();
             if (lane == 0) arrive0(&bar_aug, r_aug);
+            if (p.timeline && blockIdx.x == 0 && tid == 0 && tl_it >= 0) p.timeline[tl_it * 16 + 15] = clock64();
         };
         float y[16];
 #pragma unroll
@@ -351,6 +364,7 @@ esn_predict_tcs(const TcsParams p, const __grid_constant__ CUtensorMap map_w, co
                     y[o] = (o < p.n_out) ? fmaf(s, inv_xs, y[o]) : 0.f;
                 }
                 if (it + 1 < nst) {                                   // feedback first: the issuer will wait for it
+                    tl_it = it;
                     float yf[16];
 #pragma unroll
                     for (int o = 0; o < 16; ++o) yf[o] = (p.feedback && o < NOP) ? y[o] : 0.f;
@@ -365,44 +379,47 @@ esn_predict_tcs(const TcsParams p, const __grid_constant__ CUtensorMap map_w, co
             }
         }
     } else if (warp == 2) {
-        // ============ producer: this CTA's state chunks (ring A) and weight tiles (ring B) ============
+        // ============ weight producers: this CTA's slab of every pass, hi | lo tile of a chunk in ONE 32 KB copy ============
         if (elect_one()) {
-            const uint32_t ringA_s = smem_u32(ringA), ringB_s = smem_u32(ringB);
-            uint32_t r_fullA[TCS_MAXA], r_fullB[TCS_MAXB];
-#pragma unroll
-            for (int i = 0; i < TCS_MAXA; ++i) r_fullA[i] = mapa_u32(smem_u32(&fullA[i]), 0);
+            const uint32_t ringB_s = smem_u32(ringB);
+            uint32_t r_fullB[TCS_MAXB];
 #pragma unroll
             for (int i = 0; i < TCS_MAXB; ++i) r_fullB[i] = mapa_u32(smem_u32(&fullB[i]), 0);
-            uint32_t itemA = 0, itemB = 0;
-            int slotA = 0, slotB = 0;
-            auto fetchA = [&](int buf, int c) {
-                mbar_wait<false>(&emptyA[slotA], ((itemA / p.nA) & 1) ^ 1);
-                if (rank == 0) mbar_expect_tx(&fullA[slotA], 2u * ATILE);
-                tma2_g2s(ringA_s + (uint32_t)slotA * ATILE, &map_x, 0, xrow_cta + (buf * Cx + c) * (ATILE / 512), r_fullA[slotA]);
-                ++itemA;
-                if (++slotA == p.nA) slotA = 0;
-            };
-            auto fetchB = [&](int s, int c, int h) {
-                mbar_wait<false>(&emptyB[slotB], ((itemB / p.nB) & 1) ^ 1);
-                if (rank == 0) mbar_expect_tx(&fullB[slotB], 2u * SLOT);
-                tma2_g2s(ringB_s + (uint32_t)slotB * SLOT, &map_w, 0, ((s * C + c) * 2 + h) * (SLOT / 512), r_fullB[slotB]);
-                ++itemB;
-                if (++slotB == p.nB) slotB = 0;
-            };
-            for (int it = 0; it < nst; ++it) {
-                const int rb = (it + 1) & 1;                           // buffer that holds x_{it-1}
+            uint32_t itemB = 0;
+            int slotB = 0;
+            for (int it = 0; it < nst; ++it)
                 for (int ps = 0; ps < NP; ++ps) {
                     const int slab = 2 * ps + (int)rank;
+                    for (int c = 0; c <= Cx; ++c) {                  // state chunks, then the aug chunk
+                        mbar_wait<false>(&emptyB[slotB], ((itemB / p.nB) & 1) ^ 1);
+                        if (rank == 0) mbar_expect_tx(&fullB[slotB], 2u * BSLOT);
+                        tma2_g2s(ringB_s + (uint32_t)slotB * BSLOT, &map_w, 0, ((slab * C + c) * 2) * (SLOT / 512), r_fullB[slotB]);
+                        ++itemB;
+                        if (++slotB == p.nB) slotB = 0;
+                    }
+                }
+        }
+    } else if (warp == 20) {
+        // ============ state producers: this CTA's state chunks of x_{it-1}, once per pass ============
+        if (elect_one()) {
+            const uint32_t ringA_s = smem_u32(ringA);
+            uint32_t r_fullA[TCS_MAXA];
+#pragma unroll
+            for (int i = 0; i < TCS_MAXA; ++i) r_fullA[i] = mapa_u32(smem_u32(&fullA[i]), 0);
+            uint32_t itemA = 0;
+            int slotA = 0;
+            for (int it = 0; it < nst; ++it) {
+                const int rb = (it + 1) & 1;                           // buffer that holds x_{it-1}
+                for (int ps = 0; ps < NP; ++ps)
                     for (int c = 0; c < Cx; ++c) {
                         // chunk c was written by the epilogue of pass c / 4 of the previous step
                         if (ps == 0 && it > 0 && (c & 3) == 0) mbar_wait<false>(&bar_xready[c >> 2], (it - 1) & 1);
-                        fetchA(rb, c);
-                        fetchB(slab, c, 0);
-                        fetchB(slab, c, 1);
+                        mbar_wait<false>(&emptyA[slotA], ((itemA / p.nA) & 1) ^ 1);
+                        if (rank == 0) mbar_expect_tx(&fullA[slotA], 2u * ATILE);
+                        tma2_g2s(ringA_s + (uint32_t)slotA * ATILE, &map_x, 0, xrow_cta + (rb * Cx + c) * (ATILE / 512), r_fullA[slotA]);
+                        ++itemA;
+                        if (++slotA == p.nA) slotA = 0;
                     }
-                    fetchB(slab, Cx, 0);
-                    fetchB(slab, Cx, 1);
-                }
             }
         }
     } else if (warp == 3 && rank == 1) {
@@ -416,40 +433,43 @@ esn_predict_tcs(const TcsParams p, const __grid_constant__ CUtensorMap map_w, co
             const int ku = (gm.UW + 15) / 16, ky = gm.YO / 16;
             uint32_t itemA = 0, itemB = 0;
             int slotA = 0, slotB = 0, s = 0;
-            // one state chunk (descriptor low word a_hi) against the pass's slab pair: two ring-B items.  Main
+            // one state chunk (descriptor low word a_hi) against the pass's slab pair: one ring-B item [hi | lo].  Main
             // products hi*hi -> accumulator dm, corrections lo*hi and hi*lo -> accumulator dc.
+            long long *trace = nullptr;                               // per-chunk stamps of one step (profiling aid)
+            int tr_i = 0;
             auto chunk_items = [&](uint32_t a_hi, uint32_t dm, uint32_t dc, bool first_main, bool first_corr, bool is_aug) {
                 const int ks = is_aug ? ku + 1 : 4;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    mbar_wait<false>(&fullB[slotB], (itemB / p.nB) & 1);
-                    tc_fence_after();
-                    const uint32_t w = ringB0 + slotB * (SLOT >> 4);
+                mbar_wait<false>(&fullB[slotB], (itemB / p.nB) & 1);
+                if (trace && tr_i < 64) trace[tr_i * 4 + 2] = clock64();
+                tc_fence_after();
+                const uint32_t w = ringB0 + slotB * (BSLOT >> 4), wl = w + (SLOT >> 4);
 #pragma unroll 4
-                    for (int kk = 0; kk < ks; ++kk) {
-                        const uint32_t ko = (uint32_t)((is_aug && kk == ku) ? ky : kk) * 2;
-                        if (h == 0) {
-                            umma2_f16(dm, a_hi + ko, w + ko, idesc, (first_main && kk == 0) ? 0u : 1u);
-                            umma2_f16(dc, a_hi + lod + ko, w + ko, idesc, (first_corr && kk == 0) ? 0u : 1u);
-                        } else {
-                            umma2_f16(dc, a_hi + ko, w + ko, idesc, 1u);
-                        }
-                    }
-                    umma2_commit_pair(&emptyB[slotB]);
-                    ++itemB;
-                    if (++slotB == p.nB) slotB = 0;
+                for (int kk = 0; kk < ks; ++kk) {
+                    const uint32_t ko = (uint32_t)((is_aug && kk == ku) ? ky : kk) * 2;
+                    umma2_f16(dm, a_hi + ko, w + ko, idesc, (first_main && kk == 0) ? 0u : 1u);
+                    umma2_f16(dc, a_hi + lod + ko, w + ko, idesc, (first_corr && kk == 0) ? 0u : 1u);
+                    umma2_f16(dc, a_hi + ko, wl + ko, idesc, 1u);
                 }
+                umma2_commit_pair(&emptyB[slotB]);
+                if (trace && tr_i < 64) { trace[tr_i * 4 + 3] = clock64(); ++tr_i; }
+                ++itemB;
+                if (++slotB == p.nB) slotB = 0;
             };
             const int nmain = nacc - 1;
             for (int it = 0; it < nst; ++it) {
-                if (p.timeline) p.timeline[it * 2] = clock64();
+                if (p.timeline) p.timeline[it * 16] = clock64();
+                trace = (p.timeline && it == 200) ? p.timeline + (size_t)nst * 16 : nullptr;
+                tr_i = 0;
                 for (int ps = 0; ps < NP; ++ps, ++s) {
                     const int buf = nbuf == 2 ? (s & 1) : 0, use = nbuf == 2 ? (s >> 1) : s;
                     const uint32_t dbase = tmem + buf * nacc * 128, dc = dbase + nmain * 128;
                     mbar_wait_cluster<false>(&bar_tfree[buf], use & 1);          // both CTAs have drained this TMEM buffer
                     tc_fence_after();
+                    if (p.timeline && ps < 2) p.timeline[it * 16 + 1 + 4 * ps] = clock64();
                     for (int c = 0; c < Cx; ++c) {
+                        if (trace && tr_i < 64) trace[tr_i * 4] = clock64();
                         mbar_wait<false>(&fullA[slotA], (itemA / p.nA) & 1);
+                        if (trace && tr_i < 64) trace[tr_i * 4 + 1] = clock64();
                         tc_fence_after();
                         const uint32_t a = ringA0 + slotA * (ATILE >> 4);
                         chunk_items(a, dbase + (c % nmain) * 128, dc, c < nmain, c == 0, false);
@@ -457,18 +477,20 @@ esn_predict_tcs(const TcsParams p, const __grid_constant__ CUtensorMap map_w, co
                         ++itemA;
                         if (++slotA == p.nA) slotA = 0;
                     }
+                    if (p.timeline && ps < 2) p.timeline[it * 16 + 2 + 4 * ps] = clock64();
                     if (ps == 0) {
-                        if (p.timeline) p.timeline[it * 2 + 1] = clock64();
                         mbar_wait_cluster<false>(&bar_aug, it & 1);              // [u_it | y_{it-1}] is in place in both CTAs
                         tc_fence_after();
+                        if (p.timeline) p.timeline[it * 16 + 3] = clock64();
                     }
                     chunk_items(aug0, dbase + (Cx % nmain) * 128, dc, false, false, true);
                     umma2_commit_pair(&bar_pass[buf]);
+                    if (p.timeline && ps < 2) p.timeline[it * 16 + 4 + 4 * ps] = clock64();
                 }
                 if (harvest) umma2_commit_pair(&bar_step);
             }
         }
-    } else {
+    } else if (warp >= 4 && warp < 20) {
         // ============ epilogue: TMEM -> tanh -> noise -> fp16 hi/lo -> next state image; readout shares ============
         const int e = warp - 4, q = warp & 3, cq = e >> 2, hl = q >> 1;
         const int f = 32 * (q & 1) + lane, b = tile0 + f;
@@ -478,6 +500,24 @@ esn_predict_tcs(const TcsParams p, const __grid_constant__ CUtensorMap map_w, co
         const int g = (live && p.group_ids) ? min(max(p.group_ids[b], 0), p.n_groups - 1) : 0;
         const float *wo_g = harvest ? nullptr : p.wo_x + (size_t)g * N_pad * NOP;
         const size_t frow = (size_t)(f >> 3) * 1024 + fx * 128;
+        // The readout rows this warp needs in a pass -- [32 neurons][NOP outputs] of each distinct readout among its 32
+        // frames, 1 KB per readout -- are staged in shared memory by cp.async while the warp waits for the pass's MMAs
+        // (from L2 they cost ~600 cycles per dependent batch: 11 K cycles per block instead of 3 K).
+        constexpr bool STAGE = NOP == 8;
+        int wslot = WSTAGE_SLOTS, nslots = 0, g_slot[WSTAGE_SLOTS] = {0, 0, 0};
+        unsigned char *wst = wstage + (size_t)e * WSTAGE_SLOTS * 1024;
+        if (STAGE && !harvest) {
+            const unsigned mm = __match_any_sync(0xffffffffu, g);
+            const int leader = __ffs(mm) - 1;
+            const unsigned leaders = __ballot_sync(0xffffffffu, lane == leader);
+            wslot = __popc(leaders & ((1u << leader) - 1));
+            nslots = min(__popc(leaders), WSTAGE_SLOTS);
+#pragma unroll
+            for (int sl = 0; sl < WSTAGE_SLOTS; ++sl) {
+                const unsigned src_lane = __fns(leaders, 0, sl + 1);
+                g_slot[sl] = __shfl_sync(0xffffffffu, g, src_lane & 31);
+            }
+        }
         TcsEpi es;
         es.dsc = ldexpf(1.0f, -(SX + SW));
         es.ampf = p.noise_amp * (float)(1 << SX);
@@ -502,9 +542,23 @@ esn_predict_tcs(const TcsParams p, const __grid_constant__ CUtensorMap map_w, co
             for (int o = 0; o < NOP; ++o) acc[o] = pk2(0.f, 0.f);
             for (int ps = 0; ps < NP; ++ps, ++s) {
                 const int buf = nbuf == 2 ? (s & 1) : 0, use = nbuf == 2 ? (s >> 1) : s;
+                const int n0 = 256 * ps + 128 * hl + 32 * cq;
+                if (STAGE && !harvest) {
+                    __syncwarp();                                      // the previous block's reads of the staging slots are done
+#pragma unroll
+                    for (int sl = 0; sl < WSTAGE_SLOTS; ++sl)
+                        if (sl < nslots) {
+                            const unsigned char *src = reinterpret_cast<const unsigned char *>(
+                                p.wo_x + (size_t)g_slot[sl] * N_pad * NOP + (size_t)(n0 >> 1) * (2 * NOP));
+                            cp_async16(wst + sl * 1024 + lane * 16, src + lane * 16);
+                            cp_async16(wst + sl * 1024 + 512 + lane * 16, src + 512 + lane * 16);
+                        }
+                    cp_async_commit();
+                }
                 mbar_wait<true>(&bar_pass[buf], use & 1);
                 tc_fence_after();
-                const int n0 = 256 * ps + 128 * hl + 32 * cq;
+                const bool st4 = p.timeline && blockIdx.x == 0 && warp == 4 && lane == 0 && ps < 2;
+                if (st4) p.timeline[it * 16 + 9 + 3 * ps] = clock64();
                 uint32_t v[32];
                 {
                     // the pass's partial sums (main accumulators, then the corrections), added in fp32 RN
@@ -522,12 +576,18 @@ esn_predict_tcs(const TcsParams p, const __grid_constant__ CUtensorMap map_w, co
                 tc_fence_before();                                     // this warp is done with the TMEM buffer
                 __syncwarp();
                 if (lane == 0) arrive0(&bar_tfree[buf], r_tfree[buf]);
+                if (st4) p.timeline[it * 16 + 10 + 3 * ps] = clock64();
                 float m = 0.f;
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) m = fmaxf(m, fmaxf(fabsf(__uint_as_float(v[i])), fabsf(__uint_as_float(v[i + 1]))));
                 const bool big = __any_sync(0xffffffffu, m * es.dsc > 3.0f);
                 unsigned char *grow = nbuf_ptr + (size_t)(n0 >> 6) * ATILE + frow;
                 const float *wo = harvest ? nullptr : wo_g + (size_t)(n0 >> 1) * (2 * NOP);
+                if (STAGE && !harvest) {
+                    cp_async_wait<0>();
+                    __syncwarp();
+                    if (wslot < WSTAGE_SLOTS) wo = reinterpret_cast<const float *>(wst + wslot * 1024);
+                }
                 if (harvest) {
                     if (n0 + 32 <= p.N && !big) tcs_block32<DBG, false, false, NOP, false>(p, v, it, n0, b, live, grow, fx, P, es, wo, acc);
                     else tcs_block32<DBG, true, true, NOP, false>(p, v, it, n0, b, live, grow, fx, P, es, wo, acc);
@@ -535,10 +595,11 @@ esn_predict_tcs(const TcsParams p, const __grid_constant__ CUtensorMap map_w, co
                     if (n0 + 32 <= p.N && !big) tcs_block32<DBG, false, false, NOP, true>(p, v, it, n0, b, live, grow, fx, P, es, wo, acc);
                     else tcs_block32<DBG, true, true, NOP, true>(p, v, it, n0, b, live, grow, fx, P, es, wo, acc);
                 }
-                // publish the chunks of this pass: generic stores -> visible to the producer's tensor-map copies
+                // publish the chunks of this pass: generic stores -> visible to the producers' tensor-map copies
                 fence_async_global();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_xready[ps]);
+                if (st4) p.timeline[it * 16 + 11 + 3 * ps] = clock64();
             }
             if (!harvest) {
 #pragma unroll
@@ -625,14 +686,15 @@ extern "C" int esn_tcs_run(const esn_tcs_args *a, void *stream) {
     p.timeline = (long long *)a->timeline;
     // shared memory: aug tile + rings + readout partial sums, as deep as 227 KB allow
     const size_t ypart = (size_t)8 * g.NOP * FT * sizeof(float);
-    const size_t budget = 227 * 1024 - 3072 - 1024 - ATILE - ypart;
+    const size_t wstage = g.NOP == 8 ? (size_t)16 * WSTAGE_SLOTS * 1024 : 0;
+    const size_t budget = 227 * 1024 - 1024 - 1024 - ATILE - ypart - wstage;
     p.nA = a->ring_a > 0 ? std::min(a->ring_a, TCS_MAXA) : 3;
-    int nb = (int)((budget - (size_t)p.nA * ATILE) / SLOT);
+    int nb = (int)((budget - (size_t)p.nA * ATILE) / BSLOT);
     nb = std::min(nb, TCS_MAXB);
     if (a->ring_b > 0) nb = std::min(nb, a->ring_b);
     if (nb < 2) return ESN_E_TOOLARGE;
     p.nB = nb;
-    const size_t smem = 1024 + ATILE + (size_t)p.nA * ATILE + (size_t)p.nB * SLOT + ypart;
+    const size_t smem = 1024 + ATILE + (size_t)p.nA * ATILE + (size_t)p.nB * BSLOT + ypart + wstage;
     const int grid = 2 * ((a->B + 2 * FT - 1) / (2 * FT));
     typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -645,17 +707,17 @@ extern "C" int esn_tcs_run(const esn_tcs_args *a, void *stream) {
         if (!fn || qres != cudaDriverEntryPointSuccess) return ESN_E_UNSUPPORTED;
         encode = (encode_fn)fn;
     }
-    auto make_map = [&](CUtensorMap *m, const void *base, size_t bytes) -> bool {
+    auto make_map = [&](CUtensorMap *m, const void *base, size_t bytes, unsigned box_bytes) -> bool {
         const cuuint64_t dims[2] = {256, (cuuint64_t)(bytes / 512)};
         const cuuint64_t strides[1] = {512};
-        const cuuint32_t box[2] = {256, SLOT / 512}, estr[2] = {1, 1};
+        const cuuint32_t box[2] = {256, box_bytes / 512}, estr[2] = {1, 1};
         return encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void *>(base), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     };
     CUtensorMap map_w, map_x;
-    if (!make_map(&map_w, a->weights, gm.weight_bytes)) return ESN_E_BADARG;
-    if (!make_map(&map_x, a->workspace, (size_t)grid * 2 * g.Cx * ATILE)) return ESN_E_BADARG;
+    if (!make_map(&map_w, a->weights, gm.weight_bytes, BSLOT)) return ESN_E_BADARG;
+    if (!make_map(&map_x, a->workspace, (size_t)grid * 2 * g.Cx * ATILE, ATILE)) return ESN_E_BADARG;
     const bool dbg = a->noise_uniforms || a->ext_out;
     auto launch = [&](auto kern) -> int {
         ESN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -541,8 +541,11 @@ class Reservoir:
     # streaming SIMT kernels cost one wave per ~48-300 frames: below AUTO_TC_MIN_FRAMES[N_pad] frames the SIMT
     # side is faster AND more accurate (4e-7 vs 9e-6 state error).  Table measured by profiles/crossover.py
     # (profiles/r2_crossover.txt, with the ncu counters of both sides at the boundary).
-    AUTO_TC_MIN_FRAMES = {256: 512, 512: 128}
-    AUTO_TCS_MIN_FRAMES = 64              # reservoirs above 512 neurons: streamed tensor-core kernel vs streaming SIMT
+    # (largest N, first batch size at which the tensor-core launch beats the cluster / streaming SIMT kernels):
+    # measured 1.30 ms per ~290-frame wave vs 3.3 ms at 100 neurons, 1.77 ms per ~96 frames vs 6.5 ms at 300,
+    # 2.55 ms per 48 frames vs 6.1 ms at 512 (profiles/r2_crossover.txt)
+    AUTO_TC_MIN_FRAMES = ((128, 640), (256, 448), (384, 320), (512, 100))
+    AUTO_TCS_MIN_FRAMES = 1               # above 512 neurons the streaming SIMT kernel never wins (92 ms vs 32 ms at 1024)
 
     def auto_predict_path(self, B, group_ids=None):
         """'tc' (resident tensor-core kernel), 'tcs' (streamed-state tensor-core kernel) or 'fp32' (cluster kernel
@@ -551,8 +554,8 @@ class Reservoir:
             return "fp32"
         if self.N > 512:
             return "tcs" if B >= self.AUTO_TCS_MIN_FRAMES else "fp32"
-        n_pad = 256 if self.N <= 256 else 512
-        if B < self.AUTO_TC_MIN_FRAMES[n_pad]:
+        b_min = next(b for n, b in self.AUTO_TC_MIN_FRAMES if self.N <= n)
+        if B < b_min:
             return "fp32"
         return "tc" if self._tc_resident_ok(None, group_ids) else "tcs"
 
@@ -563,19 +566,21 @@ class Reservoir:
             return False
         if group_ids is None:
             return True
-        tiles = torch.as_tensor(group_ids).reshape(-1)
-        key = (tiles.data_ptr(), tiles.numel(), getattr(tiles, "_version", 0)) if tiles.is_cuda else None
+        # the answer for a device tensor costs a sync: remembered per tensor OBJECT (weak reference + version counter)
         cache = getattr(self, "_tile_ok_cache", None)
-        if key is not None and cache is not None and cache[0] == key:
-            return cache[1]
+        if (isinstance(group_ids, torch.Tensor) and cache is not None and cache[0]() is group_ids
+                and cache[1] == group_ids._version):
+            return cache[2]
+        tiles = torch.as_tensor(group_ids).reshape(-1)
         tile = self.tc_tile_frames()
         pad = (-tiles.numel()) % tile
         if pad:
             tiles = torch.cat([tiles, tiles[-1:].expand(pad)])
         tiles = tiles.view(-1, tile)
         ok = bool((tiles == tiles[:, :1]).all())
-        if key is not None:
-            self._tile_ok_cache = (key, ok)
+        if isinstance(group_ids, torch.Tensor):
+            import weakref
+            self._tile_ok_cache = (weakref.ref(group_ids), group_ids._version, ok)
         return ok
 
     # -------------------------------------------------------------- readout --

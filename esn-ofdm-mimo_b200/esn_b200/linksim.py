@@ -19,6 +19,9 @@ from . import dist as D
 from . import ofdm
 
 DETECTORS = ("ESN", "Perfect_ZF", "LS_ZF", "MMSE")
+# the template's second ESN: trained on the pilot re-sent at a FIXED Eb/N0 (12 dB in the demos), applied to the
+# data symbols of the actual Eb/N0 (OFDM_MIMO_2-2_NBF_LDPC.py:182-183, 240-241, 346-367, 440-448)
+DETECTORS_TRAIN_FIXED = DETECTORS + ("ESN_trainFixed",)
 
 
 def isi_profile(isi, device):
@@ -85,9 +88,20 @@ def _side_stream(dev):
     return _SIDE[key]
 
 
+def channel_frequency_response(taps, N):
+    """H_true[g, k, nr, nt] = sum_t taps[g, nr, nt, t] exp(-2 pi i k t / N) (OFDM_MIMO_2-2_NBF_LDPC.py:281-285) through
+    the repo's own FFT kernel: the taps of every link are laid out as a zero-padded frame column."""
+    G, N_r, N_t, isi = taps.shape
+    col = torch.zeros((G, N, N_r * N_t), dtype=torch.complex128, device=taps.device)
+    col[:, :isi, :] = taps.to(torch.complex128).permute(0, 3, 1, 2).reshape(G, isi, N_r * N_t)
+    H = ofdm.rx_fft(col, N, 0) * N                     # rx_fft carries the 1/N of the receiver side (:428)
+    return H.reshape(G, N, N_r, N_t)
+
+
 def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_bits, isi=8, No=1e-5,
                   clip_db=3.0, delay=None, fit_precision="fp64", detect_precision="fp32", seed=0,
-                  noise_pilot=None, noise_data=None, state_noise_seed=1):
+                  noise_pilot=None, noise_data=None, state_noise_seed=1, train_fixed_ebno_db=None,
+                  noise_pilot_fixed=None):
     """One SNR point on this rank's blocks.
 
     res             Reservoir with n_inputs = 2 N_r, n_outputs = 2 N_t (input_scaling as the template:
@@ -96,6 +110,9 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
     data_idx        [B, N, N_t] uint8 data symbol indices, block_of_frame [B] int32 in [0, G)
     taps            [G, N_r, N_t, isi] complex channel taps
     noise_*         optional standard-normal complex noise [G or B, N+cp, N_r] (else the device stream)
+    train_fixed_ebno_db  if set, the template's second ESN is trained as well (pilot re-sent at this Eb/N0 through
+                    the same channel with fresh noise, input scaling 0.005 / sqrt(var_x of THAT Eb/N0)) and detects the
+                    same data symbols: counters under "ESN_trainFixed"
     Returns {detector: int64 tensor [bit errors, bits]} and the extras used by the tests.
     """
     dev = pil_idx.device
@@ -116,10 +133,12 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
     # block) is latency-bound and leaves most SMs idle; everything that does not depend on the readouts -- data
     # frame synthesis, the channel estimates and the three comparison detectors -- runs beside it on a side stream
     # and joins the main stream before the ESN detects (esn_in) and at the end (the counters).
-    if detect_precision == "tc":                        # checked first, while nothing is queued: a host sync here is free
-        per_ = B // G
-        if not (B == G * per_ and bool((block_of_frame.view(G, per_) == torch.arange(G, device=dev, dtype=block_of_frame.dtype)[:, None]).all())):
-            raise ValueError("tensor-core detect needs block-contiguous frames, the same number per block")
+    if detect_precision in ("tc", "auto"):              # decided first, while nothing is queued: a host sync here is free
+        # resident tensor-core kernel when every readout owns whole aligned tiles, else (blocks of 18 frames as in the
+        # demos, reservoirs above 512 neurons) the streamed-state kernel, which takes any frame -> readout map;
+        # 'auto' falls back to the cluster / SIMT kernels for small batches
+        detect_precision = res.auto_predict_path(B, block_of_frame) if detect_precision == "auto" else \
+            ("tc" if res._tc_resident_ok(None, block_of_frame) else "tcs")
     main = torch.cuda.current_stream(dev)
     side = _side_stream(dev)
     side.wait_stream(main)
@@ -131,7 +150,20 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
     teacher[:, delay:, :] = torch.view_as_real(pil["x_cp"]).reshape(G, N + cp, 2 * N_t)
     ext = res.harvest(pil["esn_in"].to(rd), teacher.to(rd), precision=fit_precision, seed=state_noise_seed)
     W_out, info = res.train_readout(ext, teacher, transient)
-    dd = torch.float32 if detect_precision in ("fp32", "tc") else torch.float64
+    dd = torch.float32 if detect_precision in ("fp32", "tc", "tcs") else torch.float64
+    W_out_f = res_f = None
+    if train_fixed_ebno_db is not None:
+        Pi_f = 10 ** (train_fixed_ebno_db / 10) * No
+        var_x_f = Pi_f * N
+        pil_f = ofdm.synth_frames(pil_idx, taps, Pi_f, math.sqrt(var_x_f) * 10 ** (clip_db / 20), N, cp, qam_bits, std,
+                                  delay=delay, noise=noise_pilot_fixed, seed=seed + 2, dtype=torch.float64, want_x_cp=True)
+        teacher_f = torch.zeros((G, N + cp + delay, 2 * N_t), dtype=torch.float64, device=dev)
+        teacher_f[:, delay:, :] = torch.view_as_real(pil_f["x_cp"]).reshape(G, N + cp, 2 * N_t)
+        res_f = res.rescaled(input_scaling=res._aff[1]["in_scale"] * math.sqrt(var_x / var_x_f))
+        ext_f = res_f.harvest(pil_f["esn_in"].to(rd), teacher_f.to(rd), precision=fit_precision, seed=state_noise_seed + 2)
+        W_out_f, info_f = res_f.train_readout(ext_f, teacher_f, transient)
+        info = torch.maximum(info.abs(), info_f.abs())
+        del ext_f, pil_f
     out = {}
     with torch.cuda.stream(side):
         fr = ofdm.synth_frames(data_idx, taps.to(torch.complex64 if dd == torch.float32 else torch.complex128), Pi, A_clip,
@@ -149,7 +181,7 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
                            const[pil_idx.long()])
         Y_LS = ofdm.rx_fft(ls["y_cp"], N, cp)
         H_LS, H_MMSE = ofdm.chanest(Y_LS, X_LS, Pi, isi_profile(isi, dev), isi, No)
-        H_true = torch.fft.fft(taps.to(torch.complex128), n=N, dim=3).permute(0, 3, 1, 2).contiguous()   # [G,N,N_r,N_t]
+        H_true = channel_frequency_response(taps, N)                                                   # [G,N,N_r,N_t]
         Y = ofdm.rx_fft(fr["y_cp"], N, cp)
         cd = Y.dtype
         for name, H, reg in (("Perfect_ZF", H_true, 1e-12), ("LS_ZF", H_LS, 1e-12), ("MMSE", H_MMSE, No / Pi)):
@@ -161,30 +193,21 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
     # ---- data symbols
     main.wait_event(frames_ready)
     fr["esn_in"].record_stream(main)
-    esn_in, gids, pick = fr["esn_in"], block_of_frame, None
-    if detect_precision == "tc":
-        # the tensor-core kernel wants one readout per 128-frame tile: lay every block out on whole tiles
-        # (the filler frames are zeros and are dropped again before the FFT / slicer)
-        tile = res.tc_tile_frames()
-        per = B // G
-        if per % tile:
-            padded = -(-per // tile) * tile
-            pick = (torch.arange(G, device=dev)[:, None] * padded + torch.arange(per, device=dev)[None, :]).reshape(-1)
-            big = torch.zeros((G * padded,) + tuple(esn_in.shape[1:]), dtype=esn_in.dtype, device=dev)
-            big[pick] = esn_in
-            esn_in = big
-            gids = (torch.arange(G * padded, device=dev) // padded).to(torch.int32)
-    if detect_precision == "tc":                        # layout checked above: straight to the kernel, no host sync
-        y = res.predict_tc(esn_in, res.tc_prepare(W_out, su_exp), transient=transient, group_ids=gids,
-                           seed=state_noise_seed + 1)
-    else:
-        y = res.predict(esn_in, W_out, transient=transient, group_ids=gids, precision=detect_precision,
-                        seed=state_noise_seed + 1)
-    if pick is not None:
-        y = y[pick].contiguous()
+    esn_in, gids = fr["esn_in"], block_of_frame
     total = B * N * N_t * qam_bits
-    _, _, c = ofdm.unpack_fft_demap(y, N, N_t, Pi, qam_bits, tx_idx=data_idx, want_xhat=False, want_idx=False)
-    out["ESN"] = c
+
+    def esn_detect(r, W, sd):
+        if detect_precision == "tc":                    # layout checked above: straight to the kernel, no host sync
+            su = su_exp if r is res else r.input_scale_exponent(esn_in)      # (the second reservoir scales its inputs differently)
+            y = r.predict_tc(esn_in, r.tc_prepare(W, su), transient=transient, group_ids=gids, seed=sd)
+        elif detect_precision == "tcs":
+            y = r.predict_tcs(esn_in, r.tcs_prepare(W), transient=transient, group_ids=gids, seed=sd)
+        else:
+            y = r.predict(esn_in, W, transient=transient, group_ids=gids, precision=detect_precision, seed=sd)
+        return ofdm.unpack_fft_demap(y, N, N_t, Pi, qam_bits, tx_idx=data_idx, want_xhat=False, want_idx=False)[2]
+    out["ESN"] = esn_detect(res, W_out, state_noise_seed + 1)
+    if W_out_f is not None:
+        out["ESN_trainFixed"] = esn_detect(res_f, W_out_f, state_noise_seed + 3)
     if int(info.abs().max()) != 0:                      # after the detect is queued: the check costs no GPU idle time
         raise np.linalg.LinAlgError("readout training failed for block %d" % int(torch.nonzero(info)[0]))
     main.wait_stream(side)
@@ -193,12 +216,14 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
     tot_t = torch.full((), total, dtype=torch.int64, device=dev)
     res_ = {k: torch.stack([v[0], tot_t.to(v.dtype)]) for k, v in out.items()}
     res_["_W_out"], res_["_delay"], res_["_transient"] = W_out, delay, transient
+    if W_out_f is not None:
+        res_["_W_out_trainFixed"] = W_out_f
     return res_
 
 
 def ber_curve(res_factory, N_t, N_r, N, qam_bits, ebno_db_list, n_blocks, frames_per_block, isi=8, No=1e-5, seed=0,
               fit_precision="fp64", detect_precision="tc", device=None, channel="rayleigh", fs_hz=2 * 1.024e6,
-              ds_ns=300.0, shard=True, max_blocks_per_launch=148):
+              ds_ns=300.0, shard=True, max_blocks_per_launch=148, train_fixed_ebno_db=None):
     """BER-vs-SNR Monte-Carlo: for every Eb/N0, `n_blocks` coherence blocks of `frames_per_block` data
     symbols (blocks sharded over ranks, counters summed over ranks).  `res_factory(var_x)` returns the
     Reservoir for an SNR point (the template scales the inputs by 0.005 / sqrt(var_x)).  Returns
@@ -215,11 +240,12 @@ def ber_curve(res_factory, N_t, N_r, N, qam_bits, ebno_db_list, n_blocks, frames
     g0, g1 = D.shard_range(n_blocks, rank, world)
     G = g1 - g0
     gen = torch.Generator(device=device)
-    curves = {k: [] for k in DETECTORS}
+    dets = DETECTORS_TRAIN_FIXED if train_fixed_ebno_db is not None else DETECTORS
+    curves = {k: [] for k in dets}
     all_counts = []
     for si, ebno in enumerate(ebno_db_list):
         gen.manual_seed(seed * 100003 + si * 1009 + rank)
-        counts = torch.zeros((len(DETECTORS), 2), dtype=torch.int64, device=device)
+        counts = torch.zeros((len(dets), 2), dtype=torch.int64, device=device)
         res = res_factory(10 ** (ebno / 10) * No * N) if G > 0 else None
         for ci, c0 in enumerate(range(0, G, max(1, int(max_blocks_per_launch)))):
             Gc = min(int(max_blocks_per_launch), G - c0)
@@ -237,13 +263,14 @@ def ber_curve(res_factory, N_t, N_r, N, qam_bits, ebno_db_list, n_blocks, frames
             r = detect_blocks(res, pil_idx, data_idx, blk, taps, ebno, N, qam_bits, isi=isi, No=No,
                               fit_precision=fit_precision, detect_precision=detect_precision,
                               seed=seed * 7919 + si * 31 + rank * 3 + 11 + ci * 104729,
-                              state_noise_seed=seed + 17 * si + rank + ci * 7907)
-            for di, k in enumerate(DETECTORS):
+                              state_noise_seed=seed + 17 * si + rank + ci * 7907,
+                              train_fixed_ebno_db=train_fixed_ebno_db)
+            for di, k in enumerate(dets):
                 counts[di] += r[k]
         if shard:
             D.allreduce_sum_(counts)
         all_counts.append(counts)
-        for di, k in enumerate(DETECTORS):
+        for di, k in enumerate(dets):
             curves[k].append(float(counts[di, 0]) / max(1, int(counts[di, 1])))
     curves["EBN0"] = [int(e) if float(e).is_integer() else float(e) for e in ebno_db_list]
     curves["_counts"] = torch.stack(all_counts)

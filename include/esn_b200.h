@@ -224,7 +224,7 @@ typedef struct esn_tcs_args {
     float *y_out;               /* [B][T-transient][n_out] (predict mode) */
     const float *teacher;       /* harvest mode: [B][T][n_out] raw teachers, else null */
     void *workspace;            /* esn_tcs_workspace_bytes(B, N) bytes */
-    void *timeline;             /* profiling aid: [steps][2] int64 SM-clock stamps, or null */
+    void *timeline;             /* profiling aid: [steps][16] int64 SM-clock stamps of CTA 0, or null */
 } esn_tcs_args;
 
 int esn_tcs_supported(int N, int n_in, int n_out);

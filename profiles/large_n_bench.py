@@ -46,9 +46,9 @@ for N in (512, 600, 1024, 2048):
             flop = B * T * (2 * N * (N + ni + no) + 2 * no * (N + ni))
             extra = ""
             if name == "tcs":
-                tl = torch.zeros((T, 2), dtype=torch.int64, device="cuda")
+                tl = torch.zeros((T * 16 + 256,), dtype=torch.int64, device="cuda")
                 res.predict_tcs(us[:128], rd, transient=10, group_ids=gid[:128], seed=3, timeline=tl)
                 torch.cuda.synchronize()
-                st = tl[:, 0].cpu().numpy()
+                st = tl[:T * 16].view(T, 16)[:, 0].cpu().numpy()
                 extra = "  %.1f K cycles/step alone" % (np.median(np.diff(st[50:])) / 1e3)
             print(f"N={N:5d} B={B:5d} {name:5s}: {best:9.2f} ms  {B / best * 1e3:10.0f} sym/s  {flop / best / 1e9:7.2f} TFLOP/s{extra}")

@@ -114,3 +114,35 @@ def test_tcs_widest_io_continuation_and_tuning_knobs():
                            **{**aff, "teacher_forcing": False})
         fb = max(fb, rel_err(nofb, ref))
     assert fb > 1e-2
+
+
+def test_auto_path_is_never_far_from_the_best_explicit_path():
+    """precision='auto' (Reservoir.auto_predict_path) against every explicit path on a batch x reservoir grid:
+    it must not lose more than 10 % (+ 0.2 ms of timer slack) to the fastest one."""
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best
+    T = 200
+    rows = []
+    for n_res, n_in, n_out in ((100, 4, 4), (512, 16, 8), (1024, 16, 8)):
+        rng, Ws, aff, eng = _setup(n_res, n_in, n_out, seed=1, noise=0.001, in_scale=0.005)
+        Wo = _cuda(rng.randn(1, n_out, n_res + n_in) * 1e-6)
+        for B in (8, 64, 256, 1024, 4096):
+            u = torch.randn(B, T, n_in, device="cuda")
+            t = {"fp32": timed(lambda: eng.predict(u, Wo, transient=10, precision="fp32", seed=1)),
+                 "tcs": timed(lambda: eng.predict(u, Wo, transient=10, precision="tcs", seed=1))}
+            if eng.tc_supported():
+                t["tc"] = timed(lambda: eng.predict(u, Wo, transient=10, precision="tc", seed=1))
+            auto = eng.auto_predict_path(B, None)
+            rows.append((n_res, B, auto, t))
+            assert t[auto] <= 1.1 * min(t.values()) + 0.2, (n_res, B, auto, t)
+    print("auto path:", [(n, b, a) for n, b, a, _ in rows])
