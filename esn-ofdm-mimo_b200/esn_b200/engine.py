@@ -39,7 +39,10 @@ def dtype_code(precision):
 
 
 def _vec(v, n, default, device):
-    """None / scalar / length-n vector -> fp64 device vector of length n."""
+    """None / scalar / length-n vector (numpy or torch, any device) -> fp64 device vector of length n."""
+    if isinstance(v, torch.Tensor):
+        t = v.detach().to(device=device, dtype=torch.float64).reshape(-1)
+        return (t.expand(n) if t.numel() == 1 else t.reshape(n)).contiguous()
     if v is None:
         a = np.full(n, default, dtype=np.float64)
     else:

@@ -32,7 +32,9 @@ def main():
     ap.add_argument("--blocks", type=int, default=74)
     ap.add_argument("--frames-per-block", type=int, default=128)
     ap.add_argument("--fit-precision", default="fp64", choices=["fp64", "fp32", "tc"])
-    ap.add_argument("--detect-precision", default="tc", choices=["tc", "fp32", "fp64"])
+    ap.add_argument("--detect-precision", default="tc", choices=["tc", "auto", "fp32", "fp64"])
+    ap.add_argument("--train-fixed-ebno", type=float, default=None,
+                    help="also train the template's second ESN on the pilot re-sent at this Eb/N0 (12 dB in the demos)")
     ap.add_argument("--channel", default="rayleigh", choices=["rayleigh", "tdlb"],
                     help="rayleigh: exponential 8-tap profile of the NBF template; tdlb: TDL-B taps of the CDL demo")
     ap.add_argument("--blocks-per-launch", type=int, default=148,
@@ -67,7 +69,8 @@ def main():
     t0 = time.time()
     c = linksim.ber_curve(factory, a.nt, a.nr, a.nsub, a.qam_bits, ebno, a.blocks, a.frames_per_block,
                           seed=a.seed, fit_precision=a.fit_precision, detect_precision=a.detect_precision,
-                          channel=a.channel, max_blocks_per_launch=a.blocks_per_launch)
+                          channel=a.channel, max_blocks_per_launch=a.blocks_per_launch,
+                          train_fixed_ebno_db=a.train_fixed_ebno)
     torch.cuda.synchronize()
     dt = time.time() - t0
     if rank == 0:
@@ -77,11 +80,11 @@ def main():
                 "NumOfdmSymbols": a.blocks * (a.frames_per_block + 1),
                 "esn": {"n_reservoir": a.nres, "spectral_radius": 0.9, "input_scaler": 0.005, "teacher_scaling_base": 5e-7},
                 "channel": {"model": "CDL-B (TDL-equivalent)" if a.channel == "tdlb" else "block-fading Rayleigh, 8 taps, exponential profile"},
-                "all_detectors": {k: c[k] for k in linksim.DETECTORS}, "gpus": world, "seconds": dt}
+                "all_detectors": {k: c[k] for k in c if not k.startswith("_") and k != "EBN0"}, "gpus": world, "seconds": dt}
         results.write_results_pkl(os.path.join(a.out, "results_ber.pkl"),
                                   results.results_bundle(c["EBN0"], c["ESN"], c["MMSE"], meta=meta))
         frames = len(ebno) * a.blocks * a.frames_per_block
-        print(json.dumps({"ebno": c["EBN0"], **{k: [round(v, 5) for v in c[k]] for k in linksim.DETECTORS},
+        print(json.dumps({"ebno": c["EBN0"], **{k: [round(v, 5) for v in c[k]] for k in c if not k.startswith("_") and k != "EBN0"},
                           "frames": frames, "seconds": round(dt, 2), "gpus": world}))
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -10,7 +10,8 @@ Whole configurations are placed on ranks (largest first, esn_b200.dist.assign_by
 data-path collective -- one allreduce at the end gathers the error counters.  The host-side weight
 initialisation (pyESN.initweights order, libs/pyESN.py:93-109; the eigenvalue solve costs 3.5 s at
 2048 neurons) of the next configuration runs on a host thread while the GPU works on the current one.
-Reservoirs up to 512 neurons detect on the tensor cores, larger ones on the fp32 streaming kernel.
+Every size detects on the tensor cores: up to 512 neurons on the kernel that keeps the state in shared memory,
+larger reservoirs (600, 1024, 2048) on the streamed-state kernel (esn_predict_tcs).
 """
 import argparse
 import concurrent.futures as cf
@@ -83,7 +84,7 @@ def main():
             t0 = time.time()
             c = linksim.ber_curve(factory, a.nt, a.nr, a.nsub, a.qam_bits, ebno, a.blocks, a.frames_per_block,
                                   seed=a.seed, fit_precision=a.fit_precision,
-                                  detect_precision="tc" if N <= 512 else "fp32", shard=False)
+                                  detect_precision="tc", shard=False)
             torch.cuda.synchronize()
             counts[i] = c["_counts"]
             secs[i] = time.time() - t0

@@ -577,6 +577,39 @@ def draw_channel(rng, N_r, N_t, isi_magnitude, isi_duration):
     return c
 
 
+# 3GPP TR 38.901 Table 7.7.2-2, TDL-B: normalised delays and powers [dB] (the table of the reference's CDL demo,
+# system_model_2/Demo_MIMO_4x8_Sionna_CDL_ESN_v2.py:127-137)
+TDLB_NORM_DELAYS = np.array([0.0000, 0.1072, 0.2155, 0.2095, 0.2870, 0.2986, 0.3752, 0.5055, 0.3681, 0.3697, 0.5700,
+                             0.5283, 1.1021, 1.2756, 1.5474, 1.7842, 2.0169, 2.8294, 3.0219, 3.6187, 4.1067, 4.2790, 4.7834])
+TDLB_POW_DB = np.array([0.0, -2.2, -4.0, -3.2, -9.8, -1.2, -3.4, -5.2, -7.6, -3.0, -8.9, -9.0, -4.8, -5.7, -7.5, -1.9,
+                        -7.6, -12.2, -9.8, -11.4, -14.9, -9.2, -11.3])
+
+
+def draw_channel_tdlb(rng, N_r, N_t, isi_duration, fs_hz=2 * 1.024e6, ds_ns=300.0):
+    """`build_cdlb_mimo_taps` / `_gen_cdlb_impulse` (Demo_MIMO_4x8_Sionna_CDL_ESN_v2.py:139-177): per link, every
+    TDL-B path gets a CN(0, p) gain, is split linearly between the two neighbouring sample taps, paths beyond
+    `isi_duration` taps are dropped and the link is normalised to unit energy.  `rng`: a RandomState (the demo uses
+    `default_rng`; the draw order per link -- re then im per path -- is the demo's)."""
+    p = 10.0 ** (TDLB_POW_DB / 10.0)
+    p = p / p.sum()
+    d = TDLB_NORM_DELAYS * ds_ns * 1e-9 * fs_hz
+    c = np.zeros((N_r, N_t, isi_duration), dtype=complex)
+    for nr in range(N_r):
+        for nt in range(N_t):
+            h = np.zeros(isi_duration, dtype=complex)
+            for k in range(len(d)):
+                i0 = int(np.floor(d[k]))
+                frac = d[k] - i0
+                g = (rng.standard_normal() + 1j * rng.standard_normal()) / np.sqrt(2.0) * np.sqrt(p[k])
+                if 0 <= i0 < isi_duration:
+                    h[i0] += g * (1.0 - frac)
+                if 0 <= i0 + 1 < isi_duration:
+                    h[i0 + 1] += g * frac
+            e = np.sum(np.abs(h) ** 2)
+            c[nr, nt] = h / np.sqrt(e) if e > 0 else h
+    return c
+
+
 def fir_causal(h, x):
     """`scipy.signal.lfilter(h, [1], x)` for an FIR h: causal convolution
     truncated to len(x), zero initial state (OFDM_MIMO_2-2_NBF_LDPC.py:305)."""
@@ -608,7 +641,7 @@ def channel_apply(rng, c, x_nld, No):
 
 
 def synth_block(seed, N, N_t, N_r, m, ebno_db, n_data, isi_duration=8, No=1e-5,
-                clip_db=3.0):
+                clip_db=3.0, channel="rayleigh"):
     """One coherence block of the block-fading template: a pilot frame plus
     `n_data` data frames through one channel draw (restates the generator of
     OFDM_MIMO_2-2_NBF_LDPC.py:270-312 and :387-426 with an explicit
@@ -621,7 +654,8 @@ def synth_block(seed, N, N_t, N_r, m, ebno_db, n_data, isi_duration=8, No=1e-5,
     var_x = 10 ** (ebno_db / 10) * No * N
     A_clip = math.sqrt(var_x) * 10 ** (clip_db / 20)
     mag = isi_profile(isi_duration)
-    c = draw_channel(rng, N_r, N_t, mag, isi_duration)
+    c = draw_channel_tdlb(rng, N_r, N_t, isi_duration) if channel == "tdlb" else \
+        draw_channel(rng, N_r, N_t, mag, isi_duration)
     H_true = np.fft.fft(np.concatenate(
         [c, np.zeros((N_r, N_t, N - isi_duration))], axis=2), axis=2).transpose(2, 0, 1)
 

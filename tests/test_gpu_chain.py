@@ -191,6 +191,10 @@ def test_linksim_block_loop_matches_oracle_loop():
     dat_idx = rng.randint(0, 16, size=(G * per, N, N_t))
     nz_p = rng.randn(G, N + cp, N_r) + 1j * rng.randn(G, N + cp, N_r)
     nz_d = rng.randn(G * per, N + cp, N_r) + 1j * rng.randn(G * per, N + cp, N_r)
+    nz_f = rng.randn(G, N + cp, N_r) + 1j * rng.randn(G, N + cp, N_r)      # fresh noise of the pilot re-sent at 12 dB
+    ebno_f = 12
+    Pi_f = 10 ** (ebno_f / 10) * No
+    var_x_f, A_f = Pi_f * N, math.sqrt(Pi_f * N) * 10 ** (3 / 20)
     blk = np.repeat(np.arange(G), per)
     kw = dict(n_inputs=2 * N_r, n_outputs=2 * N_t, n_reservoir=40, spectral_radius=0.9, sparsity=0.1,
               input_shift=np.zeros(2 * N_r), input_scaling=(0.005 / var_x ** 0.5) * np.ones(2 * N_r),
@@ -201,19 +205,26 @@ def test_linksim_block_loop_matches_oracle_loop():
     out = linksim.detect_blocks(res, _cuda(pil_idx.astype(np.uint8)), _cuda(dat_idx.astype(np.uint8)),
                                 _cuda(blk.astype(np.int32)), _cuda(taps), ebno, N, m, isi=isi, No=No,
                                 fit_precision="fp64", detect_precision="fp64", noise_pilot=_cuda(nz_p),
-                                noise_data=_cuda(nz_d))
+                                noise_data=_cuda(nz_d), train_fixed_ebno_db=ebno_f, noise_pilot_fixed=_cuda(nz_f))
+    # the same blocks through the tensor-core detect: 4 frames per block never fill a tile, so it runs on the
+    # streamed-state kernel with a readout per frame
+    out_tc = linksim.detect_blocks(res, _cuda(pil_idx.astype(np.uint8)), _cuda(dat_idx.astype(np.uint8)),
+                                   _cuda(blk.astype(np.int32)), _cuda(taps), ebno, N, m, isi=isi, No=No,
+                                   fit_precision="fp64", detect_precision="tc", noise_pilot=_cuda(nz_p),
+                                   noise_data=_cuda(nz_d), train_fixed_ebno_db=ebno_f, noise_pilot_fixed=_cuda(nz_f))
     # ---- the oracle's loop
     const = orc.unit_qam_constellation(m)
     maxd = int(math.ceil(isi / 2) + 2)
 
-    def rx(X, c, nz):
-        x_cp, x_nld = orc.tx_frame(X, N, cp, Pi, A)
+    def rx(X, c, nz, Pi_=Pi, A_=A):
+        x_cp, x_nld = orc.tx_frame(X, N, cp, Pi_, A_)
         y = np.zeros((N + cp, N_r), dtype=complex)
         for nr in range(N_r):
             for tx in range(N_t):
                 y[:, nr] += orc.fir_causal(c[nr, tx], x_nld[:, tx])
         return x_cp, y + std * nz
-    errs = dict(ESN=0, Perfect_ZF=0, LS_ZF=0, MMSE=0)
+    errs = dict(ESN=0, Perfect_ZF=0, LS_ZF=0, MMSE=0, ESN_trainFixed=0)
+    kw_f = dict(kw, input_scaling=(0.005 / var_x_f ** 0.5) * np.ones(2 * N_r))
     for g in range(G):
         Xp = const[pil_idx[g]]
         x_cp_p, y_p = rx(Xp, taps[g], nz_p[g])
@@ -228,21 +239,28 @@ def test_linksim_block_loop_matches_oracle_loop():
         d, nforget = int(r[6]), int(r[7])
         assert d == out["_delay"] and nforget == out["_transient"]
         assert rel_err(out["_W_out"][g].cpu().numpy(), esn.W_out) < 1e-6
+        # the second ESN of the template (:346-367): the same pilot re-sent at 12 dB, fresh noise, its own input scaling
+        x_cp_f, y_f = rx(Xp, taps[g], nz_f[g], Pi_f, A_f)
+        esn_f = orc.OracleESN(**kw_f)
+        orc.train_generic(esn_f, 0, 0, maxd, cp, N, N_t, N_r, isi, y_f, x_cp_f)
+        assert rel_err(out["_W_out_trainFixed"][g].cpu().numpy(), esn_f.W_out) < 1e-6
         for f in range(per):
             fi = g * per + f
             _, y = rx(const[dat_idx[fi]], taps[g], nz_d[fi])
             tb = orc.indices_to_bits(dat_idx[fi], m)
             Xe = orc.esn_output_to_freq(esn.predict(orc.pack_rx(y, d), nforget, continuation=False), N, N_t, Pi)
             Y = orc.rx_fft(y, cp, N)
-            cand = dict(ESN=Xe, Perfect_ZF=orc.equalize(Y, H_true, math.sqrt(Pi), 1e-12),
+            Xf = orc.esn_output_to_freq(esn_f.predict(orc.pack_rx(y, d), nforget, continuation=False), N, N_t, Pi)
+            cand = dict(ESN=Xe, ESN_trainFixed=Xf, Perfect_ZF=orc.equalize(Y, H_true, math.sqrt(Pi), 1e-12),
                         LS_ZF=orc.equalize(Y, H_LS, math.sqrt(Pi), 1e-12), MMSE=orc.equalize(Y, H_MM, math.sqrt(Pi), No / Pi))
             for k, X in cand.items():
                 errs[k] += int((orc.indices_to_bits(orc.hard_demap_indices(X, const), m) != tb).sum())
     total = G * per * N * N_t * m
-    for k in linksim.DETECTORS:
+    for k in linksim.DETECTORS_TRAIN_FIXED:
         assert int(out[k][1]) == total
         assert abs(int(out[k][0]) - errs[k]) <= 2, (k, int(out[k][0]), errs[k])
-    print("linksim errors", {k: int(out[k][0]) for k in linksim.DETECTORS}, "oracle", errs)
+        assert abs(int(out_tc[k][0]) - errs[k]) <= 6, (k, int(out_tc[k][0]), errs[k])
+    print("linksim errors", {k: int(out[k][0]) for k in linksim.DETECTORS_TRAIN_FIXED}, "oracle", errs)
 
 
 def test_linksim_ber_curve_runs_and_orders_detectors():
