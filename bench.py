@@ -697,6 +697,34 @@ def run_gpu(args):
                     "tensor-core kernel (a readout per frame, blocks packed back to back), fit pipelined as above"}
         del rd19, gid19
         del fu, fy
+    # ---- ONE readout trained on pilots spread over the ranks (BASELINE.json configs[4]: "readout Gram allreduced over
+    # NVLink"): every rank harvests its own pilots on the tensor cores in chunks; the partial normal equations of a
+    # chunk (2.2 MB fp64) are all-reduced asynchronously while the next chunk is harvested; every rank runs the same
+    # Cholesky.  Weak scaling: the pilots per rank are fixed.
+    shared = None
+    if args.shared_pilots > 0:
+        Gs = args.shared_pilots
+        reps = -(-Gs // G)
+        su_ = pil_u.to(torch.float32).repeat(reps, 1, 1)[:Gs].contiguous()
+        sy_ = pil_y.to(torch.float32).repeat(reps, 1, 1)[:Gs].contiguous()
+        res.train_shared_readout(su_, sy_, TRANSIENT, precision="tc", chunks=4, seed=5)
+        torch.cuda.synchronize()
+        D.barrier()
+        bests = None
+        for rep in range(3):
+            s0, s1 = ev(), ev()
+            s0.record(stream)
+            w_sh, info_sh, nbytes = res.train_shared_readout(su_, sy_, TRANSIENT, precision="tc", chunks=4, seed=6 + rep)
+            s1.record(stream)
+            torch.cuda.synchronize()
+            t = D.max_over_ranks(s0.elapsed_time(s1), dev)
+            bests = t if bests is None else min(bests, t)
+            assert int(info_sh.abs().max()) == 0
+        shared = {"pilots_per_gpu": Gs, "pilots_total": world * Gs, "ms": bests, "pilots_per_s": world * Gs / (bests * 1e-3),
+                  "allreduce_bytes_per_fit": int(nbytes), "chunks": 4,
+                  "what": "one W_out from all ranks' pilots: tensor-core harvest -> primal Gram 528 x 528 (DMMA, summed over "
+                          "the chunk's pilots) -> async NCCL all-reduce per chunk behind the next chunk's harvest -> Cholesky"}
+        del su_, sy_, w_sh
     dropin = None
     if world == 1 and not args.no_dropin:
         dropin = dropin_latency()
@@ -762,6 +790,7 @@ def run_gpu(args):
                      "algorithmic_flop_per_symbol": algorithmic_flops_per_symbol(),
                      "kernel_share_of_step": kms / (ms / args.steps)},
         "fit": fit,
+        "shared_readout": shared,
         "dropin": dropin,
         "cpu_baseline": cpu,
         "clocks": clk.summary(),
@@ -809,6 +838,8 @@ def main():
     ap.add_argument("--fit-precision", default="fp64", choices=["fp64", "fp32", "tc"],
                     help="harvest precision of the readouts the timed detection uses")
     ap.add_argument("--fit-pilots", type=int, default=1184, help="pilots per batch of the fit-throughput leg (0 = skip)")
+    ap.add_argument("--shared-pilots", type=int, default=592,
+                    help="pilots per GPU of the shared-readout leg (one W_out from all ranks' pilots, Gram all-reduced; 0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -76,6 +76,33 @@ def allreduce_gram_(G, R):
     return G, R
 
 
+class GramReducer:
+    """Shared-readout training over ranks with the collective hidden behind the harvest: the rank's pilots are
+    worked off in chunks; the partial normal equations [G | R] of chunk k (one flat fp64 buffer, 2.2 MB at cfg3) go
+    into an ASYNCHRONOUS all-reduce while chunk k + 1 is being harvested; `finish()` waits for the outstanding
+    works and adds the reduced partials.  Only the last chunk's all-reduce (tens of microseconds on NVSwitch) is
+    exposed.  Single process: no collective, the partials are just added."""
+
+    def __init__(self):
+        self.parts, self.works, self.bytes = [], [], 0
+
+    def add(self, flat):
+        """flat: this rank's partial [G | R] of one chunk (overwritten by the reduced sum)."""
+        self.parts.append(flat)
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            self.works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True))
+            self.bytes += flat.numel() * flat.element_size()
+
+    def finish(self):
+        for w in self.works:
+            w.wait()
+        total = self.parts[0]
+        for p in self.parts[1:]:
+            total += p
+        self.works = []
+        return total
+
+
 def barrier():
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()

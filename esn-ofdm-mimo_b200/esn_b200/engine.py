@@ -653,6 +653,42 @@ class Reservoir:
                                     int(transient), 0, 1, 0, ptr(G), ptr(rhs), _stream()), "esn_gram_f64")
         return G, rhs
 
+    def gram_flat(self, ext, teachers, transient=0):
+        """As `gram`, in ONE flat fp64 buffer [P*P + P*n_out] (what goes on the wire when the frames of a shared
+        readout are spread over ranks: dist.GramReducer).  Returns (flat, G view [1,P,P], R view [1,P,n_out])."""
+        B, T, P = ext.shape
+        teachers = teachers.to(self.device).contiguous()
+        aff = self._aff[ESN_F64]
+        flat = torch.empty((P * P + P * self.n_out,), dtype=torch.float64, device=self.device)
+        G, rhs = flat[:P * P].view(1, P, P), flat[P * P:].view(1, P, self.n_out)
+        check(self.lib.esn_gram_f64(ptr(ext), _CODE[ext.dtype], ptr(teachers), _CODE[teachers.dtype],
+                                    ptr(aff["t_scale"]), ptr(aff["t_shift"]), B, T, P, self.n_out,
+                                    int(transient), 0, 1, 0, ptr(G), ptr(rhs), _stream()), "esn_gram_f64")
+        return flat, G, rhs
+
+    def train_shared_readout(self, inputs, teachers, transient=0, precision="fp64", chunks=4, seed=0,
+                             noise_uniforms=None):
+        """ONE readout from this rank's pilots AND those of every other rank (BASELINE.json configs[4]: "readout Gram
+        allreduced over NVLink"): chunked harvest -> partial normal equations -> asynchronous all-reduce per chunk
+        (hidden behind the next chunk's harvest) -> the same Cholesky on every rank.  Returns (W_out [1,n_out,P],
+        info, bytes all-reduced)."""
+        from . import dist as D
+        B = inputs.shape[0]
+        red = D.GramReducer()
+        P = self.P
+        for k in range(chunks):
+            b0, b1 = D.shard_range(B, k, chunks)
+            if b1 <= b0:
+                continue
+            nu = None if noise_uniforms is None else noise_uniforms[b0:b1]
+            ext = self.harvest(inputs[b0:b1], teachers[b0:b1], precision=precision, noise_uniforms=nu, seed=seed + k)
+            flat, _, _ = self.gram_flat(ext, teachers[b0:b1], transient)
+            red.add(flat)
+            del ext
+        flat = red.finish()
+        W_out, info = self.solve_readout(flat[:P * P].view(1, P, P), flat[P * P:].view(1, P, self.n_out))
+        return W_out, info, red.bytes
+
     def solve_readout(self, G, rhs, ext_for_dual=None, transient=0):
         nprob, n, _ = G.shape
         info = torch.zeros((nprob,), dtype=torch.int32, device=self.device)

@@ -36,10 +36,9 @@ def main():
     y = (torch.randn((n_pil, T, no), generator=g, dtype=torch.float64) * 1e-2).to(dev)
     uni = torch.rand((n_pil, T - 1, N), generator=g, dtype=torch.float64).to(dev)
     b0, b1 = D.shard_range(n_pil, rank, world)
-    ext = res.harvest(u[b0:b1], y[b0:b1], precision="fp64", noise_uniforms=uni[b0:b1])
-    G, R = res.gram(ext, y[b0:b1], tr)
-    D.allreduce_gram_(G, R)                                    # NCCL: 2.2 MB + 33 KB, once per fit
-    W_shared, info = res.solve_readout(G, R)
+    # chunked: the all-reduce of a chunk's partial normal equations (2.2 MB + 33 KB) runs behind the next chunk's harvest
+    W_shared, info, nbytes = res.train_shared_readout(u[b0:b1], y[b0:b1], tr, precision="fp64", chunks=2,
+                                                      noise_uniforms=uni[b0:b1])
     ok = int(info.abs().max()) == 0
     ext_all = res.harvest(u, y, precision="fp64", noise_uniforms=uni)
     W_single, info1 = res.train_readout(ext_all, y, tr, shared=True)
@@ -48,7 +47,7 @@ def main():
     if world > 1:
         torch.distributed.all_reduce(errs, op=torch.distributed.ReduceOp.MAX)
     if rank == 0:
-        print(json.dumps({"gpus": world, "pilots": n_pil, "rel_err_vs_single_gpu": float(errs[0]), "cholesky_ok": ok,
+        print(json.dumps({"gpus": world, "pilots": n_pil, "rel_err_vs_single_gpu": float(errs[0]), "cholesky_ok": ok, "allreduce_bytes": int(nbytes),
                           "backend": torch.distributed.get_backend() if world > 1 else "none"}))
     assert ok and float(errs[0]) < 1e-9
     if world > 1:

@@ -286,13 +286,21 @@ def test_linksim_ber_curve_runs_and_orders_detectors():
 
 
 def test_cdl_demo_curve_matches_the_reference_published_results():
-    """The CDL demo's configuration (4x8, 128 subcarriers, 300 neurons, TDL-B taps, 16-QAM, L = 75) on the
-    device against the uncoded BERs the reference itself published for that script
-    (results/results_4x8_cdl_coded_uncoded/CDLB_run_01/results_ber.csv; 1000 OFDM symbols per point, i.e.
-    13 channel draws -- a noisy target, hence 15 %)."""
+    """The CDL demo's configuration (4x8, 128 subcarriers, 300 neurons, TDL-B taps, 16-QAM, L = 75) on the device
+    against (a) the float64 CPU oracle run on the same configuration with the same fixed reservoir (seed 42), 208
+    blocks per point (profiles/cdl_bias_oracle.py -> profiles/r2_cdl_bias_oracle.txt) and (b) the uncoded BERs the
+    reference published for that script (results/results_4x8_cdl_coded_uncoded/CDLB_run_01/results_ber.csv).
+
+    (a) is the parity statement and is held to the 3-sigma sampling interval of the two runs (different channel
+    draws): 0.005 absolute for the ESN, 0.003 for MMSE.  (b) is a noisy target: 1000 OFDM symbols are 13 channel
+    draws (standard deviation of a 13-block mean: 0.004), and the reference draws a NEW reservoir per block while
+    one fixed reservoir serves every block here -- the oracle shows that reservoir 42 sits 0.003..0.009 above the
+    fresh-reservoir mean at 12..30 dB (0.1969 vs 0.1909 at 18 dB).  Both effects together bound |device - published|
+    by 0.009 + 3 x 0.004."""
     from esn_b200 import Reservoir, linksim
-    published = {0: (0.39036279296875, 0.3196171875), 15: (0.20868408203125, 0.05450439453125),
-                 30: (0.15689892578125, 0.0189169921875)}          # EbNo -> (ESN_uncoded, MMSE_uncoded)
+    #        Eb/N0: (oracle ESN fixedW, oracle MMSE, published ESN, published MMSE)
+    table = {12: (0.2519, 0.0832, 0.24451416015625, 0.07861474609375), 18: (0.1969, 0.0362, 0.18600244140625, 0.03449072265625),
+             24: (0.1703, 0.0220, 0.15912158203125, 0.02187158203125), 30: (0.1629, 0.0184, 0.15689892578125, 0.0189169921875)}
     N, N_t, N_r, m, n_res = 128, 4, 8, 4, 300
     rng = np.random.RandomState(42)
     W, W_in, W_fb = orc.init_weights(rng, 2 * N_r, 2 * N_t, n_res, 0.9, 0.1)
@@ -300,13 +308,15 @@ def test_cdl_demo_curve_matches_the_reference_published_results():
     def factory(var_x):
         return Reservoir(W, W_in, W_fb, (0.005 / var_x ** 0.5) * np.ones(2 * N_r), np.zeros(2 * N_r),
                          5e-7 * np.ones(2 * N_t), np.zeros(2 * N_t), 0.001, True)
-    c = linksim.ber_curve(factory, N_t, N_r, N, m, sorted(published), n_blocks=148, frames_per_block=74, seed=1,
+    c = linksim.ber_curve(factory, N_t, N_r, N, m, sorted(table), n_blocks=296, frames_per_block=74, seed=1,
                           channel="tdlb", detect_precision="tc")
-    for i, e in enumerate(sorted(published)):
-        esn_ref, mmse_ref = published[e]
-        assert abs(c["ESN"][i] - esn_ref) < 0.15 * esn_ref, (e, c["ESN"][i], esn_ref)
-        assert abs(c["MMSE"][i] - mmse_ref) < 0.15 * mmse_ref, (e, c["MMSE"][i], mmse_ref)
     print("CDL demo curve", {k: [round(v, 4) for v in c[k]] for k in ("ESN", "MMSE")})
+    for i, e in enumerate(sorted(table)):
+        esn_orc, mmse_orc, esn_pub, mmse_pub = table[e]
+        assert abs(c["ESN"][i] - esn_orc) < 0.005, (e, c["ESN"][i], esn_orc)
+        assert abs(c["MMSE"][i] - mmse_orc) < 0.003, (e, c["MMSE"][i], mmse_orc)
+        assert abs(c["ESN"][i] - esn_pub) < 0.009 + 3 * 0.004, (e, c["ESN"][i], esn_pub)
+        assert abs(c["MMSE"][i] - mmse_pub) < 0.15 * mmse_pub + 0.002, (e, c["MMSE"][i], mmse_pub)
 
 
 def test_siso_demo_loop_matches_reference_counts():

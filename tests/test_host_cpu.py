@@ -179,6 +179,13 @@ def _gloo_worker(rank, world, port, tmp):
     d.allreduce_sum_(cnt)
     assert cnt.tolist() == [10 * sum(range(1, w + 1)), sum(range(w))]
     assert d.max_over_ranks(float(r), "cpu") == float(w - 1)
+    # chunked shared-readout reduction: async all-reduce per chunk, partials added at the end
+    red = d.GramReducer()
+    for k in range(3):
+        red.add(torch.full((7,), float(10 * rank + k), dtype=torch.float64))
+    tot = red.finish()
+    assert tot.tolist() == [float(sum(10 * r + k for r in range(w) for k in range(3)))] * 7
+    assert red.bytes == 3 * 7 * 8
     d.barrier()
     open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     torch.distributed.destroy_process_group()
