@@ -110,6 +110,7 @@ struct TcParams {
     const float *teacher;                    // pair kernel, harvest mode: [B][T][n_out] raw teachers fed back (or null)
     int n_groups;                            // readouts in `readouts` (group ids are clamped to it)
     int steps, row0;                         // recurrence steps and first input row: T, 0 (predict) / T-1, 1 (harvest)
+    float acc_gain;                          // 1 + (truncation bias of the tensor core's accumulate chain), see esn_tc_set_acc_k0
 };
 
 constexpr int PF = 2 * FT;             // frames per CTA pair
@@ -424,7 +425,7 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
                 tmem_ld_wait();
 #pragma unroll
                 for (int o = 0; o < 16; ++o) {
-                    y[o] = (__uint_as_float(yv[o]) + ut[o]) * ys;
+                    y[o] = fmaf(__uint_as_float(yv[o]), p.acc_gain, ut[o]) * ys;
                     if (it == 0) y[o] = (p.y0 && live && o < p.n_out) ? p.y0[(size_t)b * p.n_out + o] : 0.f;
                     if (o >= p.n_out) y[o] = 0.f;
                 }
@@ -478,10 +479,13 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
 #pragma unroll
             for (int i = 0; i < NST; ++i) r_full[i] = mapa_u32(smem_u32(&bar_full[i]), 0);
             uint32_t item = 0;
+            long long *ptrace = nullptr;                   // producer stamps of one step (profiling aid)
+            int ptr_i = 0;
             // weight tile (slab s, chunk c, half h) [+ in CTA 0 the readout rows of (c, h)] into the next slot
             auto fetch = [&](int s, int c, int h, bool y) {
                 const int slot = item % NST;
                 mbar_wait<false>(&bar_empty[slot], ((item / NST) & 1) ^ 1);
+                if (TL && ptrace && ptr_i < 64) ptrace[ptr_i * 4] = clock64();
                 const uint32_t dst = ring_s + (uint32_t)slot * SLOT2;
                 y = y && !harvest;
                 if (rank == 0) mbar_expect_tx(&bar_full[slot], 2u * SLOT + (y ? ybytes : 0u));
@@ -491,6 +495,7 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
                     if (dual)                                     // second readout: its 8 rows behind the first
                         tma2_g2s(dst + SLOT + 1024, &map_y, 0, yrow1 + (c * 2 + h) * (YTILE / 512), r_full[slot]);
                 }
+                if (TL && ptrace && ptr_i < 64) { ptrace[ptr_i * 4 + 1] = clock64(); ++ptr_i; }
                 ++item;
             };
             auto chunk = [&](int j, int c) {          // the two items (hi, lo) of slab 2j + r, chunk c
@@ -498,6 +503,7 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
             };
             for (int it = 0; it < n_it; ++it) {
                 const bool last = it == nst;
+                if (TL) { ptrace = (tl0 && it == 200) ? p.timeline + (size_t)(p.T + 1) * 8 : nullptr; ptr_i = 0; }
                 if (two && !last) { chunk(0, 0); chunk(0, 2); chunk(0, 1); chunk(0, 3); }
                 for (int c = 0; c < C - 1; ++c) chunk(J - 1, c);
                 if (last) break;
@@ -604,7 +610,7 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
         const uint32_t frow = smem_u32(st_hi) + (f >> 3) * 1024 + fx * 128;
         const bool st4 = tl0 && warp == 4 && lane == 0;
         EpiStep es;
-        es.dsc = ldexpf(1.0f, -(SX + SW));
+        es.dsc = ldexpf(1.0f, -(SX + SW)) * p.acc_gain;
         es.ampf = p.noise_amp * (float)(1 << SX);
         es.amp16s = es.ampf * (1.0f / 65536.0f);
         es.ampoffs = 0.5f * es.ampf;
@@ -698,6 +704,19 @@ esn_predict_tc2(const TcParams p, const __grid_constant__ CUtensorMap map_w, con
 
 }  // namespace
 
+// Truncation bias of the accumulate chain.  The tensor core adds every K = 16 product block to the fp32
+// accumulator with truncation (toward zero), so a chain of n MMAs into one accumulator comes out SHORT by
+// about n x k0 relative -- a systematic shrink of W x that the recurrence amplifies by ~1 / (1 - rho).  The
+// epilogues multiply the accumulators by 1 + n k0 (folded into the scale they apply anyway); k0 is calibrated
+// against the fp64 kernel (profiles/probes/tc_acc_bias.py).  n counts the MMAs that add non-zero products.
+static double g_acc_k0 = ESN_TC_ACC_K0_DEFAULT;
+extern "C" double esn_tc_set_acc_k0(double k0) {
+    const double prev = g_acc_k0;
+    g_acc_k0 = k0 < 0.0 ? ESN_TC_ACC_K0_DEFAULT : k0;
+    return prev;
+}
+extern "C" double esn_tc_acc_k0(void) { return g_acc_k0; }
+
 extern "C" int esn_tc_supported(int N, int n_in, int n_out) {
     return (N > 0 && N <= 512 && n_in > 0 && n_in <= 24 && n_out > 0 && n_out <= 16) ? 1 : 0;
 }
@@ -747,6 +766,7 @@ extern "C" int esn_tc_predict(const esn_tc_predict_args *a, void *stream) {
     p.steps = harvest ? a->T - 1 : a->T;
     p.row0 = harvest ? 1 : 0;
     const TcGeom gm = tc_geom(a->N, a->n_in);
+    p.acc_gain = (float)(1.0 + g_acc_k0 * 3.0 * ((a->N + 15) / 16 + (gm.UW + 15) / 16 + 1));   // hi*hi, lo*hi, hi*lo per k-step
     const bool dbg = a->noise_uniforms || a->ext_out;
     {
         // CTA-pair kernel (cta_group::2): 128 frames per 2-CTA cluster

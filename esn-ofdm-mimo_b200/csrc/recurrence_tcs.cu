@@ -62,6 +62,7 @@ struct TcsParams {
     const float *teacher;
     unsigned char *state;                  // [CTA][2][Cx][ATILE]
     int steps, row0;
+    float acc_gain;                        // 1 + truncation bias of a main accumulate chain (esn_tc_set_acc_k0)
     long long *timeline;                   // [steps][16] SM-clock stamps of CTA 0 (issuer 0-8, epilogue warp 9-14, frame warp 15), or null
 };
 
@@ -519,7 +520,7 @@ esn_predict_tcs(const TcsParams p, const __grid_constant__ CUtensorMap map_w, co
             }
         }
         TcsEpi es;
-        es.dsc = ldexpf(1.0f, -(SX + SW));
+        es.dsc = ldexpf(1.0f, -(SX + SW)) * p.acc_gain;
         es.ampf = p.noise_amp * (float)(1 << SX);
         es.amp16s = es.ampf * (1.0f / 65536.0f);
         es.ampoffs = 0.5f * es.ampf;
@@ -675,6 +676,8 @@ extern "C" int esn_tcs_run(const esn_tcs_args *a, void *stream) {
     p.nacc = a->accumulators == 2 || a->accumulators == 4 ? a->accumulators : (g.NG <= 3 ? 2 : 4);
     p.nbuf = 4 / p.nacc;
     if (p.NG > TCS_MAXPASS) return ESN_E_TOOLARGE;
+    // main products only (the corrections have their own accumulator, 2^-11 smaller): chains of 1 / (nacc - 1) of the k-steps
+    p.acc_gain = (float)(1.0 + esn_tc_acc_k0() * ((a->N + 15) / 16 + (gm.UW + 15) / 16 + 1) / (double)(p.nacc - 1));
     p.noise_amp = (float)a->noise_amp; p.seed = a->seed;
     p.wo_x = a->wo_x; p.wo_u = a->wo_u;
     p.in = a->in; p.in_scale = a->in_scale; p.in_shift = a->in_shift; p.t_scale = a->t_scale; p.t_shift = a->t_shift;

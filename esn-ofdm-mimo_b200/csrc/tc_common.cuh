@@ -17,6 +17,7 @@ constexpr int STILE = 8192;            // bytes per state tile: [64 rows x 64 k]
 constexpr int YTILE = 2048;            // bytes per readout tile: [16 rows x 64 k] fp16
 constexpr int SX = 8, SW = 8;          // power-of-two pre-scales of state and weights
 constexpr int TMEM_COLS = 512;
+#define ESN_TC_ACC_K0_DEFAULT 1.45e-8  // relative truncation loss per MMA of an accumulate chain (esn_tc_set_acc_k0; profiles/r2_tc_acc_bias.txt)
 
 struct TcGeom {
     int S, C, UW, YO, ca, kaug;        // slabs, 64-wide K chunks, input block width, y column offset, aug chunk, k-steps in aug chunk
@@ -160,6 +161,28 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (!done) {
+            if (SLEEP) __nanosleep(64);
+            if (spin > (1u << 24)) __trap();
+        }
+    }
+}
+// The same wait without acquire semantics.  ptxas follows every successful acquire.cluster wait by CCTL.IVALL, which
+// invalidates the SM's whole L1D: five times per time step in the issuer's SM, which a kernel whose other warps
+// read tables through L1 (the CUDA-core readout of esn_recur_tcr) cannot afford.  The issuing thread reads nothing
+// the arrivals publish: the arriving warps have fenced their shared-memory writes towards the async proxy
+// (fence.proxy.async) before they arrive, and the MMAs issued after the wait read them through that proxy, behind
+// tcgen05.fence::after_thread_sync.
+template <bool SLEEP>
+__device__ __forceinline__ void mbar_wait_cluster_relaxed(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.b32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (!done) {

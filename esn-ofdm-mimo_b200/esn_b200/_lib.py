@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libesn_b200.so")
+LIB_PATH = os.environ.get("ESN_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libesn_b200.so")   # override: kernel experiments
 
 ESN_F32, ESN_F64 = 0, 1
 MODE_HARVEST, MODE_PREDICT = 0, 1
@@ -83,11 +83,15 @@ SIGNATURES = {
     "esn_tc_prepare_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "esn_tc_prepare_readout": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "esn_tc_predict": (_i, [C.POINTER(TcPredictArgs), _vp]),
+    "esn_tc_set_acc_k0": (_d, [_d]),
+    "esn_tc_acc_k0": (_d, []),
     "esn_tcs_supported": (_i, [_i, _i, _i]),
     "esn_tcs_workspace_bytes": (C.c_longlong, [_i, _i]),
     "esn_tcs_readout_floats": (C.c_longlong, [_i, _i, C.POINTER(C.c_longlong)]),
     "esn_tcs_prepare_readout": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "esn_tcs_run": (_i, [C.POINTER(TcsArgs), _vp]),
+    "esn_tcr_supported": (_i, [_i, _i, _i]),
+    "esn_tcr_run": (_i, [C.POINTER(TcsArgs), _vp]),
     "esn_gram_f64": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "esn_cholesky_solve_f64": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "esn_cholesky_solve_piv_f64": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),

@@ -401,7 +401,10 @@ class Reservoir:
         return ws
 
     def _tcs_run(self, inputs, readout=None, teachers=None, transient=0, group_ids=None, x0=None, y0=None,
-                 noise_uniforms=None, seed=0, return_ext=False, y_absmax=None, tune=None, timeline=None):
+                 noise_uniforms=None, seed=0, return_ext=False, y_absmax=None, tune=None, timeline=None,
+                 resident=False, su_exp=None):
+        if resident and not self.tcr_supported():
+            raise EsnB200Error("resident tensor-core path needs N <= 512, n_inputs <= 16, n_outputs <= 8")
         if not self.tcs_supported():
             raise EsnB200Error("tensor-core path needs N <= 4096, n_inputs <= 24, n_outputs <= 16")
         inputs = self._as(inputs, torch.float32, 3)
@@ -420,7 +423,9 @@ class Reservoir:
             if "_y_absmax" not in a64:
                 a64["_y_absmax"] = float((a64["t_scale"].abs() * 4 + a64["t_shift"].abs()).max().item())
             y_absmax = a64["_y_absmax"]
-        su_exp, sy_exp = self.input_scale_exponent(inputs), self.output_scale_exponent(y_absmax)
+        # su_exp: the caller may pass the input pre-scale exponent (input_scale_exponent costs a device reduction + sync)
+        su_exp = self.input_scale_exponent(inputs) if su_exp is None else int(su_exp)
+        sy_exp = self.output_scale_exponent(y_absmax)
         a = _lib.TcsArgs()
         a.B, a.T, a.N, a.n_in, a.n_out = B, T, self.N, self.n_in, self.n_out
         a.transient, a.feedback = int(transient), int(self.teacher_forcing)
@@ -429,7 +434,7 @@ class Reservoir:
         if tune:
             a.accumulators, a.ring_a, a.ring_b = (int(tune.get(k, 0)) for k in ("accumulators", "ring_a", "ring_b"))
         weights = self._tc_weights(su_exp, sy_exp)
-        ws = self._tcs_workspace(B)
+        ws = None if resident else self._tcs_workspace(B)
         a.weights, a.inp, a.workspace = ptr(weights), ptr(inputs), ptr(ws)
         a.in_scale, a.in_shift = ptr(aff["in_scale"]), ptr(aff["in_shift"])
         a.t_scale, a.t_shift = ptr(aff["t_scale"]), ptr(aff["t_shift"])
@@ -464,18 +469,43 @@ class Reservoir:
             a.y_out = ptr(y)
         if timeline is not None:
             a.timeline = ptr(timeline)
-        check(self.lib.esn_tcs_run(C.byref(a), _stream()), "esn_tcs_run")
+        if resident:
+            check(self.lib.esn_tcr_run(C.byref(a), _stream()), "esn_tcr_run")
+        else:
+            check(self.lib.esn_tcs_run(C.byref(a), _stream()), "esn_tcs_run")
         return y, ext
 
+    def tcr_supported(self):
+        return bool(self.lib.esn_tcr_supported(self.N, self.n_in, self.n_out))
+
+    def predict_tcr(self, inputs, readout, transient=0, group_ids=None, x0=None, y0=None, noise_uniforms=None,
+                    seed=0, return_ext=False, y_absmax=None, timeline=None, su_exp=None):
+        """Free-running prediction on the tensor cores with the state resident in shared memory and the readout
+        on the CUDA cores in fp32: reservoirs of up to 512 neurons, n_inputs <= 16, n_outputs <= 8, one readout
+        per aligned run of 64 frames.  `readout`: W_out [G, n_out, P] or the handle from tcs_prepare."""
+        if not isinstance(readout, TcsReadout):
+            readout = self.tcs_prepare(readout)
+        if group_ids is not None and not self._tc_resident_ok(inputs, group_ids):
+            raise EsnB200Error("resident tensor-core path: each aligned run of 64 frames must share one readout "
+                               "(use predict_tcs / precision='tcs' for a free frame -> readout map)")
+        y, ext = self._tcs_run(inputs, readout=readout, transient=transient, group_ids=group_ids, x0=x0, y0=y0,
+                               noise_uniforms=noise_uniforms, seed=seed, return_ext=return_ext, y_absmax=y_absmax,
+                               timeline=timeline, resident=True, su_exp=su_exp)
+        return (y, ext) if return_ext else y
+
+    def harvest_tcr(self, inputs, teachers, noise_uniforms=None, seed=0):
+        """Teacher-forced harvesting with the resident tensor-core kernel (split accumulators)."""
+        return self._tcs_run(inputs, teachers=teachers, noise_uniforms=noise_uniforms, seed=seed, resident=True)[1]
+
     def predict_tcs(self, inputs, readout, transient=0, group_ids=None, x0=None, y0=None, noise_uniforms=None,
-                    seed=0, return_ext=False, y_absmax=None, tune=None, timeline=None):
+                    seed=0, return_ext=False, y_absmax=None, tune=None, timeline=None, su_exp=None):
         """Free-running prediction on the tensor cores with the state streamed through L2: any reservoir size up to
         4096 neurons, any frame -> readout map.  `readout`: W_out [G, n_out, P] or the handle from tcs_prepare."""
         if not isinstance(readout, TcsReadout):
             readout = self.tcs_prepare(readout)
         y, ext = self._tcs_run(inputs, readout=readout, transient=transient, group_ids=group_ids, x0=x0, y0=y0,
                                noise_uniforms=noise_uniforms, seed=seed, return_ext=return_ext, y_absmax=y_absmax,
-                               tune=tune, timeline=timeline)
+                               tune=tune, timeline=timeline, su_exp=su_exp)
         return (y, ext) if return_ext else y
 
     def harvest_tcs(self, inputs, teachers, noise_uniforms=None, seed=0, tune=None):
@@ -490,11 +520,17 @@ class Reservoir:
         if precision == "auto":
             precision = "fp64"
         if precision == "tc":
+            if self.tcr_supported():
+                return self.harvest_tcr(inputs, teachers, noise_uniforms=noise_uniforms, seed=seed)
             if not self.tc_supported():
                 return self.harvest_tcs(inputs, teachers, noise_uniforms=noise_uniforms, seed=seed)
             return self.harvest_tc(inputs, teachers, noise_uniforms=noise_uniforms, seed=seed)
+        if precision == "tc2":
+            return self.harvest_tc(inputs, teachers, noise_uniforms=noise_uniforms, seed=seed)
         if precision == "tcs":
             return self.harvest_tcs(inputs, teachers, noise_uniforms=noise_uniforms, seed=seed)
+        if precision == "tcr":
+            return self.harvest_tcr(inputs, teachers, noise_uniforms=noise_uniforms, seed=seed)
         ext, _ = self._run(MODE_HARVEST, dtype_code(precision), inputs, teachers=teachers,
                            noise_uniforms=noise_uniforms, seed=seed)
         return ext
@@ -505,7 +541,8 @@ class Reservoir:
         using readout W_out[group_ids[b]].  Returns y [B, T-transient, n_out]
         in teacher units (and E if return_ext).  precision: 'auto' (the fastest kernel for this batch, reservoir
         and readout layout: auto_predict_path), 'fp64' / 'fp32' (cluster or streaming SIMT kernels), 'tc' (tensor
-        cores: resident kernel, or the streamed-state kernel where that one cannot go), 'tcs'."""
+        cores: a resident kernel, or the streamed-state kernel where those cannot go), 'tcr' / 'tc2' / 'tcs' (one
+        tensor-core kernel explicitly)."""
         if precision == "auto":
             if isinstance(W_out, TcReadout):
                 precision = "tc"
@@ -514,23 +551,31 @@ class Reservoir:
             else:
                 B = inputs.shape[0] if getattr(inputs, "ndim", 3) == 3 else 1
                 precision = self.auto_predict_path(B, group_ids)
-        if precision == "tcs" or (precision == "tc" and not isinstance(W_out, TcReadout)
-                                  and not self._tc_resident_ok(inputs, group_ids)):
+        # 'tc': the resident kernel with the fp32 CUDA-core readout (esn_recur_tcr) where it can go -- at most 512
+        # neurons, 16 inputs, 8 outputs, one readout per aligned run of 64 frames -- else the first resident kernel
+        # (readout inside the MMA: wider I/O, throughput mode), else the streamed-state kernel.  'tc2' asks for
+        # the first resident kernel explicitly; a TcReadout handle (tc_prepare) implies it.
+        if precision == "tc" and isinstance(W_out, TcReadout):
+            precision = "tc2"
+        if precision == "tc" and isinstance(W_out, TcsReadout):
+            precision = "tcr" if (self.tcr_supported() and self._tc_resident_ok(inputs, group_ids)) else "tcs"
+        if precision == "tc":
+            if not self._tc_resident_ok(inputs, group_ids):
+                precision = "tcs"
+            else:
+                precision = "tcr" if self.tcr_supported() else "tc2"
+        if precision == "tcr":
+            return self.predict_tcr(inputs, W_out, transient=transient, group_ids=group_ids, x0=x0, y0=y0,
+                                    noise_uniforms=noise_uniforms, seed=seed, return_ext=return_ext)
+        if precision == "tcs":
             return self.predict_tcs(inputs, W_out, transient=transient, group_ids=group_ids, x0=x0, y0=y0,
                                     noise_uniforms=noise_uniforms, seed=seed, return_ext=return_ext)
-        if precision == "tc":
+        if precision == "tc2":
             inputs = self._as(inputs, torch.float32, 3)
             if not isinstance(W_out, TcReadout):
                 W_out = self.tc_prepare(W_out, self.input_scale_exponent(inputs))
-            if group_ids is not None:
-                tiles = torch.as_tensor(group_ids).to(self.device).reshape(-1)
-                tile = self.tc_tile_frames()
-                pad = (-tiles.numel()) % tile
-                if pad:
-                    tiles = torch.cat([tiles, tiles[-1:].expand(pad)])
-                tiles = tiles.view(-1, tile)
-                if not bool((tiles == tiles[:, :1]).all()):
-                    raise EsnB200Error(f"tensor-core path: each {tile}-frame tile must share one readout")
+            if group_ids is not None and not self._tc_resident_ok(inputs, group_ids):
+                raise EsnB200Error(f"tensor-core path: each {self.tc_tile_frames()}-frame tile must share one readout")
             return self.predict_tc(inputs, W_out, transient=transient, group_ids=group_ids, x0=x0, y0=y0,
                                    noise_uniforms=noise_uniforms, seed=seed, return_ext=return_ext)
         ext, y = self._run(MODE_PREDICT, dtype_code(precision), inputs, W_out=W_out,

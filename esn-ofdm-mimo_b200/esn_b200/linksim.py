@@ -199,7 +199,10 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
     def esn_detect(r, W, sd):
         if detect_precision == "tc":                    # layout checked above: straight to the kernel, no host sync
             su = su_exp if r is res else r.input_scale_exponent(esn_in)      # (the second reservoir scales its inputs differently)
-            y = r.predict_tc(esn_in, r.tc_prepare(W, su), transient=transient, group_ids=gids, seed=sd)
+            if r.tcr_supported():                       # fp32 readout on the CUDA cores
+                y = r.predict_tcr(esn_in, r.tcs_prepare(W), transient=transient, group_ids=gids, seed=sd, su_exp=su)   # (layout verdict cached per tensor)
+            else:
+                y = r.predict_tc(esn_in, r.tc_prepare(W, su), transient=transient, group_ids=gids, seed=sd)
         elif detect_precision == "tcs":
             y = r.predict_tcs(esn_in, r.tcs_prepare(W), transient=transient, group_ids=gids, seed=sd)
         else:

@@ -178,6 +178,15 @@ int esn_tc_prepare_readout(const double *W_out, int N, int n_in, int n_out, int 
                            void *image, float *yscale, void *stream);
 int esn_tc_predict(const esn_tc_predict_args *args_host, void *stream);
 
+/* Truncation-bias compensation of the tensor-core paths (esn_tc_predict, esn_tcs_run).  The tensor core adds each
+ * K = 16 product block to its fp32 accumulator with truncation toward zero, so a chain of n MMAs comes out short
+ * by about n x k0 relative; the recurrence amplifies that systematic shrink of W x (libs/pyESN.py:117-119) by
+ * ~1 / (1 - spectral radius).  The epilogues scale the accumulators by 1 + n k0.  k0 >= 0 sets the per-MMA loss
+ * (0 = no compensation), a negative value restores the calibrated default (profiles/r2_tc_acc_bias.txt).
+ * Returns the previous value.  esn_tc_acc_k0 reads it. */
+double esn_tc_set_acc_k0(double k0);
+double esn_tc_acc_k0(void);
+
 /* ---------------------------------------------------------------------------
  * Tensor-core recurrence with the state streamed through L2 ("tcs"): the same
  * reference lines and the same fp16 hi/lo arithmetic as esn_tc_predict
@@ -233,6 +242,15 @@ long long esn_tcs_readout_floats(int N, int n_out, long long *wo_u_floats_host);
 int esn_tcs_prepare_readout(const double *W_out, int N, int n_in, int n_out, int n_groups, float *wo_x,
                             float *wo_u, void *stream);
 int esn_tcs_run(const esn_tcs_args *args_host, void *stream);
+
+/* The same recurrence with the state RESIDENT in shared memory ("tcr", reservoirs of up to 512 neurons, n_in <= 16,
+ * n_out <= 8): the machine of esn_tc_predict (CTA pair, frames on M, weights streamed through a ring) with the
+ * readout on the CUDA cores in fp32 round-to-nearest and split accumulators.  Takes the argument block of
+ * esn_tcs_run; workspace, accumulators, ring_a and ring_b are ignored; timeline is [T + 33][8] int64.
+ * group_ids must be uniform over aligned runs of 64 frames (one readout per CTA; the readout of a run's FIRST
+ * frame is used). */
+int esn_tcr_supported(int N, int n_in, int n_out);
+int esn_tcr_run(const esn_tcs_args *args_host, void *stream);
 
 /* ---------------------------------------------------------------------------
  * Readout training.  Replaces np.linalg.pinv + dot of ESN.fit

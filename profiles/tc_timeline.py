@@ -15,7 +15,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "esn-ofdm-mimo_b200"))
 from esn_b200 import Reservoir  # noqa: E402
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 64
+TCR = "--tcr" in sys.argv          # the resident kernel with the CUDA-core readout (esn_recur_tcr) instead of esn_predict_tc2
+argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+B = int(argv[0]) if argv else 148 * 64
 N, ni, no, T = 512, 16, 8, 522
 rng = np.random.RandomState(42)
 W = rng.rand(N, N) - 0.5
@@ -24,11 +26,14 @@ W *= 0.9 / np.max(np.abs(np.linalg.eigvals(W)))
 res = Reservoir(W, rng.rand(N, ni) * 2 - 1, rng.rand(N, no) * 2 - 1, input_scaling=0.005 * np.ones(ni),
                 teacher_scaling=5e-7 * np.ones(no), noise=0.001)
 x = torch.randn(B, T, ni, device="cuda")
-rd = res.tc_prepare(torch.randn(1, no, N + ni, dtype=torch.float64, device="cuda") * 1e-6,
-                    res.input_scale_exponent(x))
+Wo = torch.randn(1, no, N + ni, dtype=torch.float64, device="cuda") * 1e-6
+rd = res.tcs_prepare(Wo) if TCR else res.tc_prepare(Wo, res.input_scale_exponent(x))
 tl = torch.zeros(T + 1 + 32, 8, dtype=torch.int64, device="cuda")   # + per-item trace of step 200
 for _ in range(2):
-    res.predict_tc(x, rd, transient=10, timeline=tl)
+    if TCR:
+        res.predict_tcr(x, rd, transient=10, timeline=tl)
+    else:
+        res.predict_tc(x, rd, transient=10, timeline=tl)
 torch.cuda.synchronize()
 full = tl.cpu().numpy()
 t = full[50:500]

@@ -39,7 +39,7 @@ def _setup(n_res, n_in, n_out, seed, noise=0.001, feedback=True, in_scale=0.01, 
 
 
 def _check(eng, Ws, aff, us, W_outs, gid, T, transient, noise, uni, state_tol=1e-5, out_tol=1e-4, frames=None,
-           precision="tc"):
+           precision="tc2"):
     W, W_in, W_fb = Ws
     y, ext = eng.predict(_cuda(us), _cuda(W_outs), transient=transient,
                          group_ids=None if gid is None else _cuda(gid.astype(np.int32)),
@@ -112,7 +112,7 @@ def test_tc_two_readouts_in_one_pair_tile(n_res, n_in, n_out):
     bad = gid.copy()
     bad[10] = 2
     assert not eng._tc_resident_ok(_cuda(us), bad)
-    _check(eng, Ws, aff, us, W_outs, bad, T, transient, 0.001, uni, frames=[9, 10, 11, 63, 64])
+    _check(eng, Ws, aff, us, W_outs, bad, T, transient, 0.001, uni, frames=[9, 10, 11, 63, 64], precision="tc")
 
 
 def test_tc_device_noise_and_no_feedback():
@@ -122,7 +122,7 @@ def test_tc_device_noise_and_no_feedback():
     us = rng.randn(B, T, 16)
     W_outs = rng.randn(1, 8, 272) * 1e-5
     seed = 77
-    y = eng.predict(_cuda(us), _cuda(W_outs), transient=3, precision="tc", seed=seed).double().cpu().numpy()
+    y = eng.predict(_cuda(us), _cuda(W_outs), transient=3, precision="tc2", seed=seed).double().cpu().numpy()
     uni = device_noise_uniforms(seed, B, T, 256)
     for b in (0, 31, 63):
         ref = orc.predict(Ws[0], Ws[1], Ws[2], W_outs[0], us[b], 3, 0.001, uni[b], **aff)
@@ -151,7 +151,7 @@ def test_tc_widest_io_and_harvest():
     uni = rng.rand(B, T, N)
     _check(eng, Ws, aff, us, W_outs, gid, T, 1, 0.001, uni, frames=[0, 70, 127, 128, 139])
     ts = rng.randn(B, T, 16)
-    ext = eng.harvest(_cuda(us), _cuda(ts), precision="tc", noise_uniforms=_cuda(uni[:, :T - 1])).double().cpu().numpy()
+    ext = eng.harvest(_cuda(us), _cuda(ts), precision="tc2", noise_uniforms=_cuda(uni[:, :T - 1])).double().cpu().numpy()
     for b in (0, 127, 139):
         r = orc.fit(Ws[0], Ws[1], Ws[2], us[b], ts[b], 1, 0.001, uni[b, :T - 1], **aff)
         assert rel_err(ext[b, :, :N], r["states"]) < 1e-5
@@ -191,10 +191,10 @@ def test_tc_routes_what_the_resident_kernel_cannot_do():
     us = rng.randn(130, 6, 4)
     W_outs = rng.randn(2, 4, 132) * 1e-6
     gid = np.arange(130) % 2                                    # mixed readouts inside a tile
-    _check(eng, Ws, aff, us, W_outs, gid, 6, 0, 0.0, None, frames=[0, 1, 64, 65, 129])
+    _check(eng, Ws, aff, us, W_outs, gid, 6, 0, 0.0, None, frames=[0, 1, 64, 65, 129], precision="tc")
     rng, Ws, aff, big = _setup(640, 4, 4, seed=2, noise=0.0)
     assert not big.tc_supported() and big.tcs_supported()
-    _check(big, Ws, aff, rng.randn(4, 6, 4), rng.randn(1, 4, 644) * 1e-6, None, 6, 0, 0.0, None)
+    _check(big, Ws, aff, rng.randn(4, 6, 4), rng.randn(1, 4, 644) * 1e-6, None, 6, 0, 0.0, None, precision="tc")
     rng, Ws, aff, wide = _setup(64, 32, 4, seed=3)              # n_in = 32 > 24
     with pytest.raises(EsnB200Error):
         wide.predict(_cuda(rng.randn(4, 6, 32)), _cuda(rng.randn(1, 4, 96)), precision="tc")
@@ -213,7 +213,7 @@ def test_tc_harvest_states_match_oracle():
     us = np.stack([cases.esn_io(c, i % 5)[0] for i in range(B)])
     ys = np.stack([cases.esn_io(c, i % 5)[1] for i in range(B)])
     uni = np.random.RandomState(78).rand(B, T - 1, N)
-    ext = eng.harvest(_cuda(us), _cuda(ys), precision="tc", noise_uniforms=_cuda(uni)).double().cpu().numpy()
+    ext = eng.harvest(_cuda(us), _cuda(ys), precision="tc2", noise_uniforms=_cuda(uni)).double().cpu().numpy()
     worst = 0.0
     for b in (0, 63, 64, 127, 128, 129):
         r = orc.fit(o.W, o.W_in, o.W_feedb, us[b], ys[b], c["transient"], c["noise"], uni[b],
@@ -319,7 +319,7 @@ def test_tc_cfg3_symbol_indices_match_oracle():
     near = dist < 1e-5
     errs_ref = int(np.unpackbits((idx_ref ^ tx_idx)[..., None], axis=-1).sum())
     report = {}
-    for precision, frames in (("tc", B), ("fp32", 64), ("fp64", 32)):
+    for precision, frames in (("tc", B), ("tc2", B), ("tcs", B), ("fp32", 64), ("fp64", 32)):
         sel = slice(0, frames)
         y = eng.predict(_cuda(us[sel]), _cuda(W_outs), transient=d + cp, group_ids=_cuda(gid[sel].astype(np.int32)),
                         precision=precision, noise_uniforms=_cuda(uni[sel]))
@@ -335,13 +335,17 @@ def test_tc_cfg3_symbol_indices_match_oracle():
             e_ref = errs_ref
             assert abs(int(counts[0]) - e_ref) <= m * (int(mism.sum()) + 1)
     print("symbol-index parity at cfg3:", report)
-    # fp32 / fp64 kernels: the BASELINE.json statement holds literally.  Tensor-core path: its states carry
-    # ~9e-6 relative error (inside the 1e-5 state bar), which is ~1e-5..1e-4 absolute on X_hat, so a few
-    # symbols per 1e5 that lie just outside the 1e-5 band flip as well.  They are counted (here and in the
-    # bench line); every one of them is within 5e-4 of a decision boundary and they are < 1e-4 of all symbols.
+    # fp32 / fp64 kernels: the BASELINE.json statement holds literally.  'tc' = the resident kernel with the fp32
+    # CUDA-core readout (esn_recur_tcr, what bench.py times) and 'tcs': fp32-grade states (1e-6) and outputs (2e-6), so
+    # only a handful of symbols per million that lie just outside the 1e-5 band flip; they are counted (here and in
+    # the bench line) and every one of them is within 1e-4 of a decision boundary.  'tc2' (readout inside the MMA,
+    # a 100-deep truncating accumulate chain over partial sums far larger than y): ~1e-4 of all symbols.
     for precision in ("fp32", "fp64"):
         assert report[precision]["mismatch_outside_band"] == 0, (precision, report[precision])
-    r = report["tc"]
+    for precision in ("tc", "tcs"):
+        r = report[precision]
+        assert r["worst_mismatch_distance"] < 1e-4 and r["mismatch_outside_band"] <= 2e-5 * r["symbols"], (precision, r)
+    r = report["tc2"]
     assert r["worst_mismatch_distance"] < 5e-4 and r["mismatches"] <= 1e-4 * r["symbols"], r
 
 

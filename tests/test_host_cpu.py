@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(lib_path)
     hdr = open(os.path.join(ROOT, "include", "esn_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    names = re.findall(r"^\s*(?:int|float|long long)\s+((?:esn|ofdm)_\w+)\s*\(", hdr, flags=re.M)
+    names = re.findall(r"^\s*(?:int|float|double|long long)\s+((?:esn|ofdm)_\w+)\s*\(", hdr, flags=re.M)
     assert len(names) >= 15
     for n in names:
         assert hasattr(lib, n), f"{n} declared in esn_b200.h but not exported"
