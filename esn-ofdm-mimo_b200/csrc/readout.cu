@@ -101,6 +101,10 @@ syrk_f64_kernel(const TE *__restrict__ ext, int T, int p, int transient, int fra
 constexpr int DK = 32, DLD = TS + 4, DLT = DK + 4;
 constexpr int DPANEL = DK * DLD > TS * DLT ? DK * DLD : TS * DLT;
 
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(a), "l"(gmem));
+}
 __device__ __forceinline__ void dmma8x8x4(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                  : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
@@ -271,71 +275,178 @@ __global__ void scaled_teacher_rows_kernel(const TY *__restrict__ teacher, const
 }
 
 // -------------------------------------------------------------- Cholesky ----
-// One CTA per problem, matrix in global memory (L2-resident), right-looking
-// blocked factorisation with NB = 32; then forward and backward substitution
-// for n_rhs <= ESN_MAX_OUT right-hand sides.  Lower triangle is used/written.
-// NG groups of 256 threads share a problem: the 64x64 tiles of the trailing update are dealt round-robin to
-// the groups (own panel buffers, named barriers), the panel solve takes a row per thread.  NG = 1 with two
-// CTAs per SM when there are many problems, NG = 2 when the batch does not fill the GPU (the drop-in
-// ESN.fit is a batch of one).
+// One CTA per problem, matrix in global memory, LEFT-looking blocked factorisation with NB = 32: panel k first
+// receives the contributions of all previous panels,
+//     A[r][k0 + c] -= sum_{q < k0} L[r][q] L[k0 + c][q],   r >= k0,
+// on the fp64 tensor cores (mma.sync.m8n8k4.f64): a warp owns a 16 x 32 tile of the panel, the 32 pivot rows
+// L[k0 .. k0+31][q] are staged in shared memory in chunks of 32 columns (shared by all warps), the tile's own rows
+// L[r][q] go straight from L2 / HBM into A fragments (each element is used by exactly one warp), prefetched one
+// chunk ahead.  Then the diagonal block is factored in shared memory and the rows below are solved against it, one
+// row per thread.  Every element of L is written once and read ~k/2 times as a tile row: 6.6 MB of traffic per
+// 512 x 512 problem, where the right-looking update this replaces rewrote the whole trailing matrix per panel
+// (32 MB per problem; with ~450 problems in flight that is HBM traffic, not L2).  Forward and backward substitution
+// for n_rhs <= ESN_MAX_OUT right-hand sides follow.  Lower triangle is used/written.
+// NG groups of 128 threads share a problem (more warps over the same tiles): NG = 1 with four CTAs per SM when
+// there are many problems, NG = 2 when the batch does not fill the GPU (the drop-in ESN.fit is a batch of one).
 constexpr int NB = 32;
-constexpr int CH_GROUP = 256;
-typedef double PanelTile[64][NB + 1];
-
-__device__ __forceinline__ void group_sync(int g, int NG) {
-    if (NG == 1) __syncthreads();
-    else asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(CH_GROUP) : "memory");
-}
+#ifndef CH_GROUP_T
+#define CH_GROUP_T 128
+#endif
+#ifndef CH_MINB
+#define CH_MINB 4
+#endif
+constexpr int CH_GROUP = CH_GROUP_T;
+constexpr int CKK = 32;                       // K chunk of the left-looking update
+constexpr int PSTR = CKK + 4;                 // row stride of the staged pivot rows: half-warp LDS.64 conflict-free
 
 template <int NG>
-__global__ void __launch_bounds__(CH_GROUP * NG, NG == 1 ? 3 : 1)
+__global__ void __launch_bounds__(CH_GROUP * NG, NG == 1 ? CH_MINB : CH_MINB / 2)
 cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_all, int n, int n_rhs,
                           int *__restrict__ info_all, double *__restrict__ pivots) {
     constexpr int CH_THREADS = CH_GROUP * NG;
+    constexpr int NWARP = CH_THREADS / 32;
     double *A = Gall + (size_t)blockIdx.x * n * n;
     double *Bm = rhs_all + (size_t)blockIdx.x * n * n_rhs;
-    extern __shared__ __align__(16) unsigned char ch_smem[];
     __shared__ double D[NB][NB + 1];          // diagonal block / its factor
-    PanelTile *Pall = reinterpret_cast<PanelTile *>(ch_smem);       // [NG] panel rows of the i-tile
-    PanelTile *Qall = Pall + NG;                                     // [NG] panel rows of the j-tile
+    __shared__ double Pc[2][NB][PSTR];        // pivot rows of the current / next K chunk
+    __shared__ double Z[NB][ESN_MAX_OUT];     // substitution: the block's solution
     __shared__ int s_info;
     __shared__ double s_pmin, s_pmax;         // smallest / largest pivot d_jj = l_jj^2: max / min bounds cond(G) from below
-    const int tid = threadIdx.x, grp = tid / CH_GROUP, gt = tid % CH_GROUP;
-    PanelTile &Pn = Pall[grp], &Qn = Qall[grp];
-    PanelTile &P0 = Pall[0];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) { s_info = 0; s_pmin = INFINITY; s_pmax = 0.0; }
     __syncthreads();
 
     for (int k0 = 0; k0 < n; k0 += NB) {
         const int nb = min(NB, n - k0);
+        // 0. left-looking update of the panel (rows k0 .. n-1, columns k0 .. k0+nb-1) from the panels before it
+        if (k0 > 0) {
+            const int ntile = (n - k0 + 15) / 16, nchunk = k0 / CKK;       // k0 is a multiple of NB = CKK
+            const int fr = lane >> 2, fk = lane & 3;                         // fragment row / k (A, B); C: row fr, cols 2 fk, 2 fk + 1
+            constexpr int NST = NB * CKK / CH_THREADS;                       // staged pivot-row elements per thread and chunk
+            // pivot rows x chunk c -> Pc[buf] by cp.async (no registers; in flight during the DMMAs of the chunk before)
+            auto stage = [&](int c, int buf) {
+#pragma unroll
+                for (int i = 0; i < NST; ++i) {
+                    const int e = tid + i * CH_THREADS, r = e / CKK, q = e % CKK;
+                    if (r < nb) cp_async8(&Pc[buf][r][q], &A[(size_t)(k0 + r) * n + c * CKK + q]);
+                    else Pc[buf][r][q] = 0.0;
+                }
+                cp_async_commit();
+            };
+            for (int t0 = 0; t0 < ntile; t0 += NWARP) {                      // a pass: one tile per warp
+                const int tile = t0 + warp;
+                const bool have = tile < ntile;
+                const int r0 = k0 + tile * 16;
+                // rows of the two 8-row fragments (clamped: loads stay inside the matrix, stores are masked)
+                const double *ra = A + (size_t)min(r0 + fr, n - 1) * n + fk;
+                const double *rb = A + (size_t)min(r0 + 8 + fr, n - 1) * n + fk;
+                double acc[2][4][2] = {};
+                double a_cur[2][CKK / 4], a_nxt[2][CKK / 4];
+                if (have) {
+#pragma unroll
+                    for (int j = 0; j < CKK / 4; ++j) { a_cur[0][j] = ra[4 * j]; a_cur[1][j] = rb[4 * j]; }
+                }
+                stage(0, 0);
+                cp_async_wait<0>();
+                __syncthreads();
+                for (int c = 0; c < nchunk; ++c) {
+                    const int buf = c & 1;
+                    const bool more = c + 1 < nchunk;
+                    if (more) {
+                        if (have) {
+#pragma unroll
+                            for (int j = 0; j < CKK / 4; ++j) {
+                                a_nxt[0][j] = ra[(c + 1) * CKK + 4 * j];
+                                a_nxt[1][j] = rb[(c + 1) * CKK + 4 * j];
+                            }
+                        }
+                        stage(c + 1, buf ^ 1);
+                    }
+                    if (have) {
+#pragma unroll
+                        for (int j = 0; j < CKK / 4; ++j) {
+                            double bf[4];
+#pragma unroll
+                            for (int nt = 0; nt < 4; ++nt) bf[nt] = Pc[buf][nt * 8 + fr][4 * j + fk];
+#pragma unroll
+                            for (int nt = 0; nt < 4; ++nt) {
+                                dmma8x8x4(acc[0][nt], a_cur[0][j], bf[nt]);
+                                dmma8x8x4(acc[1][nt], a_cur[1][j], bf[nt]);
+                            }
+                        }
+                    }
+                    if (more) {
+                        cp_async_wait<0>();
+                        if (have) {
+#pragma unroll
+                            for (int j = 0; j < CKK / 4; ++j) { a_cur[0][j] = a_nxt[0][j]; a_cur[1][j] = a_nxt[1][j]; }
+                        }
+                    }
+                    __syncthreads();                                         // Pc[buf] consumed, Pc[buf ^ 1] staged
+                }
+                if (have) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = r0 + 8 * h + fr;
+                        if (r < n) {
+#pragma unroll
+                            for (int nt = 0; nt < 4; ++nt) {
+                                const int cc = nt * 8 + 2 * fk;
+                                double *dst = A + (size_t)r * n + k0 + cc;
+                                if (cc + 1 < nb && !(n & 1)) {
+                                    double2 v = *reinterpret_cast<double2 *>(dst);
+                                    v.x -= acc[h][nt][0];
+                                    v.y -= acc[h][nt][1];
+                                    *reinterpret_cast<double2 *>(dst) = v;
+                                } else {
+                                    if (cc < nb) dst[0] -= acc[h][nt][0];
+                                    if (cc + 1 < nb) dst[1] -= acc[h][nt][1];
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
         // 1. diagonal block -> shared, unblocked Cholesky
         for (int e = tid; e < NB * NB; e += CH_THREADS) {
             int r = e / NB, c = e % NB;
             D[r][c] = (r < nb && c < nb && c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
         }
         __syncthreads();
-        for (int j = 0; j < nb; ++j) {
-            if (tid == 0) {
+        if (warp == 0) {
+            // one warp, lane = row, warp-level barriers only: column j is scaled by 1 / l_jj, then row r >= c of every
+            // later column c loses l_rj l_cj
+            double pmin = INFINITY, pmax = 0.0;
+            int bad = 0;
+            for (int j = 0; j < nb; ++j) {
                 double d = D[j][j];
-                s_pmin = fmin(s_pmin, d);
-                s_pmax = fmax(s_pmax, d);
+                pmin = fmin(pmin, d);
+                pmax = fmax(pmax, d);
                 if (!(d > 0.0)) {
-                    if (s_info == 0) s_info = k0 + j + 1;
+                    if (bad == 0) bad = k0 + j + 1;
                     d = nan("");
                 }
-                D[j][j] = sqrt(d);
+                const double sj = sqrt(d);
+                double l = 0.0;
+                if (lane > j && lane < nb) l = D[lane][j] / sj;
+                __syncwarp();
+                if (lane == j) D[j][j] = sj;
+                else if (lane > j && lane < nb) D[lane][j] = l;
+                __syncwarp();
+#pragma unroll 4
+                for (int c = j + 1; c < nb; ++c)
+                    if (lane >= c && lane < nb) D[lane][c] -= l * D[c][j];
+                __syncwarp();
             }
-            __syncthreads();
-            const double djj = D[j][j];
-            if (tid > j && tid < nb) D[tid][j] /= djj;
-            __syncthreads();
-            // trailing update of the block: D[r][c] -= D[r][j] D[c][j], j < c <= r
-            for (int e = tid; e < nb * nb; e += CH_THREADS) {
-                int r = e / nb, c = e % nb;
-                if (c > j && r >= c) D[r][c] -= D[r][j] * D[c][j];
+            if (lane == 0) {
+                s_pmin = fmin(s_pmin, pmin);
+                s_pmax = fmax(s_pmax, pmax);
+                if (bad && s_info == 0) s_info = bad;
             }
-            __syncthreads();
         }
+        __syncthreads();
         for (int e = tid; e < nb * nb; e += CH_THREADS) {
             int r = e / nb, c = e % nb;
             if (c <= r) A[(size_t)(k0 + r) * n + k0 + c] = D[r][c];
@@ -362,48 +473,6 @@ cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_al
                 if (c < nb) row[c] = x[c];
         }
         __syncthreads();
-        // 3. trailing update A[i][j] -= sum_c L[i][c] L[j][c], i >= j >= k0+nb, 64x64 tiles dealt to the groups
-        const int t0 = k0 + nb;
-        const int ntile = (below + 63) / 64;
-        const int tx = gt & 15, ty = gt >> 4;
-        int pair = 0, loaded_ti = -1;
-        for (int ti = 0; ti < ntile; ++ti) {
-            for (int tj = 0; tj <= ti; ++tj, ++pair) {
-                if (pair % NG != grp) continue;
-                group_sync(grp, NG);                                 // previous tile of this group is done with Pn / Qn
-                if (loaded_ti != ti) {
-                    for (int e = gt; e < 64 * NB; e += CH_GROUP) {
-                        int r = e / NB, c = e % NB, gi = t0 + ti * 64 + r;
-                        Pn[r][c] = (gi < n && c < nb) ? A[(size_t)gi * n + k0 + c] : 0.0;
-                    }
-                    loaded_ti = ti;
-                }
-                for (int e = gt; e < 64 * NB; e += CH_GROUP) {
-                    int r = e / NB, c = e % NB, gj = t0 + tj * 64 + r;
-                    Qn[r][c] = (gj < n && c < nb) ? A[(size_t)gj * n + k0 + c] : 0.0;
-                }
-                group_sync(grp, NG);
-                double acc[4][4] = {};
-#pragma unroll
-                for (int c = 0; c < NB; ++c) {
-                    double a[4], b[4];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) { a[r] = Pn[ty + 16 * r][c]; b[r] = Qn[tx + 16 * r][c]; }
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[r][q] = fma(a[r], b[q], acc[r][q]);
-                }
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        int gi = t0 + ti * 64 + ty + 16 * r, gj = t0 + tj * 64 + tx + 16 * q;
-                        if (gi < n && gj <= gi) A[(size_t)gi * n + gj] -= acc[r][q];
-                    }
-            }
-        }
-        __syncthreads();
     }
 
     // ---- forward substitution L Z = B (blocked by NB) ----
@@ -421,7 +490,7 @@ cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_al
                 for (int c = 0; c < r; ++c) s -= D[r][c] * z[c];
                 z[r] = s / D[r][r];
             }
-            for (int r = 0; r < nb; ++r) P0[r][tid] = z[r];
+            for (int r = 0; r < nb; ++r) Z[r][tid] = z[r];
             for (int r = 0; r < nb; ++r) Bm[(size_t)(k0 + r) * n_rhs + tid] = z[r];
         }
         __syncthreads();
@@ -436,9 +505,9 @@ cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_al
 #pragma unroll
                 for (int c = 0; c < NB; ++c) l[c] = Lrow[c];
 #pragma unroll
-                for (int c = 0; c < NB; ++c) s = fma(l[c], P0[c][o], s);
+                for (int c = 0; c < NB; ++c) s = fma(l[c], Z[c][o], s);
             } else {
-                for (int c = 0; c < nb; ++c) s = fma(Lrow[c], P0[c][o], s);
+                for (int c = 0; c < nb; ++c) s = fma(Lrow[c], Z[c][o], s);
             }
             Bm[(size_t)(k0 + nb + i) * n_rhs + o] -= s;
         }
@@ -460,7 +529,7 @@ cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_al
                 for (int c = r + 1; c < nb; ++c) s -= D[c][r] * x[c];
                 x[r] = s / D[r][r];
             }
-            for (int r = 0; r < nb; ++r) P0[r][tid] = x[r];
+            for (int r = 0; r < nb; ++r) Z[r][tid] = x[r];
             for (int r = 0; r < nb; ++r) Bm[(size_t)(k0 + r) * n_rhs + tid] = x[r];
         }
         __syncthreads();
@@ -473,9 +542,9 @@ cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_al
 #pragma unroll
                 for (int c = 0; c < NB; ++c) l[c] = A[(size_t)(k0 + c) * n + i];
 #pragma unroll
-                for (int c = 0; c < NB; ++c) s = fma(l[c], P0[c][o], s);
+                for (int c = 0; c < NB; ++c) s = fma(l[c], Z[c][o], s);
             } else {
-                for (int c = 0; c < nb; ++c) s = fma(A[(size_t)(k0 + c) * n + i], P0[c][o], s);
+                for (int c = 0; c < nb; ++c) s = fma(A[(size_t)(k0 + c) * n + i], Z[c][o], s);
             }
             Bm[(size_t)i * n_rhs + o] -= s;
         }
@@ -591,17 +660,12 @@ extern "C" int esn_cholesky_solve_f64(double *G, double *rhs, int batch, int n, 
 extern "C" int esn_cholesky_solve_piv_f64(double *G, double *rhs, int batch, int n, int n_rhs, int32_t *info,
                                           double *pivots, void *stream) {
     if (!G || !rhs || batch <= 0 || n <= 0 || n_rhs <= 0 || n_rhs > ESN_MAX_OUT) return ESN_E_BADARG;
-    // many problems: 256 threads each, two CTAs per SM; no more problems than SMs: two groups per problem
-    // (measured 2.15 -> 1.74 ms for one 512 x 512 problem, 2.51 -> 1.87 ms for 74; four groups leave 64
-    // registers per thread and spill: 2.0 ms)
+    // many problems: 128 threads each, four CTAs per SM (the diagonal factor, the row solves and the substitutions are
+    // latency-bound and overlap across problems: 8.3 ms per 1184 problems of 512 x 512 against 11.7 ms with 256
+    // threads x 2; five CTAs of 96 registers spill: 11.4 ms); no more problems than SMs: two groups per problem
     cudaStream_t st = (cudaStream_t)stream;
-    if (batch <= 148) {
-        constexpr size_t smem = 2 * 2 * sizeof(PanelTile);
-        ESN_CUDA_TRY(cudaFuncSetAttribute(cholesky_solve_f64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cholesky_solve_f64_kernel<2><<<batch, CH_GROUP * 2, smem, st>>>(G, rhs, n, n_rhs, info, pivots);
-    } else {
-        cholesky_solve_f64_kernel<1><<<batch, CH_GROUP, 2 * sizeof(PanelTile), st>>>(G, rhs, n, n_rhs, info, pivots);
-    }
+    if (batch <= 148) cholesky_solve_f64_kernel<2><<<batch, CH_GROUP * 2, 0, st>>>(G, rhs, n, n_rhs, info, pivots);
+    else cholesky_solve_f64_kernel<1><<<batch, CH_GROUP, 0, st>>>(G, rhs, n, n_rhs, info, pivots);
     return esn_launch_status();
 }
 
