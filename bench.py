@@ -674,14 +674,17 @@ def run_gpu(args):
                              "fit_detect_symbols_per_s": world * per_group / ((us_fit_piped + per_group * us_det) * 1e-6),
                              "what": "steady state over two CUDA streams: harvest of batch k+1 beside the Gram / Cholesky of batch k"},
                "block": f"1 pilot + {per_group} data frames per coherence block"}
-        fit["parity"] = ("throughput-mode: W_out of a readout trained on tensor-core states differs from the fp64 fit by "
-                         "more than the 1e-4 bar (measured below); the parity-grade fit is `fit_parity`")
+
         # W_out of the tensor-core-harvest fit against the fp64-harvest fit: same pilots, same device noise stream
         npar = min(8, Gf)
         w_tc, _ = res.train_readout(res.harvest(fu[:npar], fy[:npar], precision="tc", seed=5), fy[:npar], TRANSIENT)
         e64 = res.harvest(fu[:npar].double(), fy[:npar].double(), precision="fp64", seed=5)
         w_64, _ = res.train_readout(e64, fy[:npar].double(), TRANSIENT)
         fit["wout_rel_err_vs_fp64_fit"] = float(((w_tc - w_64).flatten(1).norm(dim=1) / w_64.flatten(1).norm(dim=1)).max())
+        fit["parity"] = ("W_out of a readout trained on tensor-core states (fp32-grade, 1e-6) against the fp64 fit on the same pilots: "
+                         "measured below; BASELINE.json's bar is 1e-4 and the fp32 SIMT harvest sits at 1.0e-4 itself, so this is "
+                         + ("inside the bar here" if fit["wout_rel_err_vs_fp64_fit"] <= 1e-4 else
+                            "a THROUGHPUT mode (above the bar here); the parity-grade fit is `fit_parity`"))
         del w_tc, w_64, e64
         # the parity-grade fit at the same batch size: fp64 harvest (streaming SIMT kernel) + the same solve
         fu64, fy64 = fu.double(), fy.double()
@@ -875,8 +878,10 @@ def main():
     ap.add_argument("--ebno", type=float, default=15.0, help="Eb/N0 (dB) of the simulated link")
     ap.add_argument("--fit-precision", default="fp64", choices=["fp64", "fp32", "tc"],
                     help="harvest precision of the readouts the timed detection uses")
-    ap.add_argument("--fit-pilots", type=int, default=1184, help="pilots per batch of the fit-throughput leg (0 = skip)")
-    ap.add_argument("--shared-pilots", type=int, default=592,
+    ap.add_argument("--fit-pilots", type=int, default=4736,
+                    help="pilots per batch of the fit-throughput leg (0 = skip); 4736 = 37 CTA pairs of the harvest kernel "
+                         "(1184 occupy 10 of the 74 resident pairs for the same 10 ms)")
+    ap.add_argument("--shared-pilots", type=int, default=4736,
                     help="pilots per GPU of the shared-readout leg (one W_out from all ranks' pilots, Gram all-reduced; 0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
