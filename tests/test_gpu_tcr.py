@@ -103,3 +103,47 @@ def test_tcr_widest_io_continuation_device_noise(n_res, n_in, n_out):
     # wider I/O stays on the streamed-state kernel
     _, _, _, big = _setup(400, 24, 16, seed=1)
     assert not big.tcr_supported() and big.tcs_supported()
+
+
+def test_tcr_device_noise_no_feedback_and_small_io():
+    """teacher_forcing = False with the device counter noise (restated on the host for the oracle), and the padded
+    reservoirs / small I/O shapes of the 2x2 and SISO demos."""
+    from esn_b200.noise import device_noise_uniforms
+    rng, Ws, aff, eng = _setup(256, 16, 8, seed=5, noise=0.001, feedback=False)
+    B, T = 64, 40
+    us = rng.randn(B, T, 16)
+    W_outs = rng.randn(1, 8, 272) * 1e-5
+    seed = 77
+    y = eng.predict(_cuda(us), _cuda(W_outs), transient=3, precision="tcr", seed=seed).double().cpu().numpy()
+    uni = device_noise_uniforms(seed, B, T, 256)
+    for b in (0, 31, 63):
+        ref = orc.predict(Ws[0], Ws[1], Ws[2], W_outs[0], us[b], 3, 0.001, uni[b], **aff)
+        assert rel_err(y[b], ref) < 1e-4
+    for n_res, n_in, n_out in ((100, 4, 4), (200, 2, 2), (300, 4, 4)):
+        rng, Ws, aff, eng = _setup(n_res, n_in, n_out, seed=n_res, noise=0.001)
+        B, T = 20, 30
+        us = rng.randn(B, T, n_in)
+        W_outs = rng.randn(1, n_out, n_res + n_in) * 1e-6
+        uni = rng.rand(B, T, n_res)
+        _check(eng, Ws, aff, us, W_outs, None, T, 2, 0.001, uni, precision="tcr")
+
+
+def test_tcr_gain_setter_round_trip():
+    """esn_tc_set_acc_k0: 0 switches the compensation off (states move by the known bias), a negative value restores
+    the calibrated default."""
+    from esn_b200._lib import load
+    lib = load()
+    rng, Ws, aff, eng = _setup(512, 16, 8, seed=42, noise=0.0, in_scale=0.005)
+    B, T = 64, 200
+    us, ts = rng.randn(B, T, 16), rng.randn(B, T, 8)
+    k0 = lib.esn_tc_acc_k0()
+    assert 1e-8 < k0 < 2e-8
+    on = eng.harvest(_cuda(us), _cuda(ts), precision="tcr").double()
+    assert lib.esn_tc_set_acc_k0(0.0) == k0
+    off = eng.harvest(_cuda(us), _cuda(ts), precision="tcr").double()
+    assert lib.esn_tc_set_acc_k0(-1.0) == 0.0 and lib.esn_tc_acc_k0() == k0
+    ref = eng.harvest(_cuda(us).double(), _cuda(ts).double(), precision="fp64")
+    e_on = float((on - ref).abs().max() / ref.abs().max())
+    e_off = float((off - ref).abs().max() / ref.abs().max())
+    print("tcr states vs fp64, gain on / off: %.2e / %.2e" % (e_on, e_off))
+    assert e_on < 2e-6 and e_on < 0.6 * e_off
