@@ -585,15 +585,18 @@ def run_gpu(args):
         m2 = idx_2 != idx_64
         detect(frames, group_ids, rd2, "tc2")
         torch.cuda.synchronize()
-        best2 = None
-        for _ in range(3):
-            k0, k1 = ev(), ev()
-            k0.record(stream)
+        # timed like the headline kernel: the same number of back-to-back launches (a single launch after an idle
+        # period runs at a higher SM clock than the sustained loop under the power cap)
+        for _ in range(args.warmup):
             detect(frames, group_ids, rd2, "tc2")
-            k1.record(stream)
-            torch.cuda.synchronize()
-            t = D.max_over_ranks(k0.elapsed_time(k1), dev)
-            best2 = t if best2 is None else min(best2, t)
+        torch.cuda.synchronize()
+        k0, k1 = ev(), ev()
+        k0.record(stream)
+        for _ in range(args.steps):
+            detect(frames, group_ids, rd2, "tc2")
+        k1.record(stream)
+        torch.cuda.synchronize()
+        best2 = D.max_over_ranks(k0.elapsed_time(k1), dev) / args.steps
         throughput_mode = {"kernel": "esn_predict_tc2 (readout rows inside the MMA)", "kernel_ms": best2,
                            "symbols_per_s_kernel_only": world * B / (best2 * 1e-3),
                            "output_rel_err": float((y_2.double() - y_64).norm() / y_64.norm()),

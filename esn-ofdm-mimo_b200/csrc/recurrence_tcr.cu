@@ -254,8 +254,11 @@ __device__ __forceinline__ void tcr_readout_sweep(uint32_t st_hi_s, uint32_t lo_
 //   wait tA0 (chunks 0, 2 rewritten in both CTAs; ALL G0 accumulators in registers) -> G0 items of chunks 0, 2
 //   wait tA1 (chunks 1, 3 rewritten)                                       -> G0 items of chunks 1, 3
 //   wait tD1 (G1 accumulators drained)                                     -> G1 items of chunks 0..3
-//   wait tB  (everything rewritten)  -> G1 items of chunks 4..7, G0 items of chunks 4..6
-//   wait yready (u_t, y_{t-1} in the aug chunk) -> aug items of G0 and G1, G0 item of chunk 7 -> commit d
+//   wait tB  (everything rewritten)  -> G0 items of chunks 4..7
+//   wait yready (u_t, y_{t-1} in the aug chunk) -> aug item of G0 -> commit d0 (G0 complete)
+//                                    -> G1 items of chunks 4..7, aug item of G1 -> commit d1 (step complete)
+// G0 finishes ~4 K cycles before G1: its epilogue (which only rewrites chunks 0..3, read by nothing that is
+// still queued) runs behind G1's remaining MMAs, so the next step's first MMAs do not wait for it.
 // With one group (N_pad = 256) nothing overlaps: wait tB -> chunks 0..3, wait yready -> aug -> commit d.
 // Warps (640 threads, 5 per scheduler = 96 registers): 0-1 frame warps (thread = frame: inputs, readout assembly,
 // feedback), 2 producer, 3 issuer (CTA 0), 4-19 epilogue (thread = frame x 64 neurons).  The state barriers tA /
@@ -265,7 +268,7 @@ template <bool DBG, bool TL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TCR_THREADS, 1)
 esn_recur_tcr(const TcrParams p, const __grid_constant__ CUtensorMap map_w) {
     extern __shared__ unsigned char smem_dyn[];
-    __shared__ __align__(8) uint64_t bar_full[TCR_NST], bar_empty[TCR_NST], bar_d, bar_tA0, bar_tA1, bar_tD1, bar_tB, bar_yready, bar_yp;
+    __shared__ __align__(8) uint64_t bar_full[TCR_NST], bar_empty[TCR_NST], bar_d0, bar_d1, bar_tA0, bar_tA1, bar_tD1, bar_tB, bar_yready, bar_yp;
     __shared__ uint32_t s_tmem;
 
     const TcGeom gm = tc_geom(p.N, p.n_in);
@@ -287,7 +290,8 @@ esn_recur_tcr(const TcrParams p, const __grid_constant__ CUtensorMap map_w) {
 
     if (tid == 0) {
         for (int i = 0; i < TCR_NST; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-        mbar_init(&bar_d, 1);
+        mbar_init(&bar_d0, 1);                               // every MMA of group G0 of a step has completed
+        mbar_init(&bar_d1, 1);                               // every MMA of the step has completed
         mbar_init(&bar_yready, 2 * 2);                       // frame warps of both CTAs (used in CTA 0)
         mbar_init(&bar_tA0, 2 * 16);                         // epilogue warps of both CTAs (used in CTA 0)
         mbar_init(&bar_tA1, 2 * 16);
@@ -408,7 +412,7 @@ esn_recur_tcr(const TcrParams p, const __grid_constant__ CUtensorMap map_w) {
             for (int it = 0; it < nst; ++it) {
                 const bool more = it + 1 < nst;
                 if (more) { load_row(it + 2); load_teacher(it + 1); }
-                mbar_wait<true>(&bar_d, it & 1);                      // every MMA of step it is done with the aug chunk
+                mbar_wait<true>(&bar_d1, it & 1);                     // every MMA of step it is done with the aug chunk
                 if (more) publish(y);
             }
         } else {
@@ -478,11 +482,14 @@ esn_recur_tcr(const TcrParams p, const __grid_constant__ CUtensorMap map_w) {
             };
             for (int it = 0; it < nst; ++it) {
                 if (TL) { ptrace = (tl0 && it == 200) ? p.timeline + (size_t)(p.T + 1) * 8 : nullptr; ptr_i = 0; }
-                if (two) { chunk(0, 0); chunk(0, 2); chunk(0, 1); chunk(0, 3); }
-                for (int c = 0; c < C - 1; ++c) chunk(J - 1, c);
-                if (two) { chunk(0, 4); chunk(0, 5); chunk(0, 6); }
-                for (int j = 0; j < J; ++j) chunk(j, C - 1);
-                if (two) chunk(0, 7);
+                if (two) {
+                    chunk(0, 0); chunk(0, 2); chunk(0, 1); chunk(0, 3);
+                    for (int c = 0; c < 4; ++c) chunk(1, c);
+                    for (int c = 4; c < C; ++c) chunk(0, c);      // G0: chunks 4..7, aug
+                    for (int c = 4; c < C; ++c) chunk(1, c);      // G1: chunks 4..7, aug
+                } else {
+                    for (int c = 0; c < C; ++c) chunk(0, c);
+                }
             }
         }
     } else if (warp == 3 && rank == 1) {
@@ -528,7 +535,6 @@ esn_recur_tcr(const TcrParams p, const __grid_constant__ CUtensorMap map_w) {
                     ++item;
                 }
             };
-            const int gl = J - 1;                                  // the last (or only) group
             for (int it = 0; it < nst; ++it) {
                 if (TL) tr_i = (it == 200) ? 0 : -1;
                 if (tl0) p.timeline[it * 8 + 0] = clock64();
@@ -550,15 +556,18 @@ esn_recur_tcr(const TcrParams p, const __grid_constant__ CUtensorMap map_w) {
                 mbar_wait_cluster_relaxed<false>(&bar_tB, it & 1);
                 tc_fence_after();
                 if (tl0) p.timeline[it * 8 + 3] = clock64();
-                for (int c = two ? 4 : 0; c < C - 1; ++c) chunk(c, gl);
-                if (two) { chunk(4, 0); chunk(5, 0); chunk(6, 0); }
+                // G0 finishes first (chunks 4..7, aug) so that its epilogue runs behind G1's remaining MMAs and the
+                // next step's G0 MMAs find their state chunks rewritten when G1 is through
+                for (int c = two ? 4 : 0; c < C - 1; ++c) chunk(c, 0);
                 if (tl0) p.timeline[it * 8 + 7] = clock64();
                 mbar_wait_cluster_relaxed<false>(&bar_yready, it & 1);
                 tc_fence_after();
-                if (two) chunk(C - 1, 0);
-                chunk(C - 1, gl);
-                if (two) chunk(7, 0);
-                umma2_commit_pair(&bar_d);
+                chunk(C - 1, 0);
+                if (two) {
+                    umma2_commit_pair(&bar_d0);
+                    for (int c = 4; c < C; ++c) chunk(c, 1);
+                }
+                umma2_commit_pair(&bar_d1);
             }
         }
     } else {
@@ -605,7 +614,7 @@ esn_recur_tcr(const TcrParams p, const __grid_constant__ CUtensorMap map_w) {
         }
         for (int it = 0; it < nst; ++it) {
             es.key = esn_noise_key(p.seed, (uint32_t)b, (uint32_t)it);
-            mbar_wait<true>(&bar_d, it & 1);
+            mbar_wait<true>(two ? &bar_d0 : &bar_d1, it & 1);
             tc_fence_after();
             if (st4) p.timeline[it * 8 + 4] = clock64();
             cx.it = it;
@@ -620,6 +629,8 @@ esn_recur_tcr(const TcrParams p, const __grid_constant__ CUtensorMap map_w) {
                 if (st4) p.timeline[it * 8 + 5] = clock64();
                 tcr_block16<DBG>(p, cx, es, vb, 128 * hl + 64 + 16 * cq);
                 publish(&bar_tA1, r_tA1);
+                mbar_wait<true>(&bar_d1, it & 1);              // G1's MMAs (issued after G0's) are through as well
+                tc_fence_after();
             }
             {
                 // the last (or only) group: 32 neurons as two 16-neuron halves

@@ -38,14 +38,25 @@ torch.cuda.synchronize()
 full = tl.cpu().numpy()
 t = full[50:500]
 step = t[1:, 0] - t[:-1, 0]
-rows = (("step", step),
-        ("wait tA0 (chunks 0,2 rewritten)", t[:, 1] - t[:, 0]),
-        ("issue G0 c0-3, G1 c0-3", t[:, 2] - t[:, 1]),
-        ("wait tB (all state rewritten)", t[:, 3] - t[:, 2]),
-        ("issue G1 c4-7 (y), G0 c4-6", t[:, 7] - t[:, 3]),
-        ("wait y, aug, G0 c7 -> D ready", t[:, 4] - t[:, 7]),
-        ("epilogue block a (+publish)", t[:, 5] - t[:, 4]),
-        ("epilogue block b + G1", t[:, 6] - t[:, 5]))
+if TCR:
+    # esn_recur_tcr: G0 finishes before G1 (commit d0 / d1); stamp 7 = G0 chunks 4-7 issued, stamp 4 = epilogue woke on d0
+    rows = (("step", step),
+            ("wait tA0 (chunks 0,2 rewritten)", t[:, 1] - t[:, 0]),
+            ("issue G0 c0-3, G1 c0-3", t[:, 2] - t[:, 1]),
+            ("wait tB (all state rewritten)", t[:, 3] - t[:, 2]),
+            ("issue G0 c4-7", t[:, 7] - t[:, 3]),
+            ("wait y, aug G0, G1 c4-7 + aug (to next step)", t[1:, 0] - t[:-1, 7]),
+            ("epilogue G0 block a (+publish)", t[:, 5] - t[:, 4]),
+            ("epilogue G0 b, wait d1, G1, readout sweep", t[:, 6] - t[:, 5]))
+else:
+  rows = (("step", step),
+          ("wait tA0 (chunks 0,2 rewritten)", t[:, 1] - t[:, 0]),
+          ("issue G0 c0-3, G1 c0-3", t[:, 2] - t[:, 1]),
+          ("wait tB (all state rewritten)", t[:, 3] - t[:, 2]),
+          ("issue G1 c4-7 (y), G0 c4-6", t[:, 7] - t[:, 3]),
+          ("wait y, aug, G0 c7 -> D ready", t[:, 4] - t[:, 7]),
+          ("epilogue block a (+publish)", t[:, 5] - t[:, 4]),
+          ("epilogue block b + G1", t[:, 6] - t[:, 5]))
 for name, v in rows:
     print(f"{name:32s} mean {v.mean():9.0f}  p10 {np.percentile(v, 10):9.0f}  p90 {np.percentile(v, 90):9.0f} cycles")
 
