@@ -16,6 +16,8 @@ constexpr int MAXA = 8;   // max antennas per side in the equaliser
 
 __device__ __forceinline__ void sincospi_t(float x, float *s, float *c) { sincospif(x, s, c); }
 __device__ __forceinline__ void sincospi_t(double x, double *s, double *c) { sincospi(x, s, c); }
+__device__ __forceinline__ float log_t(float x) { return logf(x); }
+__device__ __forceinline__ double log_t(double x) { return log(x); }
 __device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
 __device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
 
@@ -881,7 +883,7 @@ __global__ void synth_frames_kernel(const uint8_t *__restrict__ tx_idx, const T 
                 const uint32_t h2 = esn_mix32(h1 ^ 0x68E31DA4U);
                 const T u1 = ((T)(h1 >> 8) + (T)0.5) * (T)(1.0 / 16777216.0);
                 const T u2 = (T)(h2 >> 8) * (T)(1.0 / 16777216.0);
-                const T rad = sqrt_t((T)-2 * (T)log((double)u1));
+                const T rad = sqrt_t((T)-2 * log_t(u1));
                 T sn, cn;
                 sincospi_t((T)2 * u2, &sn, &cn);
                 nr = rad * cn; ni = rad * sn;
@@ -958,14 +960,37 @@ synth_frames_frame_kernel(const uint8_t *__restrict__ tx_idx, const T *__restric
         for (int tx = 0; tx < N_t; ++tx) {
             const T *c_r = tr + (rx * N_t + tx) * ntaps, *c_i = ti + (rx * N_t + tx) * ntaps;
             const T *x_r = xr + tx * L, *x_i = xi + tx * L;
-            for (int k = 0; k < ntaps; ++k) {
-                const T ar = c_r[k], ai = c_i[k];
+            if (ntaps <= 8) {
+                // sliding window in registers: the TB + 7 samples the block needs are loaded once per Tx stream
+                constexpr int WIN = TB + 7;
+                T wr[WIN], wi[WIN];
 #pragma unroll
-                for (int j = 0; j < TB; ++j) {
-                    const int t = t0 + j - k;
-                    if (t >= 0 && t0 + j < L) {
-                        const T br = x_r[t], bi = x_i[t];
-                        yr[j] += ar * br - ai * bi; yi[j] += ar * bi + ai * br;
+                for (int q = 0; q < WIN; ++q) {
+                    const int t = t0 - 7 + q;
+                    const bool ok = t >= 0 && t < L;
+                    wr[q] = ok ? x_r[t] : (T)0; wi[q] = ok ? x_i[t] : (T)0;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (k < ntaps) {
+                        const T ar = c_r[k], ai = c_i[k];
+#pragma unroll
+                        for (int j = 0; j < TB; ++j) {
+                            const T br = wr[7 + j - k], bi = wi[7 + j - k];
+                            yr[j] += ar * br - ai * bi; yi[j] += ar * bi + ai * br;
+                        }
+                    }
+                }
+            } else {
+                for (int k = 0; k < ntaps; ++k) {
+                    const T ar = c_r[k], ai = c_i[k];
+#pragma unroll
+                    for (int j = 0; j < TB; ++j) {
+                        const int t = t0 + j - k;
+                        if (t >= 0 && t0 + j < L) {
+                            const T br = x_r[t], bi = x_i[t];
+                            yr[j] += ar * br - ai * bi; yi[j] += ar * bi + ai * br;
+                        }
                     }
                 }
             }
@@ -984,7 +1009,7 @@ synth_frames_frame_kernel(const uint8_t *__restrict__ tx_idx, const T *__restric
                 const uint32_t h2 = esn_mix32(h1 ^ 0x68E31DA4U);
                 const T u1 = ((T)(h1 >> 8) + (T)0.5) * (T)(1.0 / 16777216.0);
                 const T u2 = (T)(h2 >> 8) * (T)(1.0 / 16777216.0);
-                const T rad = sqrt_t((T)-2 * (T)log((double)u1));
+                const T rad = sqrt_t((T)-2 * log_t(u1));
                 T sn, cn;
                 sincospi_t((T)2 * u2, &sn, &cn);
                 nr = rad * cn; ni = rad * sn;
