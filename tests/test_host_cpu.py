@@ -224,3 +224,29 @@ def test_result_writers_reproduce_reference_files(tmp_path):
     assert mine == ref and list(mine) == list(ref)
     # uncoded-only run: coded columns are zeros, like the reference's zero-initialised arrays
     assert R.results_bundle(eb, g["writers/ue"], g["writers/um"])["BER_coded"]["ESN_calLLR"] == [0.0] * len(eb)
+
+
+def test_argument_structs_have_the_layout_of_the_header(tmp_path):
+    """The ctypes Structures of esn_b200/_lib.py against include/esn_b200.h compiled by gcc: same size and the same
+    offset for every field (field names differ only where Python reserves them: `in` -> `inp`)."""
+    import ctypes as C
+    import subprocess
+    from esn_b200 import _lib
+    pairs = (("esn_recurrence_args", _lib.RecurrenceArgs), ("esn_tc_predict_args", _lib.TcPredictArgs),
+             ("esn_tcs_args", _lib.TcsArgs))
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "esn_b200.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            cf = "in" if fname == "inp" else fname
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {cf}));')
+    lines += ["  return 0;", "}"]
+    src, exe = tmp_path / "layout.c", tmp_path / "layout"
+    src.write_text("\n".join(lines))
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    got = {(a, b): int(c) for a, b, c in (ln.split() for ln in out if ln.strip())}
+    for cname, cls in pairs:
+        assert got[(cname, "size")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
