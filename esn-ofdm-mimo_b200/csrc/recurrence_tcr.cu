@@ -191,7 +191,7 @@ __device__ __forceinline__ void tcr_lane_granule(int l, int k, int &chunk, int &
 
 template <int GPL>
 __device__ __forceinline__ void tcr_readout_sweep(uint32_t st_hi_s, uint32_t lo_delta, uint32_t wtab_s, uint32_t aug_s,
-                                                  int e, int lane) {
+                                                  int e, int lane, int N) {
     float acc[4][8];
 #pragma unroll
     for (int fr = 0; fr < 4; ++fr)
@@ -203,6 +203,7 @@ __device__ __forceinline__ void tcr_readout_sweep(uint32_t st_hi_s, uint32_t lo_
     for (int k = 0; k < GPL; ++k) {
         int chunk, gidx;
         tcr_lane_granule<GPL>(lane, k, chunk, gidx);
+        if (64 * chunk + 8 * gidx >= N) continue;          // padding neurons: x = 0 and w = 0
         uint32_t xh[4][4], xl[4][4];
 #pragma unroll
         for (int fr = 0; fr < 4; ++fr) {
@@ -274,6 +275,10 @@ esn_recur_tcr(const TcrParams p, const __grid_constant__ CUtensorMap map_w) {
     const TcGeom gm = tc_geom(p.N, p.n_in);
     const int S = gm.S, C = gm.C, J = S >> 1;
     const bool two = J == 2;
+    // State chunks that hold real neurons: a reservoir of 300 neurons is padded to 512 (8 chunks of 64), but the
+    // chunks 5..7 of the state are identically zero (padded neurons are held at 0), so their MMAs and weight tiles
+    // are skipped: 24 ring items per step instead of 36.
+    const int Cr = (p.N + 63) >> 6;
     unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     unsigned char *st_hi = base, *ring = base + (size_t)2 * C * STILE;
     unsigned char *wtab = ring + (size_t)TCR_NST * SLOT;      // lane-interleaved readout rows of this CTA's readout: S x 128 x 8 floats
@@ -478,6 +483,7 @@ esn_recur_tcr(const TcrParams p, const __grid_constant__ CUtensorMap map_w) {
                 ++item;
             };
             auto chunk = [&](int j, int c) {          // the two items (hi, lo) of slab 2j + r, chunk c
+                if (c >= Cr && c < C - 1) return;     // padding chunk: the state there is identically zero
                 for (int h = 0; h < 2; ++h) fetch(2 * j + (int)rank, c, h);
             };
             for (int it = 0; it < nst; ++it) {
@@ -507,6 +513,7 @@ esn_recur_tcr(const TcrParams p, const __grid_constant__ CUtensorMap map_w) {
             // one state chunk against one slab pair of group grp = two ring items: the hi weight tile meets x_hi
             // (main accumulator) and x_lo (correction accumulator), the lo weight tile x_hi (correction).
             auto chunk = [&](int c, int grp) {
+                if (c >= Cr && c < C - 1) return;     // padding chunk (the producer skips it as well)
                 const uint32_t x = hi0 + c * (STILE >> 4);
                 const uint32_t dm = tmem + 128u * grp, dc = dm + (TCR_SPLIT ? 256u : 0u);
                 const bool aug = c == C - 1;
@@ -621,13 +628,16 @@ esn_recur_tcr(const TcrParams p, const __grid_constant__ CUtensorMap map_w) {
             if (two) {
                 // BOTH G0 blocks leave TMEM before the first barrier: the next step's first G0 MMA overwrites
                 // every G0 column, whichever state chunk it reads
+                // (blocks that lie entirely in the padding -- neurons >= N -- are skipped: their state stays at the
+                // zeros it was initialised with, and nothing reads their accumulators)
                 uint32_t va[16], vb[16];
+                const int na = 128 * hl + 16 * cq, nb = na + 64;
                 tcr_load16(lane_tm + (uint32_t)(16 * cq), va);
                 tcr_load16(lane_tm + (uint32_t)(64 + 16 * cq), vb);
-                tcr_block16<DBG>(p, cx, es, va, 128 * hl + 16 * cq);
+                if (na < p.N) tcr_block16<DBG>(p, cx, es, va, na);
                 publish(&bar_tA0, r_tA0);
                 if (st4) p.timeline[it * 8 + 5] = clock64();
-                tcr_block16<DBG>(p, cx, es, vb, 128 * hl + 64 + 16 * cq);
+                if (nb < p.N) tcr_block16<DBG>(p, cx, es, vb, nb);
                 publish(&bar_tA1, r_tA1);
                 mbar_wait<true>(&bar_d1, it & 1);              // G1's MMAs (issued after G0's) are through as well
                 tc_fence_after();
@@ -647,15 +657,15 @@ esn_recur_tcr(const TcrParams p, const __grid_constant__ CUtensorMap map_w) {
                         else mbar_arrive_cluster_relaxed(r_tD1);
                     }
                 }
-                tcr_block16<DBG>(p, cx, es, v0, n0);
-                tcr_block16<DBG>(p, cx, es, v1, n0 + 16);
+                if (n0 < p.N) tcr_block16<DBG>(p, cx, es, v0, n0);
+                if (n0 + 16 < p.N) tcr_block16<DBG>(p, cx, es, v1, n0 + 16);
             }
             publish(&bar_tB, r_tB);
             if (!harvest) {
                 // every epilogue warp of this CTA has rewritten its part of the state: the readout sweep may read it
                 asm volatile("bar.sync 1, 512;" ::: "memory");
-                if (two) tcr_readout_sweep<2>(smem_u32(st_hi), lo_delta, smem_u32(wtab), smem_u32(st_hi) + gm.ca * STILE, e, lane);
-                else tcr_readout_sweep<1>(smem_u32(st_hi), lo_delta, smem_u32(wtab), smem_u32(st_hi) + gm.ca * STILE, e, lane);
+                if (two) tcr_readout_sweep<2>(smem_u32(st_hi), lo_delta, smem_u32(wtab), smem_u32(st_hi) + gm.ca * STILE, e, lane, p.N);
+                else tcr_readout_sweep<1>(smem_u32(st_hi), lo_delta, smem_u32(wtab), smem_u32(st_hi) + gm.ca * STILE, e, lane, p.N);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_yp);
             }

@@ -18,7 +18,7 @@ from esn_b200 import Reservoir  # noqa: E402
 TCR = "--tcr" in sys.argv          # the resident kernel with the CUDA-core readout (esn_recur_tcr) instead of esn_predict_tc2
 argv = [a for a in sys.argv[1:] if not a.startswith("--")]
 B = int(argv[0]) if argv else 148 * 64
-N, ni, no, T = 512, 16, 8, 522
+N, ni, no, T = int(os.environ.get("TL_N", "512")), 16, 8, 522
 rng = np.random.RandomState(42)
 W = rng.rand(N, N) - 0.5
 W[rng.rand(N, N) < 0.1] = 0
