@@ -202,6 +202,7 @@ esn_predict_tcs(const TcsParams p, const __grid_constant__ CUtensorMap map_w, co
 
     const TcGeom gm = tc_geom(p.N, p.n_in);
     const int C = gm.C, Cx = p.Cx, NG = p.NG, NP = p.NG, nacc = p.nacc, nbuf = p.nbuf;
+    const int Cr = (p.N + 63) >> 6;        // state chunks that hold real neurons (600 neurons: 10 of the 12 of N_pad = 768)
     unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     unsigned char *aug = base, *ringA = base + ATILE, *ringB = ringA + (size_t)p.nA * ATILE;
     float *ypart = reinterpret_cast<float *>(ringB + (size_t)p.nB * BSLOT);         // [8][NOP][64]
@@ -392,6 +393,7 @@ esn_predict_tcs(const TcsParams p, const __grid_constant__ CUtensorMap map_w, co
                 for (int ps = 0; ps < NP; ++ps) {
                     const int slab = 2 * ps + (int)rank;
                     for (int c = 0; c <= Cx; ++c) {                  // state chunks, then the aug chunk
+                        if (c >= Cr && c < Cx) continue;             // padding chunk: the state there is identically zero
                         mbar_wait<false>(&emptyB[slotB], ((itemB / p.nB) & 1) ^ 1);
                         if (rank == 0) mbar_expect_tx(&fullB[slotB], 2u * BSLOT);
                         tma2_g2s(ringB_s + (uint32_t)slotB * BSLOT, &map_w, 0, ((slab * C + c) * 2) * (SLOT / 512), r_fullB[slotB]);
@@ -412,7 +414,7 @@ esn_predict_tcs(const TcsParams p, const __grid_constant__ CUtensorMap map_w, co
             for (int it = 0; it < nst; ++it) {
                 const int rb = (it + 1) & 1;                           // buffer that holds x_{it-1}
                 for (int ps = 0; ps < NP; ++ps)
-                    for (int c = 0; c < Cx; ++c) {
+                    for (int c = 0; c < Cr; ++c) {
                         // chunk c was written by the epilogue of pass c / 4 of the previous step
                         if (ps == 0 && it > 0 && (c & 3) == 0) mbar_wait<false>(&bar_xready[c >> 2], (it - 1) & 1);
                         mbar_wait<false>(&emptyA[slotA], ((itemA / p.nA) & 1) ^ 1);
@@ -467,7 +469,7 @@ esn_predict_tcs(const TcsParams p, const __grid_constant__ CUtensorMap map_w, co
                     mbar_wait_cluster<false>(&bar_tfree[buf], use & 1);          // both CTAs have drained this TMEM buffer
                     tc_fence_after();
                     if (p.timeline && ps < 2) p.timeline[it * 16 + 1 + 4 * ps] = clock64();
-                    for (int c = 0; c < Cx; ++c) {
+                    for (int c = 0; c < Cr; ++c) {                   // (chunks >= Cr hold padding neurons only: skipped)
                         if (trace && tr_i < 64) trace[tr_i * 4] = clock64();
                         mbar_wait<false>(&fullA[slotA], (itemA / p.nA) & 1);
                         if (trace && tr_i < 64) trace[tr_i * 4 + 1] = clock64();
