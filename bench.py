@@ -620,7 +620,7 @@ def run_gpu(args):
         for rep in range(3):
             f0, f1, f2 = ev(), ev(), ev()
             f0.record(stream)
-            ext = res.harvest(fu, fy, precision="tc", seed=3 + rep)
+            ext = res.harvest(fu, fy, precision="tc", seed=3 + rep, su_exp=su_in, y_absmax=y_absmax)
             f1.record(stream)
             w, info = res.train_readout(ext, fy, TRANSIENT)
             prep_readouts(w)
@@ -641,14 +641,14 @@ def run_gpu(args):
             s_s.wait_stream(stream)
             exts, dones = {}, {}
             with torch.cuda.stream(s_h):
-                exts[0] = res.harvest(fu, fy, precision="tc", seed=11)
+                exts[0] = res.harvest(fu, fy, precision="tc", seed=11, su_exp=su_in, y_absmax=y_absmax)
                 dones[0] = ev()
                 dones[0].record(s_h)
             p0.record(s_s)
             for k in range(nb):
                 if k + 1 < nb:
                     with torch.cuda.stream(s_h):
-                        exts[k + 1] = res.harvest(fu, fy, precision="tc", seed=12 + k)
+                        exts[k + 1] = res.harvest(fu, fy, precision="tc", seed=12 + k, su_exp=su_in, y_absmax=y_absmax)
                         dones[k + 1] = ev()
                         dones[k + 1].record(s_h)
                 with torch.cuda.stream(s_s):
@@ -745,14 +745,14 @@ def run_gpu(args):
         reps = -(-Gs // G)
         su_ = pil_u.to(torch.float32).repeat(reps, 1, 1)[:Gs].contiguous()
         sy_ = pil_y.to(torch.float32).repeat(reps, 1, 1)[:Gs].contiguous()
-        res.train_shared_readout(su_, sy_, TRANSIENT, precision="tc", chunks=4, seed=5)
+        res.train_shared_readout(su_, sy_, TRANSIENT, precision="tc", chunks=4, seed=5, su_exp=su_in, y_absmax=y_absmax)
         torch.cuda.synchronize()
         D.barrier()
         bests = None
         for rep in range(3):
             s0, s1 = ev(), ev()
             s0.record(stream)
-            w_sh, info_sh, nbytes = res.train_shared_readout(su_, sy_, TRANSIENT, precision="tc", chunks=4, seed=6 + rep)
+            w_sh, info_sh, nbytes = res.train_shared_readout(su_, sy_, TRANSIENT, precision="tc", chunks=4, seed=6 + rep, su_exp=su_in, y_absmax=y_absmax)
             s1.record(stream)
             torch.cuda.synchronize()
             t = D.max_over_ranks(s0.elapsed_time(s1), dev)

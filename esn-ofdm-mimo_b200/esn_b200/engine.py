@@ -417,7 +417,8 @@ class Reservoir:
             teachers = self._as(teachers, torch.float32, 3)
             if tuple(teachers.shape) != (B, T, self.n_out):
                 raise ValueError(f"teachers must be [{B},{T},{self.n_out}]")
-            y_absmax = float((teachers * aff["t_scale"] + aff["t_shift"]).abs().max().item())
+            if y_absmax is None:               # (a device reduction + sync; callers in a pipeline pass it)
+                y_absmax = float((teachers * aff["t_scale"] + aff["t_shift"]).abs().max().item())
         elif y_absmax is None:
             a64 = self._aff[ESN_F64]
             if "_y_absmax" not in a64:
@@ -493,9 +494,12 @@ class Reservoir:
                                timeline=timeline, resident=True, su_exp=su_exp)
         return (y, ext) if return_ext else y
 
-    def harvest_tcr(self, inputs, teachers, noise_uniforms=None, seed=0):
-        """Teacher-forced harvesting with the resident tensor-core kernel (split accumulators)."""
-        return self._tcs_run(inputs, teachers=teachers, noise_uniforms=noise_uniforms, seed=seed, resident=True)[1]
+    def harvest_tcr(self, inputs, teachers, noise_uniforms=None, seed=0, su_exp=None, y_absmax=None):
+        """Teacher-forced harvesting with the resident tensor-core kernel (split accumulators).  su_exp / y_absmax:
+        the input pre-scale exponent and the largest |scaled teacher|, if the caller knows them (each costs a device
+        reduction and a host sync otherwise)."""
+        return self._tcs_run(inputs, teachers=teachers, noise_uniforms=noise_uniforms, seed=seed, resident=True,
+                             su_exp=su_exp, y_absmax=y_absmax)[1]
 
     def predict_tcs(self, inputs, readout, transient=0, group_ids=None, x0=None, y0=None, noise_uniforms=None,
                     seed=0, return_ext=False, y_absmax=None, tune=None, timeline=None, su_exp=None):
@@ -508,11 +512,12 @@ class Reservoir:
                                tune=tune, timeline=timeline, su_exp=su_exp)
         return (y, ext) if return_ext else y
 
-    def harvest_tcs(self, inputs, teachers, noise_uniforms=None, seed=0, tune=None):
+    def harvest_tcs(self, inputs, teachers, noise_uniforms=None, seed=0, tune=None, su_exp=None, y_absmax=None):
         """Teacher-forced harvesting with the streamed-state tensor-core kernel (throughput mode, see harvest_tc)."""
-        return self._tcs_run(inputs, teachers=teachers, noise_uniforms=noise_uniforms, seed=seed, tune=tune)[1]
+        return self._tcs_run(inputs, teachers=teachers, noise_uniforms=noise_uniforms, seed=seed, tune=tune,
+                             su_exp=su_exp, y_absmax=y_absmax)[1]
 
-    def harvest(self, inputs, teachers, precision="fp64", noise_uniforms=None, seed=0):
+    def harvest(self, inputs, teachers, precision="fp64", noise_uniforms=None, seed=0, su_exp=None, y_absmax=None):
         """Teacher-forced harvesting (libs/pyESN.py:179-182).  Returns the
         extended states E [B, T, N+n_in] = [x_n, u_n] (libs/pyESN.py:189).  precision 'auto' = 'fp64': the readout
         solve amplifies state errors, and only the fp64 harvest keeps W_out inside the 1e-4 bar with margin
@@ -521,9 +526,11 @@ class Reservoir:
             precision = "fp64"
         if precision == "tc":
             if self.tcr_supported():
-                return self.harvest_tcr(inputs, teachers, noise_uniforms=noise_uniforms, seed=seed)
+                return self.harvest_tcr(inputs, teachers, noise_uniforms=noise_uniforms, seed=seed, su_exp=su_exp,
+                                        y_absmax=y_absmax)
             if not self.tc_supported():
-                return self.harvest_tcs(inputs, teachers, noise_uniforms=noise_uniforms, seed=seed)
+                return self.harvest_tcs(inputs, teachers, noise_uniforms=noise_uniforms, seed=seed, su_exp=su_exp,
+                                        y_absmax=y_absmax)
             return self.harvest_tc(inputs, teachers, noise_uniforms=noise_uniforms, seed=seed)
         if precision == "tc2":
             return self.harvest_tc(inputs, teachers, noise_uniforms=noise_uniforms, seed=seed)
@@ -712,7 +719,7 @@ class Reservoir:
         return flat, G, rhs
 
     def train_shared_readout(self, inputs, teachers, transient=0, precision="fp64", chunks=4, seed=0,
-                             noise_uniforms=None):
+                             noise_uniforms=None, su_exp=None, y_absmax=None):
         """ONE readout from this rank's pilots AND those of every other rank (BASELINE.json configs[4]: "readout Gram
         allreduced over NVLink"): chunked harvest -> partial normal equations -> asynchronous all-reduce per chunk
         (hidden behind the next chunk's harvest) -> the same Cholesky on every rank.  Returns (W_out [1,n_out,P],
@@ -726,7 +733,8 @@ class Reservoir:
             if b1 <= b0:
                 continue
             nu = None if noise_uniforms is None else noise_uniforms[b0:b1]
-            ext = self.harvest(inputs[b0:b1], teachers[b0:b1], precision=precision, noise_uniforms=nu, seed=seed + k)
+            ext = self.harvest(inputs[b0:b1], teachers[b0:b1], precision=precision, noise_uniforms=nu, seed=seed + k,
+                               su_exp=su_exp, y_absmax=y_absmax)
             flat, _, _ = self.gram_flat(ext, teachers[b0:b1], transient)
             red.add(flat)
             del ext
