@@ -314,6 +314,7 @@ cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_al
     __shared__ double s_pmin, s_pmax;         // smallest / largest pivot d_jj = l_jj^2: max / min bounds cond(G) from below
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) { s_info = 0; s_pmin = INFINITY; s_pmax = 0.0; }
+    for (int e = tid; e < NB * ESN_MAX_OUT; e += CH_THREADS) Z[e / ESN_MAX_OUT][e % ESN_MAX_OUT] = 0.0;   // (rows / columns a short block leaves unwritten)
     __syncthreads();
 
     for (int k0 = 0; k0 < n; k0 += NB) {
@@ -415,9 +416,10 @@ cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_al
             D[r][c] = (r < nb && c < nb && c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
         }
         __syncthreads();
-        if (warp == 0) {
-            // one warp, lane = row, warp-level barriers only: column j is scaled by 1 / l_jj, then row r >= c of every
-            // later column c loses l_rj l_cj
+        {
+            // all warps: thread = (row r, column class cg); per column j two block barriers -- the column is scaled by
+            // l_jj by class 0, every class subtracts l_rj l_cj from its own columns c > j
+            const int r = lane, cg = warp;
             double pmin = INFINITY, pmax = 0.0;
             int bad = 0;
             for (int j = 0; j < nb; ++j) {
@@ -429,18 +431,26 @@ cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_al
                     d = nan("");
                 }
                 const double sj = sqrt(d);
-                double l = 0.0;
-                if (lane > j && lane < nb) l = D[lane][j] / sj;
-                __syncwarp();
-                if (lane == j) D[j][j] = sj;
-                else if (lane > j && lane < nb) D[lane][j] = l;
-                __syncwarp();
-#pragma unroll 4
-                for (int c = j + 1; c < nb; ++c)
-                    if (lane >= c && lane < nb) D[lane][c] -= l * D[c][j];
-                __syncwarp();
+                const double lr = (r > j && r < nb) ? D[r][j] / sj : 0.0;
+                double lc[(NB + NWARP - 1) / NWARP];                 // l_cj of this class's columns: lane c of the warp holds it
+#pragma unroll
+                for (int q = 0; q < (NB + NWARP - 1) / NWARP; ++q) {
+                    const int c = j + 1 + cg + q * NWARP;
+                    lc[q] = __shfl_sync(0xffffffffu, lr, c & 31);
+                }
+                __syncthreads();                                     // column j has been read by everyone
+                if (cg == 0) {
+                    if (r == j) D[j][j] = sj;
+                    else if (r > j && r < nb) D[r][j] = lr;
+                }
+#pragma unroll
+                for (int q = 0; q < (NB + NWARP - 1) / NWARP; ++q) {
+                    const int c = j + 1 + cg + q * NWARP;
+                    if (c < nb && r >= c && r < nb) D[r][c] -= lr * lc[q];
+                }
+                __syncthreads();                                     // column j + 1 is final
             }
-            if (lane == 0) {
+            if (tid == 0) {
                 s_pmin = fmin(s_pmin, pmin);
                 s_pmax = fmax(s_pmax, pmax);
                 if (bad && s_info == 0) s_info = bad;
@@ -483,33 +493,42 @@ cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_al
             D[r][c] = (r < nb && c < nb && c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
         }
         __syncthreads();
-        if (tid < n_rhs) {     // one thread per right-hand side solves the nb x nb block
-            double z[NB];
-            for (int r = 0; r < nb; ++r) {
-                double s = Bm[(size_t)(k0 + r) * n_rhs + tid];
-                for (int c = 0; c < r; ++c) s -= D[r][c] * z[c];
-                z[r] = s / D[r][r];
+        // the nb x nb block: a warp per right-hand side, lane = row, column-oriented -- z_c is final once the columns
+        // before it have been subtracted; lane c broadcasts it and the rows below take their share
+        for (int o = warp; o < n_rhs; o += NWARP) {
+            double bv = lane < nb ? Bm[(size_t)(k0 + lane) * n_rhs + o] : 0.0;
+            const double dii = lane < nb ? D[lane][lane] : 1.0;
+            double zr = 0.0;
+            for (int c = 0; c < nb; ++c) {
+                const double zc = __shfl_sync(0xffffffffu, bv / dii, c);
+                if (lane == c) zr = zc;
+                if (lane > c && lane < nb) bv -= D[lane][c] * zc;
             }
-            for (int r = 0; r < nb; ++r) Z[r][tid] = z[r];
-            for (int r = 0; r < nb; ++r) Bm[(size_t)(k0 + r) * n_rhs + tid] = z[r];
+            if (lane < nb) {
+                Z[lane][o] = zr;
+                Bm[(size_t)(k0 + lane) * n_rhs + o] = zr;
+            }
         }
         __syncthreads();
-        // update the rows below: B[i] -= L[i, k0:k0+nb] z
+        // update the rows below: B[i] -= L[i, k0:k0+nb] z.  One row per thread (its 32 entries of L are loaded once, in
+        // flight together, and meet all right-hand sides), eight right-hand sides at a time in registers.
         const int below = n - (k0 + nb);
-        for (int e = tid; e < below * n_rhs; e += CH_THREADS) {
-            int i = e / n_rhs, o = e - i * n_rhs;
+        for (int i = tid; i < below; i += CH_THREADS) {
             const double *Lrow = A + (size_t)(k0 + nb + i) * n + k0;
-            double s = 0.0;
-            if (nb == NB) {                                          // all 32 loads of the row in flight at once
-                double l[NB];
+            double l[NB];
 #pragma unroll
-                for (int c = 0; c < NB; ++c) l[c] = Lrow[c];
+            for (int c = 0; c < NB; ++c) l[c] = c < nb ? Lrow[c] : 0.0;
+            double *brow = Bm + (size_t)(k0 + nb + i) * n_rhs;
+            for (int o0 = 0; o0 < n_rhs; o0 += 8) {
+                double sacc[8] = {};
 #pragma unroll
-                for (int c = 0; c < NB; ++c) s = fma(l[c], Z[c][o], s);
-            } else {
-                for (int c = 0; c < nb; ++c) s = fma(Lrow[c], Z[c][o], s);
+                for (int c = 0; c < NB; ++c)
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) sacc[o] = fma(l[c], Z[c][o0 + o], sacc[o]);
+#pragma unroll
+                for (int o = 0; o < 8; ++o)
+                    if (o0 + o < n_rhs) brow[o0 + o] -= sacc[o];
             }
-            Bm[(size_t)(k0 + nb + i) * n_rhs + o] -= s;
         }
         __syncthreads();
     }
@@ -522,31 +541,38 @@ cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_al
             D[r][c] = (r < nb && c < nb && c <= r) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
         }
         __syncthreads();
-        if (tid < n_rhs) {
-            double x[NB];
-            for (int r = nb - 1; r >= 0; --r) {
-                double s = Bm[(size_t)(k0 + r) * n_rhs + tid];
-                for (int c = r + 1; c < nb; ++c) s -= D[c][r] * x[c];
-                x[r] = s / D[r][r];
+        for (int o = warp; o < n_rhs; o += NWARP) {               // L_kk^T x = z: the same, from the last column up
+            double bv = lane < nb ? Bm[(size_t)(k0 + lane) * n_rhs + o] : 0.0;
+            const double dii = lane < nb ? D[lane][lane] : 1.0;
+            double xr = 0.0;
+            for (int c = nb - 1; c >= 0; --c) {
+                const double xc = __shfl_sync(0xffffffffu, bv / dii, c);
+                if (lane == c) xr = xc;
+                if (lane < c) bv -= D[c][lane] * xc;
             }
-            for (int r = 0; r < nb; ++r) Z[r][tid] = x[r];
-            for (int r = 0; r < nb; ++r) Bm[(size_t)(k0 + r) * n_rhs + tid] = x[r];
+            if (lane < nb) {
+                Z[lane][o] = xr;
+                Bm[(size_t)(k0 + lane) * n_rhs + o] = xr;
+            }
         }
         __syncthreads();
-        // rows above: B[i] -= sum_c L[k0+c][i] x[c], i < k0
-        for (int e = tid; e < k0 * n_rhs; e += CH_THREADS) {
-            int i = e / n_rhs, o = e - i * n_rhs;
-            double s = 0.0;
-            if (nb == NB) {
-                double l[NB];
+        // rows above: B[i] -= sum_c L[k0+c][i] x[c], i < k0: one row i per thread (the loads of a column block are
+        // coalesced over i), eight right-hand sides at a time
+        for (int i = tid; i < k0; i += CH_THREADS) {
+            double l[NB];
 #pragma unroll
-                for (int c = 0; c < NB; ++c) l[c] = A[(size_t)(k0 + c) * n + i];
+            for (int c = 0; c < NB; ++c) l[c] = c < nb ? A[(size_t)(k0 + c) * n + i] : 0.0;
+            double *brow = Bm + (size_t)i * n_rhs;
+            for (int o0 = 0; o0 < n_rhs; o0 += 8) {
+                double sacc[8] = {};
 #pragma unroll
-                for (int c = 0; c < NB; ++c) s = fma(l[c], Z[c][o], s);
-            } else {
-                for (int c = 0; c < nb; ++c) s = fma(A[(size_t)(k0 + c) * n + i], Z[c][o], s);
+                for (int c = 0; c < NB; ++c)
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) sacc[o] = fma(l[c], Z[c][o0 + o], sacc[o]);
+#pragma unroll
+                for (int o = 0; o < 8; ++o)
+                    if (o0 + o < n_rhs) brow[o0 + o] -= sacc[o];
             }
-            Bm[(size_t)i * n_rhs + o] -= s;
         }
         __syncthreads();
     }
