@@ -310,6 +310,7 @@ cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_al
     __shared__ double D[NB][NB + 1];          // diagonal block / its factor
     __shared__ double Pc[2][NB][PSTR];        // pivot rows of the current / next K chunk
     __shared__ double Z[NB][ESN_MAX_OUT];     // substitution: the block's solution
+    __shared__ double Rd[NB];                 // reciprocals of the current block's pivots l_cc
     __shared__ int s_info;
     __shared__ double s_pmin, s_pmax;         // smallest / largest pivot d_jj = l_jj^2: max / min bounds cond(G) from below
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -463,6 +464,10 @@ cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_al
         }
         // 2. panel: rows below the block, A[i, k0:k0+nb] <- A[i, k0:k0+nb] L_kk^-T (one row per thread)
         const int below = n - (k0 + nb);
+        // (32 divisions per row by the same 32 pivots: reciprocal, one residual correction -- the quotient the divide
+        // instruction sequence itself would return, without its special-case handling)
+        if (tid < NB) Rd[tid] = tid < nb ? 1.0 / D[tid][tid] : 0.0;
+        __syncthreads();
         for (int i = tid; i < below; i += CH_THREADS) {
             double *row = A + (size_t)(k0 + nb + i) * n + k0;
             double x[NB];
@@ -475,7 +480,10 @@ cholesky_solve_f64_kernel(double *__restrict__ Gall, double *__restrict__ rhs_al
 #pragma unroll
                     for (int q = 0; q < NB; ++q)
                         if (q < c) s -= x[q] * D[c][q];
-                    x[c] = s / D[c][c];
+                    const double dcc = D[c][c], rc = Rd[c];
+                    double qv = s * rc;
+                    qv = fma(fma(-qv, dcc, s), rc, qv);
+                    x[c] = fma(fma(-qv, dcc, s), rc, qv);
                 }
             }
 #pragma unroll
