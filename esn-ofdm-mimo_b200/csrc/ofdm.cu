@@ -378,93 +378,109 @@ __device__ void fft512_forward(Cx<T> *a, Cx<T> *b, const Cx<T> *tw, int nb) {
     fft512_stage<T, 6>(a, b, tw, nb);
 }
 
+// The two N = 512 kernels below are persistent: grid = (CTAs that fit an SM) x SMs, every CTA builds its twiddle
+// table once and walks frames b = blockIdx.x, + gridDim.x, ...; the global loads of its next frame are issued
+// into registers before the current frame's three FFT stages and land in `a` (free after the last stage) behind
+// the output loop, so the load latency hides behind the transform instead of heading every frame.
+// NV = elements per thread and frame: 512 x nb streams / 256 threads (8 up to four streams, 16 up to eight)
+#define F512_LOAD(v, src, ne)                                                                                    \
+    _Pragma("unroll") for (int i = 0; i < NV; ++i) {                                                        \
+        const int e = i * 256 + (int)threadIdx.x;                                                                \
+        if (e < (ne)) v[i] = (src)[e];                                                                           \
+    }
+#define F512_STORE(v, A, ne, nb, p2, lg)                                                                         \
+    _Pragma("unroll") for (int i = 0; i < NV; ++i) {                                                        \
+        const int e = i * 256 + (int)threadIdx.x;                                                                \
+        if (e < (ne)) {                                                                                          \
+            const int t = p2 ? (e >> lg) : e / (nb), s_ = e - t * (nb);                                          \
+            A[s_ * F512_STR + f512_skew(t)] = v[i];                                                              \
+        }                                                                                                        \
+    }
+
 // ESN output -> FFT -> slicer -> error count for N = 512 (see unpack_fft_demap_frame_kernel for the semantics)
-template <typename T>
+template <typename T, int NV>
 __global__ void __launch_bounds__(256)
-unpack_fft_demap_frame512_kernel(const T *__restrict__ y, int rows, int N_t, const T *__restrict__ Pi, int pi_stride,
-                                 int qam_bits, T *__restrict__ X_hat, uint8_t *__restrict__ idx,
+unpack_fft_demap_frame512_kernel(const T *__restrict__ y, int B, int rows, int N_t, const T *__restrict__ Pi,
+                                 int pi_stride, int qam_bits, T *__restrict__ X_hat, uint8_t *__restrict__ idx,
                                  const uint8_t *__restrict__ tx_idx, T eps, unsigned long long *__restrict__ counts) {
     extern __shared__ __align__(16) unsigned char sm[];
     constexpr int N = 512;
     Cx<T> *A = reinterpret_cast<Cx<T> *>(sm), *Bf = A + N_t * F512_STR, *tw = Bf + N_t * F512_STR;
-    const int b = blockIdx.x;
-    const Cx<T> *yb = reinterpret_cast<const Cx<T> *>(y + (size_t)b * rows * 2 * N_t);   // [t][tx] complex pairs
+    const int ne = N * N_t;
     const bool p2 = (N_t & (N_t - 1)) == 0;
     const int lg = ilog2(N_t);
-    // the frame's loads are in flight while the twiddle table is built
-    for (int e0 = 0; e0 < N * N_t; e0 += 8 * blockDim.x) {
-        Cx<T> v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int e = e0 + i * blockDim.x + threadIdx.x;
-            if (e < N * N_t) v[i] = yb[e];
-        }
-        if (e0 == 0) fft512_make_table(tw);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int e = e0 + i * blockDim.x + threadIdx.x;
-            if (e < N * N_t) {
-                const int t = p2 ? (e >> lg) : e / N_t, tx = e - t * N_t;
-                A[tx * F512_STR + f512_skew(t)] = v[i];
-            }
-        }
-    }
-    __syncthreads();
-    fft512_forward(A, Bf, tw, N_t);
-    const T scale = (T)1 / ((T)N * sqrt_t(Pi[(size_t)b * pi_stride]));
     const Slicer<T> sl(qam_bits);
     unsigned long long errs = 0, near = 0;
-    for (int e = threadIdx.x; e < N * N_t; e += blockDim.x) {          // e = k N_t + tx: contiguous outputs
-        const int k = p2 ? (e >> lg) : e / N_t, tx = e - k * N_t;
-        const Cx<T> v = Bf[tx * F512_STR + f512_skew(k)];
-        const T xr = v.re * scale, xi = v.im * scale;
-        const size_t o = (size_t)b * N * N_t + e;
-        if (X_hat) { X_hat[2 * o] = xr; X_hat[2 * o + 1] = xi; }
-        const int id = sl.index(xr, xi);
-        if (idx) idx[o] = (uint8_t)id;
-        if (tx_idx) errs += __popc((unsigned)(id ^ (int)tx_idx[o]));
-        if (eps > (T)0 && sl.boundary_dist(xr, xi) < eps) near += 1;
+    Cx<T> v[NV];
+    int b = blockIdx.x;
+    {
+        const Cx<T> *yb = reinterpret_cast<const Cx<T> *>(y + (size_t)b * rows * 2 * N_t);   // [t][tx] complex pairs
+        F512_LOAD(v, yb, ne)
+        fft512_make_table(tw);                                     // built while the first frame is in flight
+        F512_STORE(v, A, ne, N_t, p2, lg)
+    }
+    __syncthreads();
+    for (; b < B; b += gridDim.x) {
+        const int bn = b + gridDim.x;
+        if (bn < B) {
+            const Cx<T> *yb = reinterpret_cast<const Cx<T> *>(y + (size_t)bn * rows * 2 * N_t);
+            F512_LOAD(v, yb, ne)
+        }
+        fft512_forward(A, Bf, tw, N_t);
+        const T scale = (T)1 / ((T)N * sqrt_t(Pi[(size_t)b * pi_stride]));
+        for (int e = threadIdx.x; e < ne; e += blockDim.x) {               // e = k N_t + tx: contiguous outputs
+            const int k = p2 ? (e >> lg) : e / N_t, tx = e - k * N_t;
+            const Cx<T> w = Bf[tx * F512_STR + f512_skew(k)];
+            const T xr = w.re * scale, xi = w.im * scale;
+            const size_t o = (size_t)b * ne + e;
+            if (X_hat) { X_hat[2 * o] = xr; X_hat[2 * o + 1] = xi; }
+            const int id = sl.index(xr, xi);
+            if (idx) idx[o] = (uint8_t)id;
+            if (tx_idx) errs += __popc((unsigned)(id ^ (int)tx_idx[o]));
+            if (eps > (T)0 && sl.boundary_dist(xr, xi) < eps) near += 1;
+        }
+        if (bn < B) F512_STORE(v, A, ne, N_t, p2, lg)
+        __syncthreads();                                           // next frame in `a`; every read of `b` is done
     }
     block_add_counts(errs, near, counts);
 }
 
 // CP strip + FFT of the received samples for N = 512 (see rx_fft_frame_kernel)
-template <typename T>
+template <typename T, int NV>
 __global__ void __launch_bounds__(256)
-rx_fft_frame512_kernel(const T *__restrict__ y_cp, int cp, int N_r, T *__restrict__ Y) {
+rx_fft_frame512_kernel(const T *__restrict__ y_cp, int B, int cp, int N_r, T *__restrict__ Y) {
     extern __shared__ __align__(16) unsigned char sm[];
     constexpr int N = 512;
     Cx<T> *A = reinterpret_cast<Cx<T> *>(sm), *Bf = A + N_r * F512_STR, *tw = Bf + N_r * F512_STR;
-    const int b = blockIdx.x;
-    const Cx<T> *src = reinterpret_cast<const Cx<T> *>(y_cp + ((size_t)b * (N + cp) + cp) * 2 * N_r);
+    const int ne = N * N_r;
     const bool p2 = (N_r & (N_r - 1)) == 0;
     const int lg = ilog2(N_r);
-    for (int e0 = 0; e0 < N * N_r; e0 += 8 * blockDim.x) {          // loads in flight while the twiddle table is built
-        Cx<T> v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int e = e0 + i * blockDim.x + threadIdx.x;
-            if (e < N * N_r) v[i] = src[e];
-        }
-        if (e0 == 0) fft512_make_table(tw);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int e = e0 + i * blockDim.x + threadIdx.x;
-            if (e < N * N_r) {
-                const int t = p2 ? (e >> lg) : e / N_r, rx = e - t * N_r;
-                A[rx * F512_STR + f512_skew(t)] = v[i];
-            }
-        }
+    const T scale = (T)1 / (T)N;
+    Cx<T> v[NV];
+    int b = blockIdx.x;
+    {
+        const Cx<T> *src = reinterpret_cast<const Cx<T> *>(y_cp + ((size_t)b * (N + cp) + cp) * 2 * N_r);
+        F512_LOAD(v, src, ne)
+        fft512_make_table(tw);
+        F512_STORE(v, A, ne, N_r, p2, lg)
     }
     __syncthreads();
-    fft512_forward(A, Bf, tw, N_r);
-    const T scale = (T)1 / (T)N;
-    Cx<T> *dst = reinterpret_cast<Cx<T> *>(Y + (size_t)b * N * 2 * N_r);
-    for (int e = threadIdx.x; e < N * N_r; e += blockDim.x) {          // e = k N_r + rx: contiguous
-        const int k = p2 ? (e >> lg) : e / N_r, rx = e - k * N_r;
-        Cx<T> v = Bf[rx * F512_STR + f512_skew(k)];
-        v.re *= scale; v.im *= scale;
-        dst[e] = v;
+    for (; b < B; b += gridDim.x) {
+        const int bn = b + gridDim.x;
+        if (bn < B) {
+            const Cx<T> *src = reinterpret_cast<const Cx<T> *>(y_cp + ((size_t)bn * (N + cp) + cp) * 2 * N_r);
+            F512_LOAD(v, src, ne)
+        }
+        fft512_forward(A, Bf, tw, N_r);
+        Cx<T> *dst = reinterpret_cast<Cx<T> *>(Y + (size_t)b * N * 2 * N_r);
+        for (int e = threadIdx.x; e < ne; e += blockDim.x) {               // e = k N_r + rx: contiguous
+            const int k = p2 ? (e >> lg) : e / N_r, rx = e - k * N_r;
+            Cx<T> w = Bf[rx * F512_STR + f512_skew(k)];
+            w.re *= scale; w.im *= scale;
+            dst[e] = w;
+        }
+        if (bn < B) F512_STORE(v, A, ne, N_r, p2, lg)
+        __syncthreads();
     }
 }
 
@@ -739,9 +755,172 @@ equalize_fixed_kernel(const T *__restrict__ Y, const T *__restrict__ H, const in
     }
 }
 
+// The fp32 solve when consecutive frames share their channel estimate (the frames of a coherence block):
+// thread = (run of FR consecutive frames, subcarrier).  The Gram matrix and its LU factors (same arithmetic,
+// same pivoting as above) are rebuilt only when the estimate or the regulariser changes from one frame to
+// the next; every frame then costs its 64 bytes of Y, the H^H y product, the replay of the row exchanges and
+// multipliers on the right-hand side, and the back substitution -- the results equal the per-frame solve bit
+// for bit.  The next frame's Y is in flight while the current one is solved.
+template <int NT, int NR, int FR>
+__global__ void __launch_bounds__(128)
+equalize_run_kernel(const float *__restrict__ Y, const float *__restrict__ H, const int *__restrict__ h_index, int B,
+                    int N, const float *__restrict__ reg, int reg_stride, const float *__restrict__ ps,
+                    int ps_stride, float *__restrict__ X_hat) {
+    const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const int runs = (B + FR - 1) / FR;
+    if (gid >= (size_t)runs * N) return;
+    const int b0 = (int)(gid / N) * FR, k = (int)(gid % N);
+    constexpr int HN = NR * NT * 2, YN = NR * 2, XN = NT * 2;
+    static_assert(HN % 4 == 0 && YN % 4 == 0 && XN % 4 == 0, "16-byte rows");
+    float h[HN], Ur[NT][NT], Ui[NT][NT], Mr[NT][NT], Mi[NT][NT];
+    int pv[NT];
+    float4 yn[YN / 4], yn2[YN / 4];                               // the next two frames' Y, in flight
+    const int nfr = min(FR, B - b0);
+#pragma unroll
+    for (int i = 0; i < YN / 4; ++i) {
+        yn[i] = __ldcs(reinterpret_cast<const float4 *>(Y + ((size_t)b0 * N + k) * YN) + i);
+        yn2[i] = __ldcs(reinterpret_cast<const float4 *>(Y + ((size_t)(b0 + (nfr > 1)) * N + k) * YN) + i);
+    }
+    int hb_prev = -1;
+    float rg_prev = 0.f;
+    for (int fi = 0; fi < nfr; ++fi) {
+        const int b = b0 + fi;
+        float y[YN];
+#pragma unroll
+        for (int i = 0; i < YN / 4; ++i) {
+            y[4 * i] = yn[i].x; y[4 * i + 1] = yn[i].y; y[4 * i + 2] = yn[i].z; y[4 * i + 3] = yn[i].w;
+            yn[i] = yn2[i];
+        }
+        if (fi + 2 < nfr) {
+#pragma unroll
+            for (int i = 0; i < YN / 4; ++i)
+                yn2[i] = __ldcs(reinterpret_cast<const float4 *>(Y + ((size_t)(b + 2) * N + k) * YN) + i);
+        }
+        const int hb = h_index ? h_index[b] : b;
+        const float rg = reg[(size_t)b * reg_stride];
+        if (fi == 0 || hb != hb_prev || rg != rg_prev) {
+            hb_prev = hb; rg_prev = rg;
+            const float4 *Hk = reinterpret_cast<const float4 *>(H + ((size_t)hb * N + k) * HN);
+#pragma unroll
+            for (int i = 0; i < HN / 4; ++i) {
+                const float4 v = __ldg(Hk + i);
+                h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+#pragma unroll
+                for (int j = i; j < NT; ++j) {                     // G_ij = sum_r conj(H[r][i]) H[r][j], G_ji = conj(G_ij)
+                    float gr = 0, gi = 0;
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) {
+                        const float ar = h[(r * NT + i) * 2], ai = h[(r * NT + i) * 2 + 1];
+                        const float cr = h[(r * NT + j) * 2], ci = h[(r * NT + j) * 2 + 1];
+                        gr += ar * cr + ai * ci; gi += ar * ci - ai * cr;
+                    }
+                    Ur[i][j] = gr; Ui[i][j] = gi;
+                    Ur[j][i] = gr; Ui[j][i] = -gi;
+                }
+                Ui[i][i] = 0;
+                Ur[i][i] += rg;
+            }
+#pragma unroll
+            for (int c = 0; c < NT; ++c) {
+                int piv = c; float best = Ur[c][c] * Ur[c][c] + Ui[c][c] * Ui[c][c];
+#pragma unroll
+                for (int r = c + 1; r < NT; ++r) {
+                    const float v = Ur[r][c] * Ur[r][c] + Ui[r][c] * Ui[r][c];
+                    if (v > best) { best = v; piv = r; }
+                }
+                pv[c] = piv;
+#pragma unroll
+                for (int r = c + 1; r < NT; ++r) {
+                    const bool sw = piv == r;
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const float a = Ur[c][j], d = Ur[r][j], e = Ui[c][j], f = Ui[r][j];
+                        Ur[c][j] = sw ? d : a; Ur[r][j] = sw ? a : d;
+                        Ui[c][j] = sw ? f : e; Ui[r][j] = sw ? e : f;
+                    }
+                }
+                const float inv = 1.0f / best, pr = Ur[c][c] * inv, pi_ = -Ui[c][c] * inv;   // 1/pivot
+#pragma unroll
+                for (int r = c + 1; r < NT; ++r) {
+                    const float fr = Ur[r][c] * pr - Ui[r][c] * pi_, fi_ = Ur[r][c] * pi_ + Ui[r][c] * pr;
+                    Mr[r][c] = fr; Mi[r][c] = fi_;
+#pragma unroll
+                    for (int j = c; j < NT; ++j) {
+                        Ur[r][j] -= fr * Ur[c][j] - fi_ * Ui[c][j];
+                        Ui[r][j] -= fr * Ui[c][j] + fi_ * Ur[c][j];
+                    }
+                }
+            }
+        }
+        float br[NT], bi[NT];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            float sr = 0, si = 0;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {                         // (H^H Y)_i = sum_r conj(H[r][i]) Y[r]
+                const float hr = h[(r * NT + i) * 2], hi = h[(r * NT + i) * 2 + 1];
+                sr += hr * y[2 * r] + hi * y[2 * r + 1]; si += hr * y[2 * r + 1] - hi * y[2 * r];
+            }
+            br[i] = sr; bi[i] = si;
+        }
+#pragma unroll
+        for (int c = 0; c < NT; ++c) {                             // the exchanges and multipliers of column c
+#pragma unroll
+            for (int r = c + 1; r < NT; ++r) {
+                const bool sw = pv[c] == r;
+                const float a = br[c], d = br[r], e = bi[c], f = bi[r];
+                br[c] = sw ? d : a; br[r] = sw ? a : d;
+                bi[c] = sw ? f : e; bi[r] = sw ? e : f;
+            }
+#pragma unroll
+            for (int r = c + 1; r < NT; ++r) {
+                const float fr = Mr[r][c], fi_ = Mi[r][c];
+                const float t = br[r] - (fr * br[c] - fi_ * bi[c]);
+                bi[r] -= fr * bi[c] + fi_ * br[c];
+                br[r] = t;
+            }
+        }
+        const float inv_ps = 1.0f / ps[(size_t)b * ps_stride];
+        float xr[NT], xi[NT], out[XN];
+#pragma unroll
+        for (int c = NT - 1; c >= 0; --c) {
+            float sr = br[c], si = bi[c];
+#pragma unroll
+            for (int j = c + 1; j < NT; ++j) {
+                sr -= Ur[c][j] * xr[j] - Ui[c][j] * xi[j];
+                si -= Ur[c][j] * xi[j] + Ui[c][j] * xr[j];
+            }
+            const float den = Ur[c][c] * Ur[c][c] + Ui[c][c] * Ui[c][c];
+            xr[c] = (sr * Ur[c][c] + si * Ui[c][c]) / den;
+            xi[c] = (si * Ur[c][c] - sr * Ui[c][c]) / den;
+            out[2 * c] = xr[c] * inv_ps; out[2 * c + 1] = xi[c] * inv_ps;
+        }
+        float4 *dst = reinterpret_cast<float4 *>(X_hat + ((size_t)b * N + k) * XN);
+#pragma unroll
+        for (int i = 0; i < XN / 4; ++i)
+            __stcs(dst + i, make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]));
+    }
+}
+
 template <typename T>
 static bool launch_equalize_fixed(const T *Y, const T *H, const int *h_index, int B, int N, int N_r, int N_t,
                                   const T *reg, int reg_stride, const T *ps, int ps_stride, T *X, cudaStream_t st) {
+    if constexpr (sizeof(T) == 4) {
+        // a frame -> estimate table (frames of a coherence block share H): runs of 16 frames per thread
+        constexpr int FR = 16;
+        const int rblocks = (int)(((size_t)((B + FR - 1) / FR) * N + 127) / 128);
+#define ESN_EQ_RUN(NT_, NR_)                                                                                      \
+        if (N_t == NT_ && N_r == NR_) {                                                                           \
+            equalize_run_kernel<NT_, NR_, FR><<<rblocks, 128, 0, st>>>(Y, H, h_index, B, N, reg, reg_stride, ps,  \
+                                                                       ps_stride, X);                             \
+            return true;                                                                                          \
+        }
+        if (h_index && B >= 4 * FR) { ESN_EQ_RUN(2, 2) ESN_EQ_RUN(2, 4) ESN_EQ_RUN(4, 4) ESN_EQ_RUN(4, 8) }
+#undef ESN_EQ_RUN
+    }
     const int blocks = (int)(((size_t)B * N + 127) / 128);
 #define ESN_EQ_CASE(NT_, NR_)                                                                                     \
     if (N_t == NT_ && N_r == NR_) {                                                                               \
@@ -1042,6 +1221,39 @@ inline int fft_threads(int N) { int t = N / 2; if (t < 32) t = 32; if (t > 512) 
 
 }  // namespace
 
+// grid of the persistent N = 512 kernels: the CTAs that stay resident (registers, shared memory) x SMs
+template <typename K>
+static int f512_grid(K kernel, int B, size_t smem) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return std::min(B, sms * per_sm);
+}
+
+template <typename T, int NV>
+static int launch_unpack512(const void *y, int B, int rows, int N_t, const void *Pi, int pi_stride, int qam_bits,
+                            void *X_hat, uint8_t *idx, const uint8_t *tx_idx, double eps, unsigned long long *counts,
+                            size_t smem, cudaStream_t st) {
+    auto kernel = unpack_fft_demap_frame512_kernel<T, NV>;
+    if (int rc = allow_smem(kernel, smem)) return rc;
+    kernel<<<f512_grid(kernel, B, smem), 256, smem, st>>>((const T *)y, B, rows, N_t, (const T *)Pi, pi_stride, qam_bits,
+                                                         (T *)X_hat, idx, tx_idx, (T)eps, counts);
+    return 0;
+}
+
+template <typename T, int NV>
+static int launch_rxfft512(const void *y_cp, int B, int cp, int N_r, void *Y, size_t smem, cudaStream_t st) {
+    auto kernel = rx_fft_frame512_kernel<T, NV>;
+    if (int rc = allow_smem(kernel, smem)) return rc;
+    kernel<<<f512_grid(kernel, B, smem), 256, smem, st>>>((const T *)y_cp, B, cp, N_r, (T *)Y);
+    return 0;
+}
+
 extern "C" int ofdm_unpack_fft_demap(int dtype, const void *y, int B, int rows, int N, int N_t, const void *Pi,
                                      int pi_stride, int qam_bits, void *X_hat, uint8_t *idx,
                                      const uint8_t *tx_idx, double boundary_eps, unsigned long long *counts,
@@ -1055,17 +1267,14 @@ extern "C" int ofdm_unpack_fft_demap(int dtype, const void *y, int B, int rows, 
     const size_t frame_smem = ((size_t)2 * ((size_t)N * N_t + (size_t)N * N_t / 32 + 1) + N) * el;
     if (N == 512 && N_t <= 8 && (dtype == ESN_F32 || dtype == ESN_F64)) {       // three radix-8 stages in registers
         const size_t smem512 = ((size_t)2 * N_t * F512_STR + 512) * 2 * el;
-        if (dtype == ESN_F32) {
-            if (int rc = allow_smem(unpack_fft_demap_frame512_kernel<float>, smem512)) return rc;
-            unpack_fft_demap_frame512_kernel<float><<<B, 256, smem512, st>>>(
-                (const float *)y, rows, N_t, (const float *)Pi, pi_stride, qam_bits, (float *)X_hat, idx, tx_idx,
-                (float)boundary_eps, counts);
-        } else {
-            if (int rc = allow_smem(unpack_fft_demap_frame512_kernel<double>, smem512)) return rc;
-            unpack_fft_demap_frame512_kernel<double><<<B, 256, smem512, st>>>(
-                (const double *)y, rows, N_t, (const double *)Pi, pi_stride, qam_bits, (double *)X_hat, idx, tx_idx,
-                boundary_eps, counts);
-        }
+        int rc;
+        if (dtype == ESN_F32)
+            rc = N_t <= 4 ? launch_unpack512<float, 8>(y, B, rows, N_t, Pi, pi_stride, qam_bits, X_hat, idx, tx_idx, boundary_eps, counts, smem512, st)
+                          : launch_unpack512<float, 16>(y, B, rows, N_t, Pi, pi_stride, qam_bits, X_hat, idx, tx_idx, boundary_eps, counts, smem512, st);
+        else
+            rc = N_t <= 4 ? launch_unpack512<double, 8>(y, B, rows, N_t, Pi, pi_stride, qam_bits, X_hat, idx, tx_idx, boundary_eps, counts, smem512, st)
+                          : launch_unpack512<double, 16>(y, B, rows, N_t, Pi, pi_stride, qam_bits, X_hat, idx, tx_idx, boundary_eps, counts, smem512, st);
+        if (rc) return rc;
         return esn_launch_status();
     }
     if (frame_smem <= 160 * 1024 && (dtype == ESN_F32 || dtype == ESN_F64)) {
@@ -1104,13 +1313,12 @@ extern "C" int ofdm_rx_fft(int dtype, const void *y_cp, int B, int N, int cp, in
     const size_t frame_smem = (2 * (tot + tot / 32 + 1) + N) * esz;
     if (N == 512 && N_r <= 8 && (dtype == ESN_F32 || dtype == ESN_F64)) {       // three radix-8 stages in registers
         const size_t smem512 = ((size_t)2 * N_r * F512_STR + 512) * 2 * esz;
-        if (dtype == ESN_F32) {
-            if (int rc = allow_smem(rx_fft_frame512_kernel<float>, smem512)) return rc;
-            rx_fft_frame512_kernel<float><<<B, 256, smem512, st>>>((const float *)y_cp, cp, N_r, (float *)Y);
-        } else {
-            if (int rc = allow_smem(rx_fft_frame512_kernel<double>, smem512)) return rc;
-            rx_fft_frame512_kernel<double><<<B, 256, smem512, st>>>((const double *)y_cp, cp, N_r, (double *)Y);
-        }
+        int rc;
+        if (dtype == ESN_F32)
+            rc = N_r <= 4 ? launch_rxfft512<float, 8>(y_cp, B, cp, N_r, Y, smem512, st) : launch_rxfft512<float, 16>(y_cp, B, cp, N_r, Y, smem512, st);
+        else
+            rc = N_r <= 4 ? launch_rxfft512<double, 8>(y_cp, B, cp, N_r, Y, smem512, st) : launch_rxfft512<double, 16>(y_cp, B, cp, N_r, Y, smem512, st);
+        if (rc) return rc;
         return esn_launch_status();
     }
     if (frame_smem <= 160 * 1024 && (dtype == ESN_F32 || dtype == ESN_F64)) {

@@ -383,3 +383,29 @@ def test_rescaled_reservoir_equals_a_fresh_one_and_chunked_curve_adds_up():
     cut = linksim.ber_curve(factory, N_t, N_r, Ns, m, [12], n_blocks=6, frames_per_block=8, max_blocks_per_launch=4, **kw)
     assert cut["_counts"][0, :, 1].tolist() == whole["_counts"][0, :, 1].tolist()              # same number of bits
     assert 0 < int(cut["_counts"][0, 0, 0]) < int(cut["_counts"][0, 0, 1])
+
+
+@pytest.mark.parametrize("shape", [(64, 4, 8), (32, 2, 2), (32, 2, 4), (16, 4, 4)])
+def test_equaliser_over_runs_of_frames_equals_the_per_frame_solve(shape):
+    """Frames of a coherence block share H: the fp32 equaliser factors H^H H + reg I once per run of frames
+    (`equalize_run_kernel`) and must give what the per-frame solve gives (h_index=None path, one estimate per
+    frame) and what the oracle's `solve` gives (OFDM_MIMO_2-2_NBF_LDPC.py:41-53, 453-460) -- with estimates and
+    regularisers that change in the middle of a run, and a ragged last run."""
+    from esn_b200 import ofdm
+    N, N_t, N_r = shape
+    rng = np.random.RandomState(5)
+    B, Bh = 16 * 9 + 5, 7
+    H = (rng.randn(Bh, N, N_r, N_t) + 1j * rng.randn(Bh, N, N_r, N_t)) / math.sqrt(2)
+    Y = rng.randn(B, N, N_r) + 1j * rng.randn(B, N, N_r)
+    hidx = np.sort(rng.randint(0, Bh, size=B)).astype(np.int32)
+    hidx[40:44] = [3, 0, 3, 0]                                   # not only monotone tables
+    reg = np.where(np.arange(B) % 23 < 11, 1e-3, 2e-2)
+    ps = 0.5 + rng.rand(B)
+    Yd, Hd = _cuda(Y, torch.complex64), _cuda(H, torch.complex64)
+    X_run = ofdm.equalize(Yd, Hd, _cuda(reg, torch.float32), _cuda(ps, torch.float32), h_index=_cuda(hidx))
+    X_one = ofdm.equalize(Yd, Hd[torch.from_numpy(hidx).long().cuda()].contiguous(), _cuda(reg, torch.float32),
+                          _cuda(ps, torch.float32))
+    assert rel_err(X_run.cpu().numpy(), X_one.cpu().numpy()) < 2e-6
+    for b in (0, 41, 42, B - 1):
+        ref = orc.equalize(Y[b], H[hidx[b]], ps[b], reg[b])
+        assert rel_err(X_run[b].cpu().numpy(), ref) < 2e-4
