@@ -1,0 +1,193 @@
+// Teacher-forced harvest in fp64 on the fp64 tensor cores (mma.sync.m8n8k4.f64, DMMA), sm_100a.
+//
+// The parity-grade half of ESN.fit (reference libs/pyESN.py:179-182: states[n] = tanh(W states[n-1] +
+// W_in u[n] + W_fb d[n-1]) + noise (rand - 0.5)) for reservoirs up to 512 neurons: the streaming SIMT kernel
+// (recurrence_simt.cuh) issues one DFMA per MAC with two shared-memory operands per 4 x 8 register tile and sits
+// at 0.39 of the fp64 rate; here a CTA steps a tile of 32 (16, 8) frames with the MACs on the DMMA pipe
+// (4736 pilots of cfg3: 94 -> 47 ms, 0.78 of the fp64 rate; profiles/probes/fp64_harvest_paths.py).
+//
+// Layout.  One CTA = 8 FB frames (FB = 4 below), 16 warps.  The augmented state [x | u | d | 0] of the tile lives in shared memory as
+// xs[frame][k] (row stride K_aug_pad + 4 doubles: the 8 x 4 A fragments of a half-warp fall into distinct banks).
+// Warp w owns neurons 32 w .. 32 w + 31 for all 32 frames: 4 x 4 accumulator fragments (64 registers).  The
+// augmented weights Wt_aug [K_aug_pad][N_pad] (the SIMT kernel's image; shared by every CTA, L2-resident) are
+// read straight from global memory as B fragments -- 4 rows of 64 contiguous bytes, every sector fully used --
+// two k-steps ahead of their use.  A step = 136 k-steps of (4 A loads, 4 B loads, 16 DMMAs) per warp, one barrier,
+// the epilogue (tanh, noise, E row n, new state into xs in place -- every warp has finished reading x_{n-1}), the
+// teacher / input rows of the next step, one barrier.  Same noise stream, same E layout as the SIMT kernel.
+#include "recurrence_simt.cuh"
+
+namespace {
+
+constexpr int DH_THREADS = 512;
+
+__device__ __forceinline__ void dh_dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+template <int FB>                                  // 8-frame blocks per CTA: tiles of 8, 16 or 32 frames
+__global__ void __launch_bounds__(DH_THREADS, 1)
+esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
+    constexpr int DH_BT = 8 * FB;
+    extern __shared__ __align__(16) double dh_xs[];
+    const int N = p.N, n_in = p.n_in, n_out = p.n_out, P = N + n_in, Kp = p.K_aug_pad, NP = p.N_pad;
+    const int RS = Kp + 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fk = lane & 3, fi = lane >> 2;
+    const int tile0 = blockIdx.x * DH_BT;
+    const int n0 = warp * 32;
+    const bool wact = n0 < N;
+    const double *Wt = static_cast<const double *>(p.Wt_aug);
+    const double *gin = static_cast<const double *>(p.in);
+    const double *in_scale = static_cast<const double *>(p.in_scale), *in_shift = static_cast<const double *>(p.in_shift);
+    const double *t_scale = static_cast<const double *>(p.t_scale), *t_shift = static_cast<const double *>(p.t_shift);
+    const double *teacher = static_cast<const double *>(p.teacher);
+    const double *noise = static_cast<const double *>(p.noise);
+    double *ext = static_cast<double *>(p.ext_out);
+    double *xs = dh_xs;
+    const bool use_noise = p.noise_amp != 0.0;
+    const double namp = p.noise_amp;
+    const int noise_rows = p.T - 1;
+
+    for (int i = tid; i < DH_BT * RS; i += DH_THREADS) xs[i] = 0.0;
+    // E row 0 = [0, u_0]
+    for (int i = tid; i < DH_BT * N; i += DH_THREADS) {
+        const int f = i / N, k = i - f * N, b = tile0 + f;
+        if (b < p.B) ext[((size_t)b * p.T) * P + k] = 0.0;
+    }
+    __syncthreads();
+    // scaled inputs of time step `row` -> E (and the u columns of xs); scaled teacher of `row` -> the d columns
+#define DH_STAGE_INPUTS(row, to_smem)                                                                             \
+    for (int i = tid; i < DH_BT * n_in; i += DH_THREADS) {                                                        \
+        const int f = i / n_in, j = i - f * n_in, b = tile0 + f;                                                  \
+        double v = 0.0;                                                                                           \
+        if (b < p.B && (row) < p.T) {                                                                             \
+            v = gin[((size_t)b * p.T + (row)) * n_in + j] * in_scale[j] + in_shift[j];                            \
+            ext[((size_t)b * p.T + (row)) * P + N + j] = v;                                                       \
+        }                                                                                                         \
+        if (to_smem) xs[f * RS + N + j] = v;                                                                      \
+    }
+#define DH_STAGE_TEACHER(row)                                                                                     \
+    for (int i = tid; i < DH_BT * n_out; i += DH_THREADS) {                                                       \
+        const int f = i / n_out, o = i - f * n_out, b = tile0 + f;                                                \
+        double v = 0.0;                                                                                           \
+        if (p.feedback && b < p.B && (row) < p.T)                                                                 \
+            v = teacher[((size_t)b * p.T + (row)) * n_out + o] * t_scale[o] + t_shift[o];                         \
+        xs[f * RS + P + o] = v;                                                                                   \
+    }
+    DH_STAGE_INPUTS(0, false)
+    DH_STAGE_INPUTS(1, true)
+    DH_STAGE_TEACHER(0)
+    __syncthreads();
+
+    const int nk = Kp / 4;                                  // K_aug_pad is a multiple of 16
+    const double *wb = Wt + (size_t)fk * NP + n0 + fi;      // B fragment c of k-step k4: wb[(4 k4) NP + 8 c]
+    const double *xa = xs + fi * RS + fk;                   // A fragment r of k-step k4: xa[8 r RS + 4 k4]
+    for (int n = 1; n < p.T; ++n) {
+        const int nrow = n - 1;                             // noise row of this step
+        double acc[FB][4][2];
+#pragma unroll
+        for (int r = 0; r < FB; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
+        if (wact) {
+            // B fragments two k-steps ahead of their use.  (A ring of 4 or 8 k-steps for the small tiles does not
+            // help: those are bound by the weight stream itself, 2.2 MB per step and SM at ~55 GB/s.)
+            double b0[4], b1[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { b0[c] = __ldg(wb + 8 * c); b1[c] = __ldg(wb + (size_t)4 * NP + 8 * c); }
+#pragma unroll 1
+            for (int k4 = 0; k4 < nk; k4 += 2) {
+                double bu[4], a[FB];
+                const bool more = k4 + 2 < nk;
+                // even k-step: use b0, refill it two steps ahead
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { bu[c] = b0[c]; if (more) b0[c] = __ldg(wb + (size_t)(4 * (k4 + 2)) * NP + 8 * c); }
+#pragma unroll
+                for (int r = 0; r < FB; ++r) a[r] = xa[8 * r * RS + 4 * k4];
+#pragma unroll
+                for (int r = 0; r < FB; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) dh_dmma(acc[r][c], a[r], bu[c]);
+                // odd k-step
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { bu[c] = b1[c]; if (more) b1[c] = __ldg(wb + (size_t)(4 * (k4 + 3)) * NP + 8 * c); }
+#pragma unroll
+                for (int r = 0; r < FB; ++r) a[r] = xa[8 * r * RS + 4 * (k4 + 1)];
+#pragma unroll
+                for (int r = 0; r < FB; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) dh_dmma(acc[r][c], a[r], bu[c]);
+            }
+        }
+        __syncthreads();                                    // every warp is through x_{n-1}
+        if (wact) {
+#pragma unroll
+            for (int r = 0; r < FB; ++r) {
+                const int f = 8 * r + fi, b = tile0 + f;
+                if (b < p.B) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int nn = n0 + 8 * c + 2 * fk;
+                        double x[2];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            x[h] = 0.0;
+                            if (nn + h < N) {
+                                x[h] = tanh(acc[r][c][h]);
+                                if (use_noise) {
+                                    double u;
+                                    if (noise) u = noise[((size_t)b * noise_rows + nrow) * N + nn + h];
+                                    else u = (double)esn_noise_uniform(esn_noise_key(p.seed, (uint32_t)b, (uint32_t)nrow), (uint32_t)(nn + h));
+                                    x[h] += namp * (u - 0.5);
+                                }
+                                ext[((size_t)b * p.T + n) * P + nn + h] = x[h];
+                                xs[f * RS + nn + h] = x[h];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        DH_STAGE_TEACHER(n)
+        DH_STAGE_INPUTS(n + 1, true)
+        __syncthreads();
+    }
+#undef DH_STAGE_INPUTS
+#undef DH_STAGE_TEACHER
+}
+
+}  // namespace
+
+template <int FB>
+static int dh_launch(const esn_simt::RecParams &p, cudaStream_t st) {
+    const int bt = 8 * FB, ctas = (p.B + bt - 1) / bt;
+    const size_t smem = (size_t)bt * (p.K_aug_pad + 4) * sizeof(double);
+    if (smem > 220 * 1024) return ESN_E_UNSUPPORTED;
+    ESN_CUDA_TRY(cudaFuncSetAttribute(esn_harvest_dmma_kernel<FB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    esn_harvest_dmma_kernel<FB><<<ctas, DH_THREADS, smem, st>>>(p);
+    return esn_launch_status();
+}
+
+// Takes the fp64 harvests of reservoirs up to 512 neurons that the cluster kernel (a few frames) has left:
+// the largest tile of 32 / 16 / 8 frames that still gives every SM a CTA.  ESN_HARVEST_DMMA=0 switches it off (the
+// streaming SIMT kernel as the cross-check), =8 / 16 / 32 pins the tile.
+static int dh_mode() {
+    static const int mode = [] { const char *e = getenv("ESN_HARVEST_DMMA"); return e ? atoi(e) : -1; }();
+    return mode;
+}
+bool esn_dmma_harvest_enabled() { return dh_mode() != 0; }
+
+int esn_dmma_harvest_launch(const esn_simt::RecParams &p, cudaStream_t st) {
+    const int mode = dh_mode();
+    if (mode == 0 || p.mode != ESN_MODE_HARVEST || p.N_pad > 512 || !p.ext_out) return ESN_E_UNSUPPORTED;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    int bt = mode > 0 ? mode : ((p.B + 31) / 32 >= sms ? 32 : (p.B + 15) / 16 >= sms ? 16 : 8);
+    if (bt == 32) return dh_launch<4>(p, st);
+    if (bt == 16) return dh_launch<2>(p, st);
+    return dh_launch<1>(p, st);
+}

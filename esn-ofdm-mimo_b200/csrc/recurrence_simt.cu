@@ -7,6 +7,8 @@ int esn_simt_launch_f64(const esn_simt::RecParams &p, cudaStream_t st);
 int esn_cluster_launch(const esn_simt::RecParams &p, int dtype, cudaStream_t st);   // recurrence_cluster.cu
 
 int esn_cluster_auto_limit(const esn_simt::RecParams &p, int dtype);                  // recurrence_cluster.cu
+int esn_dmma_harvest_launch(const esn_simt::RecParams &p, cudaStream_t st);           // recurrence_dmma.cu
+bool esn_dmma_harvest_enabled();
 
 // Batches of at most this many frames take the cluster kernel (weights resident in the shared memory of a
 // thread-block cluster, ~3 us per time step) instead of the streaming SIMT kernel (~90 us per step while its
@@ -63,11 +65,20 @@ extern "C" int esn_recurrence_run(const esn_recurrence_args *a, void *stream) {
     p.group_ids = a->group_ids; p.x0 = a->x0; p.y0 = a->y0; p.noise = a->noise_uniforms;
     p.ext_out = a->ext_out; p.y_out = a->y_out; p.workspace = a->workspace;
     cudaStream_t st = (cudaStream_t)stream;
-    const int limit = small_batch_setting() >= 0 ? small_batch_setting() : esn_cluster_auto_limit(p, a->dtype);
+    int limit = small_batch_setting() >= 0 ? small_batch_setting() : esn_cluster_auto_limit(p, a->dtype);
+    // the automatic limit is the crossover against the streaming SIMT kernel; fp64 harvests of up to 512 neurons
+    // continue on the fp64 tensor cores instead, which take half as long (profiles/r2_fp64_harvest.txt)
+    if (small_batch_setting() < 0 && a->mode == ESN_MODE_HARVEST && a->dtype == ESN_F64 && a->N_pad <= 512 &&
+        esn_dmma_harvest_enabled())
+        limit = limit * 11 / 20;
     if (a->B <= limit) {
         const int rc = esn_cluster_launch(p, a->dtype, st);
         if (rc != ESN_E_UNSUPPORTED && rc != ESN_E_TOOLARGE) return rc;
     }
     if (a->dtype == ESN_F32) return esn_simt_launch_f32(p, st);
+    if (a->mode == ESN_MODE_HARVEST) {               // large fp64 pilot batches: the fp64 tensor cores
+        const int rc = esn_dmma_harvest_launch(p, st);
+        if (rc != ESN_E_UNSUPPORTED) return rc;
+    }
     return esn_simt_launch_f64(p, st);
 }

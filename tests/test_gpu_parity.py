@@ -608,3 +608,39 @@ def test_bad_group_ids_are_refused_or_clamped():
         a = eng.predict(us, W_outs, group_ids=bad, precision=precision)
         b = eng.predict(us, W_outs, group_ids=ok, precision=precision)
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["mimo4x8_small", "nofeedback_small", "cfg3_4x8_n512"])
+def test_large_batch_fp64_harvest_on_the_fp64_tensor_cores_matches_oracle(name):
+    """Batches that fill the GPU with 32-frame tiles take `esn_harvest_dmma_kernel` (csrc/recurrence_dmma.cu)
+    instead of the streaming SIMT kernel: same E rows as the oracle's teacher-forced loop (libs/pyESN.py:179-182)
+    to 1e-11 on sampled frames incl. the ragged last tile, and the same device noise stream as the SIMT kernel."""
+    from esn_b200 import Reservoir
+    c = cases.ESN_CASES[name]
+    o, kw = _oracle_esn(c)
+    T = min(c["T"], 48)
+    B = 148 * 32 - 7                                        # 148 tiles, the last one ragged
+    base_u = np.stack([cases.esn_io(c, i)[0][:T] for i in range(4)])
+    base_y = np.stack([cases.esn_io(c, i)[1][:T] for i in range(4)])
+    rng = np.random.RandomState(3)
+    scale = 1.0 + 0.1 * rng.rand(B, 1, 1)
+    us, ys = base_u[np.arange(B) % 4] * scale, base_y[np.arange(B) % 4] * scale
+    eng = Reservoir(o.W, o.W_in, o.W_feedb, kw["input_scaling"], kw["input_shift"],
+                    kw["teacher_scaling"], kw["teacher_shift"], c["noise"], c["teacher_forcing"])
+    pick = [0, 31, 32, 2000, B - 1]
+    uni = rng.rand(B, T - 1, c["n_res"])
+    ext = eng.harvest(_cuda(us), _cuda(ys), precision="fp64", noise_uniforms=_cuda(uni))
+    assert ext.shape == (B, T, c["n_res"] + c["n_in"])
+    for b in pick:
+        r = orc.fit(o.W, o.W_in, o.W_feedb, us[b], ys[b], 0, c["noise"], uni[b],
+                    input_scaling=kw["input_scaling"], input_shift=kw["input_shift"],
+                    teacher_scaling=kw["teacher_scaling"], teacher_shift=kw["teacher_shift"],
+                    teacher_forcing=c["teacher_forcing"])
+        e = ext[b].cpu().numpy()
+        assert rel_err(e[:, :c["n_res"]], r["states"]) < 1e-11
+        assert rel_err(e[:, c["n_res"]:], r["in_s"]) < 1e-15
+        assert np.all(e[0, :c["n_res"]] == 0)
+    # device noise stream: a small batch (SIMT / cluster kernel) draws the same numbers for the same frame index
+    ext_d = eng.harvest(_cuda(us), _cuda(ys), precision="fp64", seed=11)
+    ext_s = eng.harvest(_cuda(us[:40]), _cuda(ys[:40]), precision="fp64", seed=11)
+    assert rel_err(ext_d[:40].cpu().numpy(), ext_s.cpu().numpy()) < 1e-11
