@@ -6,14 +6,15 @@
 // at 0.39 of the fp64 rate; here a CTA steps a tile of 32 (16, 8) frames with the MACs on the DMMA pipe
 // (4736 pilots of cfg3: 94 -> 47 ms, 0.78 of the fp64 rate; profiles/probes/fp64_harvest_paths.py).
 //
-// Layout.  One CTA = 8 FB frames (FB = 4 below), 16 warps.  The augmented state [x | u | d | 0] of the tile lives in shared memory as
-// xs[frame][k] (row stride K_aug_pad + 4 doubles: the 8 x 4 A fragments of a half-warp fall into distinct banks).
-// Warp w owns neurons 32 w .. 32 w + 31 for all 32 frames: 4 x 4 accumulator fragments (64 registers).  The
-// augmented weights Wt_aug [K_aug_pad][N_pad] (the SIMT kernel's image; shared by every CTA, L2-resident) are
-// read straight from global memory as B fragments -- 4 rows of 64 contiguous bytes, every sector fully used --
-// two k-steps ahead of their use.  A step = 136 k-steps of (4 A loads, 4 B loads, 16 DMMAs) per warp, one barrier,
-// the epilogue (tanh, noise, E row n, new state into xs in place -- every warp has finished reading x_{n-1}), the
-// teacher / input rows of the next step, one barrier.  Same noise stream, same E layout as the SIMT kernel.
+// Layout.  One CTA = 8 FB frames (FB = 4, 2, 1), 16 warps.  The augmented state [x | u | d | 0] of the tile lives in
+// shared memory as xs[frame][k] (row stride K_aug_pad + 4 doubles: the 8 x 4 A fragments of a half-warp fall into
+// distinct banks).  Warp w owns neurons 32 w .. 32 w + 31 for all frames: FB x 4 accumulator fragments.  The
+// augmented weights Wt_aug [K_aug_pad][N_pad] (the SIMT kernel's image; shared by every CTA, L2-resident) reach the
+// warp through its own cp.async ring in shared memory (see below).  A step = 136 k-steps of (FB A loads, 4 B loads,
+// 4 FB DMMAs) per warp, one barrier, the epilogue (tanh, noise, E row n, new state into xs in place -- every warp
+// has finished reading x_{n-1}), the teacher / input rows of the next step, one barrier.  Same noise stream, same
+// E layout as the SIMT kernel.  (First version: B fragments straight from global memory, 32-byte rows -- the
+// 32-frame tile ran at the same speed, the 8- and 16-frame tiles at 42 / 49 us per step against 24.5 now.)
 #include "recurrence_simt.cuh"
 
 namespace {
@@ -25,7 +26,7 @@ __device__ __forceinline__ void dh_dmma(double (&c)[2], double a, double b) {
                  : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-template <int FB>                                  // 8-frame blocks per CTA: tiles of 8, 16 or 32 frames
+template <int FB, int NSTG>                        // 8-frame blocks per CTA (tiles of 8, 16 or 32 frames), weight-ring stages
 __global__ void __launch_bounds__(DH_THREADS, 1)
 esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
     constexpr int DH_BT = 8 * FB;
@@ -79,8 +80,30 @@ esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
     DH_STAGE_TEACHER(0)
     __syncthreads();
 
-    const int nk = Kp / 4;                                  // K_aug_pad is a multiple of 16
-    const double *wb = Wt + (size_t)fk * NP + n0 + fi;      // B fragment c of k-step k4: wb[(4 k4) NP + 8 c]
+    // The weight stream: warp w needs Wt_aug[k][32 w .. 32 w + 31] for every k, 256 contiguous bytes per k row.  It
+    // copies them itself, 8 k rows (2 KB) per cp.async group, into its own ring of NSTG stages (row stride 36 doubles:
+    // conflict-free B fragments) -- full 128-byte lines instead of 32-byte fragment rows, no register staging, and
+    // only warp-level synchronisation; the ring runs ahead across time steps (the weights do not change).
+    constexpr int KR = 8, WRS = 36;
+    const int nch = Kp / KR;                                // K_aug_pad is a multiple of 16
+    double *wst = xs + DH_BT * RS + (size_t)warp * NSTG * KR * WRS;
+    const double *wsrc = Wt + n0 + 2 * (lane & 15) + (size_t)(lane >> 4) * NP;   // piece q of a chunk: + 2 q rows
+    double *wdst = wst + (lane >> 4) * WRS + 2 * (lane & 15);
+    int left = (p.T - 1) * nch, ic = 0, is = 0;             // chunks still to issue, next chunk of the image, next stage
+    auto issue = [&]() {                                    // one commit group per call, empty past the end
+        if (wact && left > 0) {
+            const double *src = wsrc + (size_t)(KR * ic) * NP;
+            double *dst = wdst + is * KR * WRS;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cp_async16(dst + 2 * q * WRS, src + (size_t)(2 * q) * NP);
+            --left;
+            if (++ic == nch) ic = 0;
+            if (++is == NSTG) is = 0;
+        }
+        cp_async_commit();
+    };
+    for (int i = 0; i < NSTG - 1; ++i) issue();
+    int ds = 0;                                             // stage of the chunk in use
     const double *xa = xs + fi * RS + fk;                   // A fragment r of k-step k4: xa[8 r RS + 4 k4]
     for (int n = 1; n < p.T; ++n) {
         const int nrow = n - 1;                             // noise row of this step
@@ -90,33 +113,25 @@ esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
         if (wact) {
-            // B fragments two k-steps ahead of their use.  (A ring of 4 or 8 k-steps for the small tiles does not
-            // help: those are bound by the weight stream itself, 2.2 MB per step and SM at ~55 GB/s.)
-            double b0[4], b1[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { b0[c] = __ldg(wb + 8 * c); b1[c] = __ldg(wb + (size_t)4 * NP + 8 * c); }
 #pragma unroll 1
-            for (int k4 = 0; k4 < nk; k4 += 2) {
-                double bu[4], a[FB];
-                const bool more = k4 + 2 < nk;
-                // even k-step: use b0, refill it two steps ahead
+            for (int c = 0; c < nch; ++c) {
+                cp_async_wait<NSTG - 2>();
+                __syncwarp();                               // this chunk has landed for every lane; the previous stage is free
+                issue();
+                const double *wb = wst + ds * KR * WRS + fk * WRS + fi;
+                if (++ds == NSTG) ds = 0;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) { bu[c] = b0[c]; if (more) b0[c] = __ldg(wb + (size_t)(4 * (k4 + 2)) * NP + 8 * c); }
+                for (int j = 0; j < 2; ++j) {
+                    double bu[4], a[FB];
 #pragma unroll
-                for (int r = 0; r < FB; ++r) a[r] = xa[8 * r * RS + 4 * k4];
+                    for (int cc = 0; cc < 4; ++cc) bu[cc] = wb[4 * j * WRS + 8 * cc];
 #pragma unroll
-                for (int r = 0; r < FB; ++r)
+                    for (int r = 0; r < FB; ++r) a[r] = xa[8 * r * RS + 4 * (2 * c + j)];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) dh_dmma(acc[r][c], a[r], bu[c]);
-                // odd k-step
+                    for (int r = 0; r < FB; ++r)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) { bu[c] = b1[c]; if (more) b1[c] = __ldg(wb + (size_t)(4 * (k4 + 3)) * NP + 8 * c); }
-#pragma unroll
-                for (int r = 0; r < FB; ++r) a[r] = xa[8 * r * RS + 4 * (k4 + 1)];
-#pragma unroll
-                for (int r = 0; r < FB; ++r)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) dh_dmma(acc[r][c], a[r], bu[c]);
+                        for (int cc = 0; cc < 4; ++cc) dh_dmma(acc[r][cc], a[r], bu[cc]);
+                }
             }
         }
         __syncthreads();                                    // every warp is through x_{n-1}
@@ -158,13 +173,13 @@ esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
 
 }  // namespace
 
-template <int FB>
+template <int FB, int NSTG>
 static int dh_launch(const esn_simt::RecParams &p, cudaStream_t st) {
     const int bt = 8 * FB, ctas = (p.B + bt - 1) / bt;
-    const size_t smem = (size_t)bt * (p.K_aug_pad + 4) * sizeof(double);
-    if (smem > 220 * 1024) return ESN_E_UNSUPPORTED;
-    ESN_CUDA_TRY(cudaFuncSetAttribute(esn_harvest_dmma_kernel<FB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    esn_harvest_dmma_kernel<FB><<<ctas, DH_THREADS, smem, st>>>(p);
+    const size_t smem = ((size_t)bt * (p.K_aug_pad + 4) + (size_t)(DH_THREADS / 32) * NSTG * 8 * 36) * sizeof(double);
+    if (smem > 226 * 1024) return ESN_E_UNSUPPORTED;
+    ESN_CUDA_TRY(cudaFuncSetAttribute(esn_harvest_dmma_kernel<FB, NSTG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    esn_harvest_dmma_kernel<FB, NSTG><<<ctas, DH_THREADS, smem, st>>>(p);
     return esn_launch_status();
 }
 
@@ -187,7 +202,7 @@ int esn_dmma_harvest_launch(const esn_simt::RecParams &p, cudaStream_t st) {
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     }
     int bt = mode > 0 ? mode : ((p.B + 31) / 32 >= sms ? 32 : (p.B + 15) / 16 >= sms ? 16 : 8);
-    if (bt == 32) return dh_launch<4>(p, st);
-    if (bt == 16) return dh_launch<2>(p, st);
-    return dh_launch<1>(p, st);
+    if (bt == 32) return dh_launch<4, 2>(p, st);
+    if (bt == 16) return dh_launch<2, 4>(p, st);
+    return dh_launch<1, 4>(p, st);
 }

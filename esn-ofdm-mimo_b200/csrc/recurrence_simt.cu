@@ -67,10 +67,10 @@ extern "C" int esn_recurrence_run(const esn_recurrence_args *a, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int limit = small_batch_setting() >= 0 ? small_batch_setting() : esn_cluster_auto_limit(p, a->dtype);
     // the automatic limit is the crossover against the streaming SIMT kernel; fp64 harvests of up to 512 neurons
-    // continue on the fp64 tensor cores instead, which take half as long (profiles/r2_fp64_harvest.txt)
+    // continue on the fp64 tensor cores instead, which take 0.28 of that time (profiles/r2_fp64_harvest.txt)
     if (small_batch_setting() < 0 && a->mode == ESN_MODE_HARVEST && a->dtype == ESN_F64 && a->N_pad <= 512 &&
         esn_dmma_harvest_enabled())
-        limit = limit * 11 / 20;
+        limit = limit / 3;
     if (a->B <= limit) {
         const int rc = esn_cluster_launch(p, a->dtype, st);
         if (rc != ESN_E_UNSUPPORTED && rc != ESN_E_TOOLARGE) return rc;
