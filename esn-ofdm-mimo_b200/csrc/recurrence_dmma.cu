@@ -26,7 +26,10 @@ __device__ __forceinline__ void dh_dmma(double (&c)[2], double a, double b) {
                  : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-template <int FB, int NSTG>                        // 8-frame blocks per CTA (tiles of 8, 16 or 32 frames), weight-ring stages
+// FB = 8-frame blocks per CTA (tiles of 8, 16 or 32 frames), NSTG = weight-ring stages, PREDICT = free-running mode
+// (ESN.predict, libs/pyESN.py:243-253: the readout y_n = W_out[g(b)] [x_n; u_n] is fed back and emitted; tiles of 8 or
+// 16 frames: one warp (or two) per frame in the readout).
+template <int FB, int NSTG, bool PREDICT>
 __global__ void __launch_bounds__(DH_THREADS, 1)
 esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
     constexpr int DH_BT = 8 * FB;
@@ -47,13 +50,22 @@ esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
     double *xs = dh_xs;
     const bool use_noise = p.noise_amp != 0.0;
     const double namp = p.noise_amp;
-    const int noise_rows = p.T - 1;
+    const int noise_rows = PREDICT ? p.T : p.T - 1;
+    const int s0 = PREDICT ? 0 : 1;
+    const double *gW_out = static_cast<const double *>(p.W_out);
+    double *yout = static_cast<double *>(p.y_out);
+    __shared__ int s_group[DH_BT];
 
     for (int i = tid; i < DH_BT * RS; i += DH_THREADS) xs[i] = 0.0;
-    // E row 0 = [0, u_0]
-    for (int i = tid; i < DH_BT * N; i += DH_THREADS) {
-        const int f = i / N, k = i - f * N, b = tile0 + f;
-        if (b < p.B) ext[((size_t)b * p.T) * P + k] = 0.0;
+    if (!PREDICT) {
+        // E row 0 = [0, u_0]
+        for (int i = tid; i < DH_BT * N; i += DH_THREADS) {
+            const int f = i / N, k = i - f * N, b = tile0 + f;
+            if (b < p.B) ext[((size_t)b * p.T) * P + k] = 0.0;
+        }
+    } else if (tid < DH_BT) {
+        const int b = tile0 + tid;                          // clamped: a bad id must not read outside W_out
+        s_group[tid] = (p.group_ids && b < p.B) ? min(max(p.group_ids[b], 0), p.n_groups - 1) : 0;
     }
     __syncthreads();
     // scaled inputs of time step `row` -> E (and the u columns of xs); scaled teacher of `row` -> the d columns
@@ -63,7 +75,7 @@ esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
         double v = 0.0;                                                                                           \
         if (b < p.B && (row) < p.T) {                                                                             \
             v = gin[((size_t)b * p.T + (row)) * n_in + j] * in_scale[j] + in_shift[j];                            \
-            ext[((size_t)b * p.T + (row)) * P + N + j] = v;                                                       \
+            if (ext) ext[((size_t)b * p.T + (row)) * P + N + j] = v;                                              \
         }                                                                                                         \
         if (to_smem) xs[f * RS + N + j] = v;                                                                      \
     }
@@ -75,9 +87,27 @@ esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
             v = teacher[((size_t)b * p.T + (row)) * n_out + o] * t_scale[o] + t_shift[o];                         \
         xs[f * RS + P + o] = v;                                                                                   \
     }
-    DH_STAGE_INPUTS(0, false)
-    DH_STAGE_INPUTS(1, true)
-    DH_STAGE_TEACHER(0)
+    if (!PREDICT) {
+        DH_STAGE_INPUTS(0, false)
+        DH_STAGE_INPUTS(1, true)
+        DH_STAGE_TEACHER(0)
+    } else {
+        if (p.x0) {                                         // continuation state / last output of the fit
+            const double *x0 = static_cast<const double *>(p.x0);
+            for (int i = tid; i < DH_BT * N; i += DH_THREADS) {
+                const int f = i / N, k = i - f * N, b = tile0 + f;
+                if (b < p.B) xs[f * RS + k] = x0[(size_t)b * N + k];
+            }
+        }
+        if (p.y0 && p.feedback) {
+            const double *y0 = static_cast<const double *>(p.y0);
+            for (int i = tid; i < DH_BT * n_out; i += DH_THREADS) {
+                const int f = i / n_out, o = i - f * n_out, b = tile0 + f;
+                if (b < p.B) xs[f * RS + P + o] = y0[(size_t)b * n_out + o];
+            }
+        }
+        DH_STAGE_INPUTS(0, true)
+    }
     __syncthreads();
 
     // The weight stream: warp w needs Wt_aug[k][32 w .. 32 w + 31] for every k, 256 contiguous bytes per k row.  It
@@ -89,7 +119,7 @@ esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
     double *wst = xs + DH_BT * RS + (size_t)warp * NSTG * KR * WRS;
     const double *wsrc = Wt + n0 + 2 * (lane & 15) + (size_t)(lane >> 4) * NP;   // piece q of a chunk: + 2 q rows
     double *wdst = wst + (lane >> 4) * WRS + 2 * (lane & 15);
-    int left = (p.T - 1) * nch, ic = 0, is = 0;             // chunks still to issue, next chunk of the image, next stage
+    int left = (p.T - s0) * nch, ic = 0, is = 0;             // chunks still to issue, next chunk of the image, next stage
     auto issue = [&]() {                                    // one commit group per call, empty past the end
         if (wact && left > 0) {
             const double *src = wsrc + (size_t)(KR * ic) * NP;
@@ -105,8 +135,8 @@ esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
     for (int i = 0; i < NSTG - 1; ++i) issue();
     int ds = 0;                                             // stage of the chunk in use
     const double *xa = xs + fi * RS + fk;                   // A fragment r of k-step k4: xa[8 r RS + 4 k4]
-    for (int n = 1; n < p.T; ++n) {
-        const int nrow = n - 1;                             // noise row of this step
+    for (int n = s0; n < p.T; ++n) {
+        const int nrow = PREDICT ? n : n - 1;               // noise row of this step
         double acc[FB][4][2];
 #pragma unroll
         for (int r = 0; r < FB; ++r)
@@ -155,7 +185,7 @@ esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
                                     else u = (double)esn_noise_uniform(esn_noise_key(p.seed, (uint32_t)b, (uint32_t)nrow), (uint32_t)(nn + h));
                                     x[h] += namp * (u - 0.5);
                                 }
-                                ext[((size_t)b * p.T + n) * P + nn + h] = x[h];
+                                if (ext) ext[((size_t)b * p.T + n) * P + nn + h] = x[h];
                                 xs[f * RS + nn + h] = x[h];
                             }
                         }
@@ -163,9 +193,70 @@ esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
                 }
             }
         }
-        DH_STAGE_TEACHER(n)
-        DH_STAGE_INPUTS(n + 1, true)
-        __syncthreads();
+        if constexpr (!PREDICT) {
+            DH_STAGE_TEACHER(n)
+            DH_STAGE_INPUTS(n + 1, true)
+            __syncthreads();
+        } else {
+            __syncthreads();                                // x_n is complete in xs
+            // the next input row's global loads are in flight during the readout
+            constexpr int UPT = (DH_BT * ESN_MAX_IN + DH_THREADS - 1) / DH_THREADS;
+            double un[UPT];
+#pragma unroll
+            for (int q = 0; q < UPT; ++q) {
+                const int i = tid + q * DH_THREADS, f = i / n_in, j = i - f * n_in, b = tile0 + f;
+                un[q] = 0.0;
+                if (i < DH_BT * n_in && b < p.B && n + 1 < p.T)
+                    un[q] = gin[((size_t)b * p.T + n + 1) * n_in + j] * in_scale[j] + in_shift[j];
+            }
+            // y_n[f][o] = sum_k W_out[g(f)][o][k] [x_n; u_n][k]: a warp owns a frame (two warps with half of the
+            // outputs each for 8-frame tiles), its lanes stride k -- coalesced readout rows, conflict-free state
+            // reads -- and a butterfly leaves every sum in every lane: no partial sums through shared memory
+            {
+                constexpr int WPF = (DH_THREADS / 32) / DH_BT;      // warps per frame: 1 or 2
+                const int f = warp % DH_BT, oh = warp / DH_BT, b = tile0 + f;
+                const double *wsrc = gW_out + (size_t)s_group[f] * n_out * P;
+                const double *xr = xs + f * RS;
+                double a[ESN_MAX_OUT / WPF];
+#pragma unroll
+                for (int q = 0; q < ESN_MAX_OUT / WPF; ++q) a[q] = 0.0;
+#pragma unroll 6
+                for (int k = lane; k < P; k += 32) {          // (unrolled: the loads of several rounds in flight)
+                    const double xv = xr[k];
+#pragma unroll
+                    for (int q = 0; q < ESN_MAX_OUT / WPF; ++q) {
+                        const int o = q * WPF + oh;
+                        if (o < n_out) a[q] = fma(__ldg(wsrc + (size_t)o * P + k), xv, a[q]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < ESN_MAX_OUT / WPF; ++q) {
+                    if (q * WPF + oh < n_out) {             // (warp-uniform)
+#pragma unroll
+                        for (int sh = 16; sh > 0; sh >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], sh);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < ESN_MAX_OUT / WPF; ++q) {
+                    const int o = q * WPF + oh;
+                    if (o < n_out && lane == (q & 31)) {
+                        xs[f * RS + P + o] = p.feedback ? a[q] : 0.0;       // the d columns are not read by any readout
+                        if (b < p.B && n >= p.transient)
+                            yout[((size_t)b * (p.T - p.transient) + (n - p.transient)) * n_out + o] = (a[q] - t_shift[o]) / t_scale[o];
+                    }
+                }
+            }
+            __syncthreads();                                // nobody reads u_n any more
+#pragma unroll
+            for (int q = 0; q < UPT; ++q) {
+                const int i = tid + q * DH_THREADS, f = i / n_in, j = i - f * n_in, b = tile0 + f;
+                if (i < DH_BT * n_in) {
+                    xs[f * RS + N + j] = un[q];
+                    if (ext && b < p.B && n + 1 < p.T) ext[((size_t)b * p.T + n + 1) * P + N + j] = un[q];
+                }
+            }
+            __syncthreads();
+        }
     }
 #undef DH_STAGE_INPUTS
 #undef DH_STAGE_TEACHER
@@ -173,19 +264,20 @@ esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
 
 }  // namespace
 
-template <int FB, int NSTG>
+template <int FB, int NSTG, bool PREDICT>
 static int dh_launch(const esn_simt::RecParams &p, cudaStream_t st) {
     const int bt = 8 * FB, ctas = (p.B + bt - 1) / bt;
     const size_t smem = ((size_t)bt * (p.K_aug_pad + 4) + (size_t)(DH_THREADS / 32) * NSTG * 8 * 36) * sizeof(double);
     if (smem > 226 * 1024) return ESN_E_UNSUPPORTED;
-    ESN_CUDA_TRY(cudaFuncSetAttribute(esn_harvest_dmma_kernel<FB, NSTG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    esn_harvest_dmma_kernel<FB, NSTG><<<ctas, DH_THREADS, smem, st>>>(p);
+    auto kernel = esn_harvest_dmma_kernel<FB, NSTG, PREDICT>;
+    ESN_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<ctas, DH_THREADS, smem, st>>>(p);
     return esn_launch_status();
 }
 
-// Takes the fp64 harvests of reservoirs up to 512 neurons that the cluster kernel (a few frames) has left:
-// the largest tile of 32 / 16 / 8 frames that still gives every SM a CTA.  ESN_HARVEST_DMMA=0 switches it off (the
-// streaming SIMT kernel as the cross-check), =8 / 16 / 32 pins the tile.
+// Takes the fp64 harvests and predictions of reservoirs up to 512 neurons that the cluster kernel (a few frames) has
+// left: the largest tile of 32 (harvest only) / 16 / 8 frames that still gives every SM a CTA.  ESN_HARVEST_DMMA=0
+// switches it off (the streaming SIMT kernel as the cross-check), =8 / 16 / 32 pins the tile.
 static int dh_mode() {
     static const int mode = [] { const char *e = getenv("ESN_HARVEST_DMMA"); return e ? atoi(e) : -1; }();
     return mode;
@@ -194,7 +286,9 @@ bool esn_dmma_harvest_enabled() { return dh_mode() != 0; }
 
 int esn_dmma_harvest_launch(const esn_simt::RecParams &p, cudaStream_t st) {
     const int mode = dh_mode();
-    if (mode == 0 || p.mode != ESN_MODE_HARVEST || p.N_pad > 512 || !p.ext_out) return ESN_E_UNSUPPORTED;
+    if (mode == 0 || p.N_pad > 512) return ESN_E_UNSUPPORTED;
+    const bool predict = p.mode == ESN_MODE_PREDICT;
+    if (!predict && (p.mode != ESN_MODE_HARVEST || !p.ext_out)) return ESN_E_UNSUPPORTED;
     static int sms = 0;
     if (!sms) {
         int dev = 0;
@@ -202,7 +296,11 @@ int esn_dmma_harvest_launch(const esn_simt::RecParams &p, cudaStream_t st) {
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     }
     int bt = mode > 0 ? mode : ((p.B + 31) / 32 >= sms ? 32 : (p.B + 15) / 16 >= sms ? 16 : 8);
-    if (bt == 32) return dh_launch<4, 2>(p, st);
-    if (bt == 16) return dh_launch<2, 4>(p, st);
-    return dh_launch<1, 4>(p, st);
+    if (predict) {
+        if (bt > 16) bt = 16;
+        return bt == 16 ? dh_launch<2, 4, true>(p, st) : dh_launch<1, 4, true>(p, st);
+    }
+    if (bt == 32) return dh_launch<4, 2, false>(p, st);
+    if (bt == 16) return dh_launch<2, 4, false>(p, st);
+    return dh_launch<1, 4, false>(p, st);
 }

@@ -66,9 +66,9 @@ extern "C" int esn_recurrence_run(const esn_recurrence_args *a, void *stream) {
     p.ext_out = a->ext_out; p.y_out = a->y_out; p.workspace = a->workspace;
     cudaStream_t st = (cudaStream_t)stream;
     int limit = small_batch_setting() >= 0 ? small_batch_setting() : esn_cluster_auto_limit(p, a->dtype);
-    // the automatic limit is the crossover against the streaming SIMT kernel; fp64 harvests of up to 512 neurons
+    // the automatic limit is the crossover against the streaming SIMT kernel; fp64 runs of up to 512 neurons
     // continue on the fp64 tensor cores instead, which take 0.28 of that time (profiles/r2_fp64_harvest.txt)
-    if (small_batch_setting() < 0 && a->mode == ESN_MODE_HARVEST && a->dtype == ESN_F64 && a->N_pad <= 512 &&
+    if (small_batch_setting() < 0 && a->dtype == ESN_F64 && a->N_pad <= 512 &&
         esn_dmma_harvest_enabled())
         limit = limit / 3;
     if (a->B <= limit) {
@@ -76,7 +76,7 @@ extern "C" int esn_recurrence_run(const esn_recurrence_args *a, void *stream) {
         if (rc != ESN_E_UNSUPPORTED && rc != ESN_E_TOOLARGE) return rc;
     }
     if (a->dtype == ESN_F32) return esn_simt_launch_f32(p, st);
-    if (a->mode == ESN_MODE_HARVEST) {               // large fp64 pilot batches: the fp64 tensor cores
+    {                                                // fp64, up to 512 neurons: the fp64 tensor cores
         const int rc = esn_dmma_harvest_launch(p, st);
         if (rc != ESN_E_UNSUPPORTED) return rc;
     }

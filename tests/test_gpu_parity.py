@@ -644,3 +644,31 @@ def test_large_batch_fp64_harvest_on_the_fp64_tensor_cores_matches_oracle(name):
     ext_d = eng.harvest(_cuda(us), _cuda(ys), precision="fp64", seed=11)
     ext_s = eng.harvest(_cuda(us[:40]), _cuda(ys[:40]), precision="fp64", seed=11)
     assert rel_err(ext_d[:40].cpu().numpy(), ext_s.cpu().numpy()) < 1e-11
+
+
+@pytest.mark.parametrize("n_res,n_in,n_out", [(512, 16, 8), (100, 4, 4)])
+def test_large_batch_fp64_predict_on_the_fp64_tensor_cores_matches_oracle(n_res, n_in, n_out):
+    """Free-running fp64 prediction of a GPU-filling batch (16-frame tiles of `esn_harvest_dmma_kernel<.., true>`):
+    states and outputs of sampled frames against the oracle's loop (libs/pyESN.py:226-253) with a readout per
+    frame group, continuation state and last output, host noise; ragged last tile."""
+    from esn_b200 import Reservoir
+    rng = np.random.RandomState(n_res)
+    W, W_in, W_fb = orc.init_weights(rng, n_in, n_out, n_res, 0.9, 0.1)
+    T, B, G = 30, 148 * 16 - 5, 5
+    aff = dict(input_scaling=0.05 * np.ones(n_in), input_shift=0.01 * np.ones(n_in),
+               teacher_scaling=5e-3 * np.ones(n_out), teacher_shift=1e-4 * np.ones(n_out))
+    eng = Reservoir(W, W_in, W_fb, aff["input_scaling"], aff["input_shift"], aff["teacher_scaling"],
+                    aff["teacher_shift"], 0.001, True)
+    us = rng.randn(B, T, n_in)
+    uni = rng.rand(B, T, n_res)
+    W_out = rng.randn(G, n_out, n_res + n_in) * 1e-2
+    gid = rng.randint(0, G, size=B).astype(np.int32)
+    x0, y0 = rng.randn(B, n_res) * 0.1, rng.randn(B, n_out) * 5e-3
+    y, pext = eng.predict(_cuda(us), _cuda(W_out), transient=3, group_ids=_cuda(gid), precision="fp64",
+                          noise_uniforms=_cuda(uni), x0=_cuda(x0), y0=_cuda(y0), return_ext=True)
+    assert y.shape == (B, T - 3, n_out)
+    for b in (0, 15, 16, 1000, B - 1):
+        ref, st = orc.predict(W, W_in, W_fb, W_out[gid[b]], us[b], 3, 0.001, uni[b], x0=x0[b], y0=y0[b],
+                              return_states=True, **aff)
+        assert rel_err(pext[b, :, :n_res].cpu().numpy(), st) < 1e-11, b
+        assert rel_err(y[b].cpu().numpy(), ref) < 1e-9, b
