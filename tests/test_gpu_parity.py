@@ -646,7 +646,7 @@ def test_large_batch_fp64_harvest_on_the_fp64_tensor_cores_matches_oracle(name):
     assert rel_err(ext_d[:40].cpu().numpy(), ext_s.cpu().numpy()) < 1e-11
 
 
-@pytest.mark.parametrize("n_res,n_in,n_out", [(512, 16, 8), (100, 4, 4)])
+@pytest.mark.parametrize("n_res,n_in,n_out", [(512, 16, 8), (100, 4, 4), (72, 64, 16), (300, 2, 1)])
 def test_large_batch_fp64_predict_on_the_fp64_tensor_cores_matches_oracle(n_res, n_in, n_out):
     """Free-running fp64 prediction of a GPU-filling batch (16-frame tiles of `esn_harvest_dmma_kernel<.., true>`):
     states and outputs of sampled frames against the oracle's loop (libs/pyESN.py:226-253) with a readout per
