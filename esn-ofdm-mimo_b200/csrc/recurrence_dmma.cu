@@ -29,7 +29,9 @@ __device__ __forceinline__ void dh_dmma(double (&c)[2], double a, double b) {
 // FB = 8-frame blocks per CTA (tiles of 8, 16 or 32 frames), NSTG = weight-ring stages, PREDICT = free-running mode
 // (ESN.predict, libs/pyESN.py:243-253: the readout y_n = W_out[g(b)] [x_n; u_n] is fed back and emitted; tiles of 8 or
 // 16 frames: one warp (or two) per frame in the readout).
-template <int FB, int NSTG, bool PREDICT>
+// CF = 8-neuron fragments per warp: 16 warps x 8 CF neurons cover the reservoir in one pass (4: up to 512 neurons,
+// 5 / 6 / 8: the 600-neuron demo, 768, 1024), so the state never has to be parked.
+template <int FB, int NSTG, bool PREDICT, int CF>
 __global__ void __launch_bounds__(DH_THREADS, 1)
 esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
     constexpr int DH_BT = 8 * FB;
@@ -38,7 +40,7 @@ esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
     const int RS = Kp + 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fk = lane & 3, fi = lane >> 2;
     const int tile0 = blockIdx.x * DH_BT;
-    const int n0 = warp * 32;
+    const int n0 = warp * 8 * CF;
     const bool wact = n0 < N;
     const double *Wt = static_cast<const double *>(p.Wt_aug);
     const double *gin = static_cast<const double *>(p.in);
@@ -114,18 +116,20 @@ esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
     // copies them itself, 8 k rows (2 KB) per cp.async group, into its own ring of NSTG stages (row stride 36 doubles:
     // conflict-free B fragments) -- full 128-byte lines instead of 32-byte fragment rows, no register staging, and
     // only warp-level synchronisation; the ring runs ahead across time steps (the weights do not change).
-    constexpr int KR = 8, WRS = 36;
+    constexpr int KR = 8, WRS = (8 * CF + 15) / 16 * 16 + 4;  // row stride = 4 mod 16 doubles: conflict-free B fragments
+    constexpr int PPR = 4 * CF;                             // 16-byte pieces per k row of the warp's columns
     const int nch = Kp / KR;                                // K_aug_pad is a multiple of 16
     double *wst = xs + DH_BT * RS + (size_t)warp * NSTG * KR * WRS;
-    const double *wsrc = Wt + n0 + 2 * (lane & 15) + (size_t)(lane >> 4) * NP;   // piece q of a chunk: + 2 q rows
-    double *wdst = wst + (lane >> 4) * WRS + 2 * (lane & 15);
     int left = (p.T - s0) * nch, ic = 0, is = 0;             // chunks still to issue, next chunk of the image, next stage
     auto issue = [&]() {                                    // one commit group per call, empty past the end
         if (wact && left > 0) {
-            const double *src = wsrc + (size_t)(KR * ic) * NP;
-            double *dst = wdst + is * KR * WRS;
+            const double *src = Wt + n0 + (size_t)(KR * ic) * NP;
+            double *dst = wst + is * KR * WRS;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) cp_async16(dst + 2 * q * WRS, src + (size_t)(2 * q) * NP);
+            for (int q = 0; q < CF; ++q) {                  // KR * PPR = 32 CF pieces per chunk
+                const int piece = lane + 32 * q, row = piece / PPR, col = 2 * (piece % PPR);
+                cp_async16(dst + row * WRS + col, src + (size_t)row * NP + col);
+            }
             --left;
             if (++ic == nch) ic = 0;
             if (++is == NSTG) is = 0;
@@ -137,11 +141,11 @@ esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
     const double *xa = xs + fi * RS + fk;                   // A fragment r of k-step k4: xa[8 r RS + 4 k4]
     for (int n = s0; n < p.T; ++n) {
         const int nrow = PREDICT ? n : n - 1;               // noise row of this step
-        double acc[FB][4][2];
+        double acc[FB][CF][2];
 #pragma unroll
         for (int r = 0; r < FB; ++r)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
+            for (int c = 0; c < CF; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
         if (wact) {
 #pragma unroll 1
             for (int c = 0; c < nch; ++c) {
@@ -152,15 +156,15 @@ esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
                 if (++ds == NSTG) ds = 0;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    double bu[4], a[FB];
+                    double bu[CF], a[FB];
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) bu[cc] = wb[4 * j * WRS + 8 * cc];
+                    for (int cc = 0; cc < CF; ++cc) bu[cc] = wb[4 * j * WRS + 8 * cc];
 #pragma unroll
                     for (int r = 0; r < FB; ++r) a[r] = xa[8 * r * RS + 4 * (2 * c + j)];
 #pragma unroll
                     for (int r = 0; r < FB; ++r)
 #pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) dh_dmma(acc[r][cc], a[r], bu[cc]);
+                        for (int cc = 0; cc < CF; ++cc) dh_dmma(acc[r][cc], a[r], bu[cc]);
                 }
             }
         }
@@ -171,7 +175,7 @@ esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
                 const int f = 8 * r + fi, b = tile0 + f;
                 if (b < p.B) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < CF; ++c) {
                         const int nn = n0 + 8 * c + 2 * fk;
                         double x[2];
 #pragma unroll
@@ -264,18 +268,31 @@ esn_harvest_dmma_kernel(const esn_simt::RecParams p) {
 
 }  // namespace
 
-template <int FB, int NSTG, bool PREDICT>
+template <int FB, int NSTG, bool PREDICT, int CF>
 static int dh_launch(const esn_simt::RecParams &p, cudaStream_t st) {
     const int bt = 8 * FB, ctas = (p.B + bt - 1) / bt;
-    const size_t smem = ((size_t)bt * (p.K_aug_pad + 4) + (size_t)(DH_THREADS / 32) * NSTG * 8 * 36) * sizeof(double);
+    constexpr int WRS = (8 * CF + 15) / 16 * 16 + 4;
+    const size_t smem = ((size_t)bt * (p.K_aug_pad + 4) + (size_t)(DH_THREADS / 32) * NSTG * 8 * WRS) * sizeof(double);
     if (smem > 226 * 1024) return ESN_E_UNSUPPORTED;
-    auto kernel = esn_harvest_dmma_kernel<FB, NSTG, PREDICT>;
+    auto kernel = esn_harvest_dmma_kernel<FB, NSTG, PREDICT, CF>;
     ESN_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kernel<<<ctas, DH_THREADS, smem, st>>>(p);
     return esn_launch_status();
 }
 
-// Takes the fp64 harvests and predictions of reservoirs up to 512 neurons that the cluster kernel (a few frames) has
+// wider reservoirs (640 / 768 / 1024 padded neurons): tiles of 16 or 8 frames, two ring stages
+template <bool PREDICT, int CF>
+static int dh_launch_wide(const esn_simt::RecParams &p, int bt, cudaStream_t st) {
+    if constexpr (CF <= 6) {
+        if (bt >= 16) {
+            const int rc = dh_launch<2, 2, PREDICT, CF>(p, st);
+            if (rc != ESN_E_UNSUPPORTED) return rc;
+        }
+    }
+    return dh_launch<1, 2, PREDICT, CF>(p, st);
+}
+
+// Takes the fp64 harvests and predictions of reservoirs up to 1024 neurons that the cluster kernel (a few frames) has
 // left: the largest tile of 32 (harvest only) / 16 / 8 frames that still gives every SM a CTA.  ESN_HARVEST_DMMA=0
 // switches it off (the streaming SIMT kernel as the cross-check), =8 / 16 / 32 pins the tile.
 static int dh_mode() {
@@ -286,7 +303,7 @@ bool esn_dmma_harvest_enabled() { return dh_mode() != 0; }
 
 int esn_dmma_harvest_launch(const esn_simt::RecParams &p, cudaStream_t st) {
     const int mode = dh_mode();
-    if (mode == 0 || p.N_pad > 512) return ESN_E_UNSUPPORTED;
+    if (mode == 0 || p.N_pad > 1024) return ESN_E_UNSUPPORTED;
     const bool predict = p.mode == ESN_MODE_PREDICT;
     if (!predict && (p.mode != ESN_MODE_HARVEST || !p.ext_out)) return ESN_E_UNSUPPORTED;
     static int sms = 0;
@@ -296,11 +313,17 @@ int esn_dmma_harvest_launch(const esn_simt::RecParams &p, cudaStream_t st) {
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     }
     int bt = mode > 0 ? mode : ((p.B + 31) / 32 >= sms ? 32 : (p.B + 15) / 16 >= sms ? 16 : 8);
+    if (p.N_pad > 512) {
+        const int cf = p.N_pad / 128;                       // 5 .. 8
+        if (cf == 5) return predict ? dh_launch_wide<true, 5>(p, bt, st) : dh_launch_wide<false, 5>(p, bt, st);
+        if (cf == 6) return predict ? dh_launch_wide<true, 6>(p, bt, st) : dh_launch_wide<false, 6>(p, bt, st);
+        return predict ? dh_launch_wide<true, 8>(p, bt, st) : dh_launch_wide<false, 8>(p, bt, st);   // 896 and 1024
+    }
     if (predict) {
         if (bt > 16) bt = 16;
-        return bt == 16 ? dh_launch<2, 4, true>(p, st) : dh_launch<1, 4, true>(p, st);
+        return bt == 16 ? dh_launch<2, 4, true, 4>(p, st) : dh_launch<1, 4, true, 4>(p, st);
     }
-    if (bt == 32) return dh_launch<4, 2, false>(p, st);
-    if (bt == 16) return dh_launch<2, 4, false>(p, st);
-    return dh_launch<1, 4, false>(p, st);
+    if (bt == 32) return dh_launch<4, 2, false, 4>(p, st);
+    if (bt == 16) return dh_launch<2, 4, false, 4>(p, st);
+    return dh_launch<1, 4, false, 4>(p, st);
 }

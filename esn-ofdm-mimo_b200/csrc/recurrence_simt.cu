@@ -76,7 +76,7 @@ extern "C" int esn_recurrence_run(const esn_recurrence_args *a, void *stream) {
         if (rc != ESN_E_UNSUPPORTED && rc != ESN_E_TOOLARGE) return rc;
     }
     if (a->dtype == ESN_F32) return esn_simt_launch_f32(p, st);
-    {                                                // fp64, up to 512 neurons: the fp64 tensor cores
+    {                                                // fp64, up to 1024 neurons: the fp64 tensor cores
         const int rc = esn_dmma_harvest_launch(p, st);
         if (rc != ESN_E_UNSUPPORTED) return rc;
     }

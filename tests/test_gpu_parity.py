@@ -672,3 +672,34 @@ def test_large_batch_fp64_predict_on_the_fp64_tensor_cores_matches_oracle(n_res,
                               return_states=True, **aff)
         assert rel_err(pext[b, :, :n_res].cpu().numpy(), st) < 1e-11, b
         assert rel_err(y[b].cpu().numpy(), ref) < 1e-9, b
+
+
+@pytest.mark.parametrize("n_res,B", [(600, 148 * 16 - 3), (1000, 1190), (700, 300)])
+def test_wide_reservoirs_fp64_on_the_fp64_tensor_cores_match_oracle(n_res, B):
+    """513..1024 neurons in fp64 (the 4x8 fast demo's 600, Demo_MIMO_4x8_ChannelRank_TrainSNR_LDPC_fast.py:142): 16 warps
+    of 40 / 48 / 64 neurons cover the reservoir in one pass of `esn_harvest_dmma_kernel`; harvest and free-running
+    prediction of sampled frames against the oracle's loops."""
+    from esn_b200 import Reservoir
+    n_in, n_out, T = 16, 8, 24
+    rng = np.random.RandomState(n_res)
+    W, W_in, W_fb = orc.init_weights(rng, n_in, n_out, n_res, 0.9, 0.1)
+    aff = dict(input_scaling=0.05 * np.ones(n_in), input_shift=0.01 * np.ones(n_in),
+               teacher_scaling=5e-3 * np.ones(n_out), teacher_shift=1e-4 * np.ones(n_out))
+    eng = Reservoir(W, W_in, W_fb, aff["input_scaling"], aff["input_shift"], aff["teacher_scaling"],
+                    aff["teacher_shift"], 0.001, True)
+    us, ys = rng.randn(B, T, n_in), rng.randn(B, T, n_out)
+    uni_h, uni_p = rng.rand(B, T - 1, n_res), rng.rand(B, T, n_res)
+    W_out = rng.randn(3, n_out, n_res + n_in) * 1e-2
+    gid = rng.randint(0, 3, size=B).astype(np.int32)
+    x0, y0 = rng.randn(B, n_res) * 0.1, rng.randn(B, n_out) * 5e-3
+    ext = eng.harvest(_cuda(us), _cuda(ys), precision="fp64", noise_uniforms=_cuda(uni_h))
+    y, pext = eng.predict(_cuda(us), _cuda(W_out), transient=2, group_ids=_cuda(gid), precision="fp64",
+                          noise_uniforms=_cuda(uni_p), x0=_cuda(x0), y0=_cuda(y0), return_ext=True)
+    for b in (0, 7, 8, 17, B - 1):
+        r = orc.fit(W, W_in, W_fb, us[b], ys[b], 0, 0.001, uni_h[b], teacher_forcing=True, **aff)
+        assert rel_err(ext[b, :, :n_res].cpu().numpy(), r["states"]) < 1e-11, b
+        assert rel_err(ext[b, :, n_res:].cpu().numpy(), r["in_s"]) < 1e-15, b
+        ref, st = orc.predict(W, W_in, W_fb, W_out[gid[b]], us[b], 2, 0.001, uni_p[b], x0=x0[b], y0=y0[b],
+                              return_states=True, **aff)
+        assert rel_err(pext[b, :, :n_res].cpu().numpy(), st) < 1e-11, b
+        assert rel_err(y[b].cpu().numpy(), ref) < 1e-9, b
