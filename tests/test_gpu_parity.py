@@ -646,8 +646,9 @@ def test_large_batch_fp64_harvest_on_the_fp64_tensor_cores_matches_oracle(name):
     assert rel_err(ext_d[:40].cpu().numpy(), ext_s.cpu().numpy()) < 1e-11
 
 
-@pytest.mark.parametrize("n_res,n_in,n_out", [(512, 16, 8), (100, 4, 4), (72, 64, 16), (300, 2, 1)])
-def test_large_batch_fp64_predict_on_the_fp64_tensor_cores_matches_oracle(n_res, n_in, n_out):
+@pytest.mark.parametrize("n_res,n_in,n_out,per_group", [(512, 16, 8, 0), (512, 16, 8, 64), (100, 4, 4, 0),
+                                                         (100, 4, 4, 128), (72, 64, 16, 0), (300, 2, 1, 48)])
+def test_large_batch_fp64_predict_on_the_fp64_tensor_cores_matches_oracle(n_res, n_in, n_out, per_group):
     """Free-running fp64 prediction of a GPU-filling batch (16-frame tiles of `esn_harvest_dmma_kernel<.., true>`):
     states and outputs of sampled frames against the oracle's loop (libs/pyESN.py:226-253) with a readout per
     frame group, continuation state and last output, host noise; ragged last tile."""
@@ -663,6 +664,8 @@ def test_large_batch_fp64_predict_on_the_fp64_tensor_cores_matches_oracle(n_res,
     uni = rng.rand(B, T, n_res)
     W_out = rng.randn(G, n_out, n_res + n_in) * 1e-2
     gid = rng.randint(0, G, size=B).astype(np.int32)
+    if per_group:                                           # runs of frames per readout: tiles with one readout stage it in shared memory
+        gid = ((np.arange(B) // per_group) % G).astype(np.int32)
     x0, y0 = rng.randn(B, n_res) * 0.1, rng.randn(B, n_out) * 5e-3
     y, pext = eng.predict(_cuda(us), _cuda(W_out), transient=3, group_ids=_cuda(gid), precision="fp64",
                           noise_uniforms=_cuda(uni), x0=_cuda(x0), y0=_cuda(y0), return_ext=True)
