@@ -770,21 +770,21 @@ def run_gpu(args):
         reps = -(-Gs // G)
         su_ = pil_u.to(torch.float32).repeat(reps, 1, 1)[:Gs].contiguous()
         sy_ = pil_y.to(torch.float32).repeat(reps, 1, 1)[:Gs].contiguous()
-        res.train_shared_readout(su_, sy_, TRANSIENT, precision="tc", chunks=4, seed=5, su_exp=su_in, y_absmax=y_absmax)
+        res.train_shared_readout(su_, sy_, TRANSIENT, precision="tc", chunks=2, seed=5, su_exp=su_in, y_absmax=y_absmax)
         torch.cuda.synchronize()
         D.barrier()
         bests = None
         for rep in range(3):
             s0, s1 = ev(), ev()
             s0.record(stream)
-            w_sh, info_sh, nbytes = res.train_shared_readout(su_, sy_, TRANSIENT, precision="tc", chunks=4, seed=6 + rep, su_exp=su_in, y_absmax=y_absmax)
+            w_sh, info_sh, nbytes = res.train_shared_readout(su_, sy_, TRANSIENT, precision="tc", chunks=2, seed=6 + rep, su_exp=su_in, y_absmax=y_absmax)
             s1.record(stream)
             torch.cuda.synchronize()
             t = D.max_over_ranks(s0.elapsed_time(s1), dev)
             bests = t if bests is None else min(bests, t)
             assert int(info_sh.abs().max()) == 0
         shared = {"pilots_per_gpu": Gs, "pilots_total": world * Gs, "ms": bests, "pilots_per_s": world * Gs / (bests * 1e-3),
-                  "allreduce_bytes_per_fit": int(nbytes), "chunks": 4,
+                  "allreduce_bytes_per_fit": int(nbytes), "chunks": 2,
                   "what": "one W_out from all ranks' pilots: tensor-core harvest -> primal Gram 528 x 528 (DMMA, summed over "
                           "the chunk's pilots) -> async NCCL all-reduce per chunk behind the next chunk's harvest -> Cholesky"}
         del su_, sy_, w_sh
