@@ -1,10 +1,12 @@
-// Teacher-forced harvest in fp64 on the fp64 tensor cores (mma.sync.m8n8k4.f64, DMMA), sm_100a.
+// Reservoir recurrence in fp64 on the fp64 tensor cores (mma.sync.m8n8k4.f64, DMMA), sm_100a.
 //
-// The parity-grade half of ESN.fit (reference libs/pyESN.py:179-182: states[n] = tanh(W states[n-1] +
-// W_in u[n] + W_fb d[n-1]) + noise (rand - 0.5)) for reservoirs up to 512 neurons: the streaming SIMT kernel
-// (recurrence_simt.cuh) issues one DFMA per MAC with two shared-memory operands per 4 x 8 register tile and sits
-// at 0.39 of the fp64 rate; here a CTA steps a tile of 32 (16, 8) frames with the MACs on the DMMA pipe
-// (4736 pilots of cfg3: 94 -> 47 ms, 0.78 of the fp64 rate; profiles/probes/fp64_harvest_paths.py).
+// The reference's own arithmetic class for whole batches: the teacher-forced harvest of ESN.fit (reference
+// libs/pyESN.py:179-182: states[n] = tanh(W states[n-1] + W_in u[n] + W_fb d[n-1]) + noise (rand - 0.5)) -- the
+// parity-grade half of readout training -- and the free-running loop of ESN.predict (:243-253), for reservoirs up to
+// 1024 neurons.  The streaming SIMT kernel (recurrence_simt.cuh) issues one DFMA per MAC with two shared-memory
+// operands per 4 x 8 register tile and sits at 0.39 of the fp64 rate; here a CTA steps a tile of 32 (16, 8) frames
+// with the MACs on the DMMA pipe (4736 pilots of cfg3: 94 -> 47 ms, 0.78 of the fp64 rate; 9472 frames predicted:
+// 215 -> 117 ms; profiles/r2_fp64_harvest.txt, r2_fp64_predict.txt).
 //
 // Layout.  One CTA = 8 FB frames (FB = 4, 2, 1), 16 warps.  The augmented state [x | u | d | 0] of the tile lives in
 // shared memory as xs[frame][k] (row stride K_aug_pad + 4 doubles: the 8 x 4 A fragments of a half-warp fall into
@@ -299,9 +301,9 @@ static int dh_mode() {
     static const int mode = [] { const char *e = getenv("ESN_HARVEST_DMMA"); return e ? atoi(e) : -1; }();
     return mode;
 }
-bool esn_dmma_harvest_enabled() { return dh_mode() != 0; }
+bool esn_dmma_enabled() { return dh_mode() != 0; }
 
-int esn_dmma_harvest_launch(const esn_simt::RecParams &p, cudaStream_t st) {
+int esn_dmma_launch(const esn_simt::RecParams &p, cudaStream_t st) {
     const int mode = dh_mode();
     if (mode == 0 || p.N_pad > 1024) return ESN_E_UNSUPPORTED;
     const bool predict = p.mode == ESN_MODE_PREDICT;

@@ -7,8 +7,8 @@ int esn_simt_launch_f64(const esn_simt::RecParams &p, cudaStream_t st);
 int esn_cluster_launch(const esn_simt::RecParams &p, int dtype, cudaStream_t st);   // recurrence_cluster.cu
 
 int esn_cluster_auto_limit(const esn_simt::RecParams &p, int dtype);                  // recurrence_cluster.cu
-int esn_dmma_harvest_launch(const esn_simt::RecParams &p, cudaStream_t st);           // recurrence_dmma.cu
-bool esn_dmma_harvest_enabled();
+int esn_dmma_launch(const esn_simt::RecParams &p, cudaStream_t st);           // recurrence_dmma.cu
+bool esn_dmma_enabled();
 
 // Batches of at most this many frames take the cluster kernel (weights resident in the shared memory of a
 // thread-block cluster, ~3 us per time step) instead of the streaming SIMT kernel (~90 us per step while its
@@ -69,7 +69,7 @@ extern "C" int esn_recurrence_run(const esn_recurrence_args *a, void *stream) {
     // the automatic limit is the crossover against the streaming SIMT kernel; fp64 runs of up to 512 neurons
     // continue on the fp64 tensor cores instead, which take 0.28 of that time (profiles/r2_fp64_harvest.txt)
     if (small_batch_setting() < 0 && a->dtype == ESN_F64 && a->N_pad <= 512 &&
-        esn_dmma_harvest_enabled())
+        esn_dmma_enabled())
         limit = limit / 3;
     if (a->B <= limit) {
         const int rc = esn_cluster_launch(p, a->dtype, st);
@@ -77,7 +77,7 @@ extern "C" int esn_recurrence_run(const esn_recurrence_args *a, void *stream) {
     }
     if (a->dtype == ESN_F32) return esn_simt_launch_f32(p, st);
     {                                                // fp64, up to 1024 neurons: the fp64 tensor cores
-        const int rc = esn_dmma_harvest_launch(p, st);
+        const int rc = esn_dmma_launch(p, st);
         if (rc != ESN_E_UNSUPPORTED) return rc;
     }
     return esn_simt_launch_f64(p, st);
