@@ -226,7 +226,7 @@ def detect_blocks(res, pil_idx, data_idx, block_of_frame, taps, ebno_db, N, qam_
 
 def ber_curve(res_factory, N_t, N_r, N, qam_bits, ebno_db_list, n_blocks, frames_per_block, isi=8, No=1e-5, seed=0,
               fit_precision="fp64", detect_precision="tc", device=None, channel="rayleigh", fs_hz=2 * 1.024e6,
-              ds_ns=300.0, shard=True, max_blocks_per_launch=592, train_fixed_ebno_db=None):
+              ds_ns=300.0, shard=True, max_blocks_per_launch=None, train_fixed_ebno_db=None):
     """BER-vs-SNR Monte-Carlo: for every Eb/N0, `n_blocks` coherence blocks of `frames_per_block` data
     symbols (blocks sharded over ranks, counters summed over ranks).  `res_factory(var_x)` returns the
     Reservoir for an SNR point (the template scales the inputs by 0.005 / sqrt(var_x)).  Returns
@@ -235,11 +235,14 @@ def ber_curve(res_factory, N_t, N_r, N, qam_bits, ebno_db_list, n_blocks, frames
     shard=False: this rank runs all blocks by itself and no collective is issued (hyper-parameter sweeps
     place whole configurations on ranks instead, examples/esn_sweep.py); the counters are returned under
     '_counts' ([n_snr, n_detectors, 2] int64) for the caller to gather.
-    A rank's blocks are processed `max_blocks_per_launch` at a time (592 blocks x 128 frames = 10 GB of
+    A rank's blocks are processed `max_blocks_per_launch` at a time (default: ~75 K frames per launch, i.e. 592
+    blocks x 128 frames or 4209 blocks x 18 frames, between 148 and 4736 blocks = 10 GB of
     frames and intermediates; the pilots of a launch are one fit batch -- 148 per launch left the fp64 harvest,
     Gram and Cholesky at a quarter of a wave: 475 K frames/s against 660 K), so a point of BASELINE.json configs[4] -- 10^6 frames per Eb/N0 -- runs in
     bounded memory; the counters accumulate on the device."""
     device = device or torch.device("cuda", torch.cuda.current_device())
+    if not max_blocks_per_launch:
+        max_blocks_per_launch = min(4736, max(148, 75776 // max(1, int(frames_per_block))))
     rank, world = (D.rank(), D.world()) if shard else (0, 1)
     g0, g1 = D.shard_range(n_blocks, rank, world)
     G = g1 - g0

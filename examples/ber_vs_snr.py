@@ -37,8 +37,8 @@ def main():
                     help="also train the template's second ESN on the pilot re-sent at this Eb/N0 (12 dB in the demos)")
     ap.add_argument("--channel", default="rayleigh", choices=["rayleigh", "tdlb"],
                     help="rayleigh: exponential 8-tap profile of the NBF template; tdlb: TDL-B taps of the CDL demo")
-    ap.add_argument("--blocks-per-launch", type=int, default=592,
-                    help="coherence blocks processed together (memory bound: ~17 MB per block of 128 frames at 4x8, N = 512); "
+    ap.add_argument("--blocks-per-launch", type=int, default=0,
+                    help="coherence blocks processed together (0 = about 75 K frames per launch; memory bound: ~17 MB per block of 128 frames at 4x8, N = 512); "
                          "with --fit-precision tc the pilot harvest costs the same 10 ms for up to 9472 blocks")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--out", default="results_ber_run")
