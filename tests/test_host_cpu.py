@@ -104,21 +104,17 @@ def test_dropin_constructor_semantics(golden):
 def test_spectral_radius_is_remembered_per_matrix_and_bit_identical():
     """Rebuilding an ESN from the same seed must give the same weights bit for bit as `eigvals` on every construction
     (reference libs/pyESN.py:99) -- the remembered radius only skips the repeated LAPACK call."""
-    import time
     import pyESN
     pyESN._RADIUS_CACHE.clear()
     kw = dict(n_inputs=4, n_outputs=4, n_reservoir=300, spectral_radius=0.9, sparsity=0.1, random_state=42)
-    t0 = time.perf_counter()
     a = pyESN.ESN(**kw)
-    t1 = time.perf_counter()
     b = pyESN.ESN(**kw)
-    t2 = time.perf_counter()
     rs = np.random.RandomState(42)
     W = rs.rand(300, 300) - 0.5
     W[rs.rand(300, 300) < 0.1] = 0
     W *= 0.9 / np.max(np.abs(np.linalg.eigvals(W)))
     assert np.array_equal(a.W, W) and np.array_equal(b.W, W)
-    assert len(pyESN._RADIUS_CACHE) == 1 and (t2 - t1) < (t1 - t0)
+    assert len(pyESN._RADIUS_CACHE) == 1
     c = pyESN.ESN(**dict(kw, spectral_radius=0.7))              # same draw, another radius: still one LAPACK call
     assert len(pyESN._RADIUS_CACHE) == 1 and np.allclose(c.W, W * (0.7 / 0.9), rtol=1e-15, atol=0)
     pyESN.ESN(**dict(kw, random_state=43))
