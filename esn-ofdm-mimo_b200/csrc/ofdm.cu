@@ -302,7 +302,8 @@ rx_fft_frame_kernel(const T *__restrict__ y_cp, int N, int cp, int N_r, T *__res
 // the twiddles from a 512-entry table: ~1.8x fewer instructions per transform.  `nb` transforms side by side;
 // input in `a` (index stream * F512_STR + f512_skew(t)), scratch `b`; the result is in `b`.
 template <typename T> struct Cx { T re, im; };
-constexpr int F512_STR = 512 + 64 + 8;                 // skewed length of one stream
+constexpr int F512_STR = 512 + 64 + 9;                 // skewed length of one stream; = 9 mod 16, so that the streams of one
+                                                       // sample (the frame's load and output order) fall into different banks
 __device__ __forceinline__ int f512_skew(int i) { return i + (i >> 3); }
 
 template <typename T>
@@ -321,7 +322,7 @@ __device__ __forceinline__ void f512_dft8(Cx<T> (&v)[8]) {
     // v now holds X[0], X[4], X[2], X[6], X[1], X[5], X[3], X[7]
 }
 
-// tw[k] = exp(-2 pi i k / 512) as tw[16 a + b] = exp(-2 pi i 16 a / 512) exp(-2 pi i b / 512): 48 sincospi per CTA
+// W^k = exp(-2 pi i k / 512) as exp(-2 pi i 16 a / 512) exp(-2 pi i b / 512), k = 16 a + b: 48 sincospi per CTA
 // instead of 512 (ends with a __syncthreads())
 template <typename T>
 __device__ void fft512_make_table(Cx<T> *tw) {
@@ -333,10 +334,15 @@ __device__ void fft512_make_table(Cx<T> *tw) {
         base[threadIdx.x].re = cs; base[threadIdx.x].im = sn;
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < 512; k += blockDim.x) {
+    // laid out as the stages read it: entry (r - 1) * 8 + k = W^(8 k r) for the second stage (k = j & 7), entry
+    // 56 + (r - 1) * 64 + j = W^(j r) for the third -- the lanes of a warp read consecutive entries (a table indexed
+    // by the exponent put W^(8 k r), r even, of all eight k into one or two banks: l1tex 95 % busy, 37 M bank
+    // conflicts per launch in profiles/r2_ncu_chain_kernels.txt)
+    for (int e = threadIdx.x; e < 504; e += blockDim.x) {
+        const int k = e < 56 ? 8 * (e & 7) * ((e >> 3) + 1) : ((e - 56) & 63) * (((e - 56) >> 6) + 1);
         const Cx<T> a = base[k >> 4], b = base[32 + (k & 15)];
-        tw[k].re = a.re * b.re - a.im * b.im;
-        tw[k].im = a.re * b.im + a.im * b.re;
+        tw[e].re = a.re * b.re - a.im * b.im;
+        tw[e].im = a.re * b.im + a.im * b.re;
     }
     __syncthreads();
 }
@@ -354,7 +360,7 @@ __device__ __forceinline__ void fft512_stage(const Cx<T> *in, Cx<T> *out, const 
         if (LOG_NS > 0) {
 #pragma unroll
             for (int r = 1; r < 8; ++r) {
-                const Cx<T> w = tw[k * r * (64 >> LOG_NS)];
+                const Cx<T> w = LOG_NS == 3 ? tw[(r - 1) * 8 + k] : tw[56 + (r - 1) * 64 + k];
                 const T xr = v[r].re, xi = v[r].im;
                 v[r].re = xr * w.re - xi * w.im;
                 v[r].im = xr * w.im + xi * w.re;
