@@ -1106,10 +1106,17 @@ synth_frames_frame_kernel(const uint8_t *__restrict__ tx_idx, const T *__restric
     const int tot = N * N_t, tots = tot + (tot >> 5) + 1, ntap_all = N_r * N_t * ntaps;
     T *re = reinterpret_cast<T *>(sm), *im = re + tots, *twr = im + tots, *twi = twr + N / 2;
     T *xr = twi + N / 2, *xi = xr + (size_t)N_t * L;          // clipped Tx samples [N_t][L]
-    T *tr = xi + (size_t)N_t * L, *ti = tr + ntap_all;         // channel taps [N_r][N_t][ntaps]
+    // channel taps [N_r][N_t][tstr]: an odd row length, so that the rows of the N_r antennas a warp reads in the FIR fall
+    // into different banks (rows of 8 taps x 4 Tx put all of them into one: 8-way conflicts on every tap load, 71 % of the
+    // kernel's shared-memory wavefronts in profiles/r2_ncu_chain_kernels.txt)
+    const int tstr = ntaps | 1;
+    T *tr = xi + (size_t)N_t * L, *ti = tr + N_r * N_t * tstr;
     fft_make_twiddles(twr, twi, N);
     const T *cb = taps + (size_t)(chan_index ? chan_index[b] : b) * ntap_all * 2;
-    for (int e = threadIdx.x; e < ntap_all; e += blockDim.x) { tr[e] = cb[2 * e]; ti[e] = cb[2 * e + 1]; }
+    for (int e = threadIdx.x; e < ntap_all; e += blockDim.x) {
+        const int o = (e / ntaps) * tstr + e % ntaps;
+        tr[o] = cb[2 * e]; ti[o] = cb[2 * e + 1];
+    }
     const int side = 1 << (qam_bits / 2);
     const T cs = (T)1 / sqrt_t((T)(2.0 * (side * side - 1) / 3.0));
     const T sp = sqrt_t(Pi[b]), A = A_clip[b];
@@ -1143,7 +1150,7 @@ synth_frames_frame_kernel(const uint8_t *__restrict__ tx_idx, const T *__restric
 #pragma unroll
         for (int j = 0; j < TB; ++j) { yr[j] = 0; yi[j] = 0; }
         for (int tx = 0; tx < N_t; ++tx) {
-            const T *c_r = tr + (rx * N_t + tx) * ntaps, *c_i = ti + (rx * N_t + tx) * ntaps;
+            const T *c_r = tr + (rx * N_t + tx) * tstr, *c_i = ti + (rx * N_t + tx) * tstr;
             const T *x_r = xr + tx * L, *x_i = xi + tx * L;
             if (ntaps <= 8) {
                 // sliding window in registers: the TB + 7 samples the block needs are loaded once per Tx stream
@@ -1632,7 +1639,7 @@ extern "C" int ofdm_synth_frames(int dtype, const uint8_t *tx_idx, const void *t
     cudaStream_t st = (cudaStream_t)stream;
     // whole-frame kernel when the N_t streams, the clipped samples and the taps fit in shared memory together
     const size_t tot = (size_t)N * N_t;
-    const size_t el_frame = 2 * (tot + tot / 32 + 1) + N + 2 * (size_t)N_t * (N + cp) + 2 * (size_t)N_r * N_t * ntaps;
+    const size_t el_frame = 2 * (tot + tot / 32 + 1) + N + 2 * (size_t)N_t * (N + cp) + 2 * (size_t)N_r * N_t * (ntaps | 1);
     const size_t esz = dtype == ESN_F64 ? sizeof(double) : sizeof(float);
     if (el_frame * esz <= 160 * 1024 && (dtype == ESN_F32 || dtype == ESN_F64)) {
         if (dtype == ESN_F32) {
