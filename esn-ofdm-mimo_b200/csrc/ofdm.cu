@@ -302,9 +302,13 @@ rx_fft_frame_kernel(const T *__restrict__ y_cp, int N, int cp, int N_r, T *__res
 // the twiddles from a 512-entry table: ~1.8x fewer instructions per transform.  `nb` transforms side by side;
 // input in `a` (index stream * F512_STR + f512_skew(t)), scratch `b`; the result is in `b`.
 template <typename T> struct Cx { T re, im; };
-constexpr int F512_STR = 512 + 64 + 9;                 // skewed length of one stream; = 9 mod 16, so that the streams of one
+constexpr int F512_STR = 512 + 32 + 9;                 // skewed length of one stream; = 9 mod 16, so that the streams of one
                                                        // sample (the frame's load and output order) fall into different banks
-__device__ __forceinline__ int f512_skew(int i) { return i + (i >> 3); }
+// one pad slot per 16 elements (8-byte elements, 16 bank pairs): aligned runs of 16 consecutive elements -- every stage's
+// reads and the last stage's writes -- stay conflict-free, as do the stride-8 writes of the first stage; only the
+// second stage's writes (two runs of 8 elements 64 apart) are 2-way.  (A slot per 8 elements made every consecutive
+// access 2-way: a run of 16 then spans 17-18 slots.)
+__device__ __forceinline__ int f512_skew(int i) { return i + (i >> 4); }
 
 template <typename T>
 __device__ __forceinline__ void f512_dft8(Cx<T> (&v)[8]) {
